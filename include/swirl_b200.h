@@ -1,0 +1,165 @@
+/*
+ * swirl_b200 — C ABI of the B200-native SWIRL prover backend (libswirl_b200.so).
+ *
+ * This is the drop-in boundary: the symbols a Rust `openvm-b200-backend` crate binds with
+ * `extern "C"` to implement the reference's plugin traits
+ *     ProverBackend / ProverDevice = TraceCommitter + MultiRapProver + OpeningProver
+ *     (reference: crates/stark-backend/src/prover/hal.rs:23-138)
+ * in place of crates/cuda-backend/src/cuda/ (one .rs per .cu) (the reference's FFI to its own kernels).
+ * INTEGRATION.md shows the Rust-side binding for every entry point.
+ *
+ * Conventions (same as the reference FFI, crates/cuda-backend/src/cuda/ntt.rs:12-21 and
+ * cuda-common/src/error.rs:53-60):
+ *   - every function returns int: 0 = ok, a cudaError_t value (1..999) for CUDA failures, or a
+ *     SWIRL_ERR_* code (>= 10000); swirl_last_error() has the text for the calling thread;
+ *   - plain pointers and sizes only; no C++ / torch types;
+ *   - field words are BabyBear in Montgomery form (x * 2^32 mod p), exactly the host
+ *     `Vec<BabyBear>` bytes the reference memcpy's (cuda-backend/src/data_transporter.rs:93-106);
+ *     EF = 4 words (basis 1,X,X^2,X^3), digest = 8 words; matrices are column-major
+ *     `values[col*height + row]` (crates/stark-backend/src/prover/matrix.rs:43-47);
+ *   - "d_" parameters are device pointers, "h_" parameters host pointers;
+ *   - all work is enqueued on the context's stream; functions that return host data synchronise
+ *     that stream before returning, the others are asynchronous (as in the reference).
+ */
+#ifndef SWIRL_B200_H
+#define SWIRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWIRL_ERR_INVALID 10001     /* bad argument (cf. cudaErrorInvalidValue in merkle_tree.cu:220-222) */
+#define SWIRL_ERR_LAYOUT 10002      /* StackedPcsError::Layout* (prover/stacked_pcs.rs:160-174) */
+#define SWIRL_ERR_UNSUPPORTED 10003
+#define SWIRL_ERR_NO_DEVICE 10004
+
+typedef struct swirl_ctx swirl_ctx; /* one per (device, stream); reference: GpuDeviceCtx, cuda-common/src/stream.rs:132-151 */
+typedef struct swirl_pcs swirl_pcs; /* reference: StackedPcsDataGpu, cuda-backend/src/stacked_pcs.rs:30-46 */
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device` with its own non-blocking stream and the NTT twiddle
+ * tables (reference: GpuDevice::new, cuda-backend/src/device.rs:52-110; twiddle init ntt.rs:20-50). */
+int swirl_ctx_create(int device, swirl_ctx** out);
+/* Same, but enqueue on a caller-owned cudaStream_t (passed as void*). */
+int swirl_ctx_create_on_stream(int device, void* cuda_stream, swirl_ctx** out);
+int swirl_ctx_destroy(swirl_ctx* ctx);
+int swirl_ctx_synchronize(swirl_ctx* ctx);
+void* swirl_ctx_stream(swirl_ctx* ctx);            /* the cudaStream_t */
+uint64_t swirl_ctx_launch_count(swirl_ctx* ctx);   /* kernels launched through this ctx so far */
+/* Tuning / test knobs: largest single-pass NTT radix (log2, default 11, range 1..13) and the
+ * bytes of inter-pass scratch kept per column group (default 48 MiB, meant to stay L2 resident). */
+int swirl_ctx_set_ntt_plan(swirl_ctx* ctx, int max_log_radix, size_t scratch_bytes);
+const char* swirl_last_error(void);
+/* Per-kernel-family device timing with CUDA events on the ctx stream (off by default).
+ * enable(on) clears the recorded spans; read() synchronises and returns the summed duration and
+ * number of launches of a family: 0 leaf hash + query levels, 1 upper tree layers, 2 chunk
+ * iDFT+zeta, 3 strided NTT passes, 4 final NTT pass, 5 stacking.
+ * Reference: gpu_metrics_span_on, cuda-common/src/stream.rs:278-303. */
+int swirl_ctx_timing_enable(swirl_ctx* ctx, int on);
+int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* count);
+
+/* ---- device memory + transport (reference: DeviceDataTransporter, hal.rs:141-207;
+ *      DeviceBuffer / cuda_memcpy, cuda-common/src/{d_buffer.rs,copy.rs}) ---------------------- */
+int swirl_malloc(swirl_ctx* ctx, size_t bytes, void** d_out); /* stream-ordered pool */
+int swirl_free(swirl_ctx* ctx, void* d_ptr);
+int swirl_memcpy_h2d(swirl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
+int swirl_memcpy_d2h(swirl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* synchronises */
+
+/* ---- kernel-level primitives (reference: the `_name` launchers listed in SURVEY.md §2b) ----- */
+
+/* In-place Poseidon2 permutation of n 16-word states.
+ * Reference: poseidon2::poseidon2_mix, cuda-common/include/poseidon2.cuh:184-202. */
+int swirl_poseidon2_permute(swirl_ctx* ctx, uint32_t* d_states, size_t n);
+/* d_out[i] = compress(d_pairs[2i], d_pairs[2i+1]); reference: _poseidon2_adjacent_compress_layer,
+ * cuda-backend/src/cuda/merkle_tree.rs:40-45. */
+int swirl_poseidon2_compress(swirl_ctx* ctx, const uint32_t* d_pairs, uint32_t* d_out, size_t n);
+
+/* Natural-order forward / inverse DFT of `cols` contiguous columns of length 2^log_n, in place.
+ * Reference: batch_ntt (cuda-backend/src/ntt.rs:111-168) = _bit_rev + _ct_mixed_radix_narrow. */
+int swirl_ntt_batch(swirl_ctx* ctx, uint32_t* d_data, int log_n, size_t cols, int inverse);
+
+/* Reed–Solomon encoding of a stacked matrix: d_in is height x width column-major (height a power
+ * of two >= 2^l_skip), d_out receives (height << log_blowup) x width.
+ * Reference: rs_code_matrix, cuda-backend/src/stacked_pcs.rs:229-337
+ * (== prover/stacked_pcs.rs:341-367). */
+int swirl_rs_encode(swirl_ctx* ctx, const uint32_t* d_in, size_t height, size_t width, int l_skip,
+                    int log_blowup, uint32_t* d_out);
+
+/* Merkle tree over a column-major base-field matrix.  d_layers receives every digest layer
+ * concatenated (layer 0 = query_stride digests ... root), 2*query_stride-1 digests of 8 words,
+ * query_stride = next_pow2(height) >> log_rows_per_query.
+ * Reference: _poseidon2_compressing_row_hashes + _poseidon2_adjacent_compress_layer
+ * (cuda-backend/src/cuda/merkle_tree.rs:18-45; MerkleTreeGpu::new merkle_tree.rs:140-197). */
+int swirl_merkle_tree(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width,
+                      int log_rows_per_query, uint32_t* d_layers);
+/* d_out[q][l] = sibling digest of query d_indices[q] at layer l, l < log2(query_stride).
+ * Reference: _query_digest_layers (cuda/merkle_tree.rs:47-54; stacked_pcs.rs:388-405). */
+int swirl_merkle_query_proofs(swirl_ctx* ctx, const uint32_t* d_layers, size_t query_stride,
+                              const uint32_t* d_indices, size_t num_queries, uint32_t* d_out);
+/* d_out[q][t][c] = matrix[c*height + t*query_stride + d_indices[q]], t < 2^log_rows_per_query.
+ * Reference: _matrix_get_rows_fp (cuda/matrix.rs:24-32; stacked_pcs.rs:516-540). */
+int swirl_matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width,
+                           size_t query_stride, int log_rows_per_query, const uint32_t* d_indices,
+                           size_t num_queries, uint32_t* d_out);
+
+/* Proof-of-work search on an 18-word sponge state (16 state words, absorb_idx, sample_idx).
+ * Finds the smallest canonical witness w in [min_w, max_w) with check_witness(bits, w) true and
+ * writes it (canonical) to *h_witness, or UINT32_MAX when none exists.
+ * Reference: _sponge_grind, cuda-backend/src/cuda/sponge.rs:13-21, sponge.cu:65-117 (which
+ * returns *a* witness; the smallest one is among its admissible answers). */
+int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], int bits, uint32_t min_w,
+                       uint32_t max_w, uint32_t* h_witness);
+
+/* ---- phase level: TraceCommitter::commit (hal.rs:84-87) ------------------------------------- */
+
+typedef struct {
+    int32_t l_skip;
+    int32_t n_stack;
+    int32_t log_blowup;
+    int32_t k_whir; /* rows per query = 2^k_whir */
+} swirl_pcs_params;
+
+typedef struct {
+    const uint32_t* data; /* column-major, height * width words */
+    uint64_t height;      /* power of two */
+    uint64_t width;
+} swirl_matrix;
+
+/* stacked_commit (reference: cuda-backend/src/stacked_pcs.rs:50-88 == prover/stacked_pcs.rs:116-134):
+ * stack the height-sorted device-resident traces, RS-encode, Merkle-commit.  Writes the root to
+ * h_root (host) and returns the PCS data that prove_openings consumes.  The traces must stay
+ * alive and unmodified while *out is (the stacked matrix may alias them). */
+int swirl_commit(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* d_traces,
+                 size_t n_traces, uint32_t h_root[8], swirl_pcs** out);
+/* Same with host-resident traces: H2D transport (reference: transport_matrix_to_device,
+ * cuda-backend/src/data_transporter.rs:93-106) + commit in one call. */
+int swirl_commit_host(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* h_traces,
+                      size_t n_traces, uint32_t h_root[8], swirl_pcs** out);
+int swirl_pcs_free(swirl_ctx* ctx, swirl_pcs* pcs);
+
+/* PCS data accessors */
+uint64_t swirl_pcs_stacked_height(const swirl_pcs* pcs);
+uint64_t swirl_pcs_stacked_width(const swirl_pcs* pcs);
+uint64_t swirl_pcs_codeword_height(const swirl_pcs* pcs);
+uint64_t swirl_pcs_query_stride(const swirl_pcs* pcs);
+const uint32_t* swirl_pcs_stacked_matrix(const swirl_pcs* pcs); /* device */
+const uint32_t* swirl_pcs_codeword(const swirl_pcs* pcs);       /* device */
+const uint32_t* swirl_pcs_layers(const swirl_pcs* pcs);         /* device, concatenated layers */
+/* Layout: number of sorted unstacked columns; fills h_out (5 x u64 per column:
+ * matrix index, column in matrix, stacked col, stacked row, log_height) when non-NULL.
+ * Reference: StackedLayout::sorted_cols, prover/stacked_pcs.rs:34-41. */
+uint64_t swirl_pcs_layout(const swirl_pcs* pcs, uint64_t* h_out);
+
+/* Host-side layout computation only (StackedLayout::new, prover/stacked_pcs.rs:144-203). */
+int swirl_stacked_layout(int l_skip, int log_stacked_height, size_t n_mats, const uint64_t* widths,
+                         const int32_t* log_heights, uint64_t* out_width, uint64_t* out_n,
+                         uint64_t* out_cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIRL_B200_H */

@@ -1,0 +1,263 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see bb31.hpp header).
+// Flat C entry points over the C++ restatement so that tests/ (ctypes) and bench.py's
+// cpu_baseline leg can drive it.  All field words cross this API in Montgomery form, exactly as
+// they cross the product's C-ABI (include/swirl_b200.h).
+#include <cstring>
+#include <stdexcept>
+
+#include "commit.hpp"
+#include "transcript.hpp"
+
+using namespace orc;
+
+#define ORC_TRY(body)                 \
+    try {                             \
+        body;                         \
+        return 0;                     \
+    } catch (const std::exception&) { \
+        return 1;                     \
+    }
+
+extern "C" {
+
+// ---- field -------------------------------------------------------------------------------
+uint32_t orc_from_canonical(uint32_t x) { return from_canonical(x).v; }
+uint32_t orc_to_canonical(uint32_t m) { return to_canonical(F::raw(m)); }
+uint32_t orc_f_add(uint32_t a, uint32_t b) { return (F::raw(a) + F::raw(b)).v; }
+uint32_t orc_f_sub(uint32_t a, uint32_t b) { return (F::raw(a) - F::raw(b)).v; }
+uint32_t orc_f_mul(uint32_t a, uint32_t b) { return (F::raw(a) * F::raw(b)).v; }
+uint32_t orc_f_inv(uint32_t a) { return f_inv(F::raw(a)).v; }
+uint32_t orc_two_adic_generator(int bits) { return two_adic_generator(bits).v; }
+void orc_from_canonical_vec(uint32_t* a, size_t n) {
+    for (size_t i = 0; i < n; i++) a[i] = from_canonical(a[i]).v;
+}
+void orc_to_canonical_vec(uint32_t* a, size_t n) {
+    for (size_t i = 0; i < n; i++) a[i] = to_canonical(F::raw(a[i]));
+}
+void orc_f_mul_vec(uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = (F::raw(a[i]) * F::raw(b[i])).v;
+}
+void orc_ef_mul(uint32_t out[4], const uint32_t a[4], const uint32_t b[4]) {
+    EF x, y;
+    memcpy(&x, a, 16);
+    memcpy(&y, b, 16);
+    EF z = x * y;
+    memcpy(out, &z, 16);
+}
+void orc_ef_inv(uint32_t out[4], const uint32_t a[4]) {
+    EF x;
+    memcpy(&x, a, 16);
+    EF z = ef_inv(x);
+    memcpy(out, &z, 16);
+}
+
+// ---- Poseidon2 ---------------------------------------------------------------------------
+void orc_poseidon2_permute(uint32_t* states, size_t n_states) {
+    parallel_for(n_states, [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; i++) poseidon2_permute(reinterpret_cast<F*>(states + 16 * i));
+    }, 256);
+}
+void orc_hash_slice(uint32_t out[8], const uint32_t* vals, size_t n) {
+    Digest d = hash_slice(reinterpret_cast<const F*>(vals), n);
+    memcpy(out, &d, 32);
+}
+void orc_compress(uint32_t out[8], const uint32_t l[8], const uint32_t r[8]) {
+    Digest a, b;
+    memcpy(&a, l, 32);
+    memcpy(&b, r, 32);
+    Digest d = compress(a, b);
+    memcpy(out, &d, 32);
+}
+
+// ---- DFT ---------------------------------------------------------------------------------
+int orc_dft(uint32_t* a, size_t n, int inverse) {
+    ORC_TRY(if (inverse) idft_inplace(reinterpret_cast<F*>(a), n);
+            else dft_inplace(reinterpret_cast<F*>(a), n));
+}
+// batch of `cols` columns of length n each (contiguous), forward natural-order DFT
+int orc_dft_batch(uint32_t* a, size_t n, size_t cols, int inverse) {
+    try {
+        std::vector<F> tw = dft_twiddles(n, inverse != 0);
+        F ninv = f_inv(from_canonical(n));
+        parallel_for(cols, [&](size_t c0, size_t c1) {
+            for (size_t c = c0; c < c1; c++) {
+                F* p = reinterpret_cast<F*>(a) + c * n;
+                dft_with_twiddles(p, n, tw);
+                if (inverse)
+                    for (size_t i = 0; i < n; i++) p[i] *= ninv;
+            }
+        });
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+int orc_coset_dft(uint32_t* a, size_t n, uint32_t shift) {
+    ORC_TRY(coset_dft_inplace(reinterpret_cast<F*>(a), n, F::raw(shift)));
+}
+
+// ---- stacking ----------------------------------------------------------------------------
+// out_cols: per sorted column 5 x u64 = (mat_idx, col_in_mat, stacked col_idx, stacked row_idx,
+// log_height).  Returns 0 ok; 1 on layout error.  *out_n receives the number of sorted columns
+// (call with out_cols == NULL to size).
+int orc_stacked_layout(int l_skip, int log_stacked_height, size_t n_mats, const uint64_t* widths,
+                       const int32_t* log_heights, uint64_t* out_width, uint64_t* out_n,
+                       uint64_t* out_cols) {
+    try {
+        std::vector<std::pair<size_t, int>> meta;
+        for (size_t i = 0; i < n_mats; i++) meta.push_back({(size_t)widths[i], (int)log_heights[i]});
+        StackedLayout lay = make_stacked_layout(l_skip, log_stacked_height, meta);
+        *out_width = lay.width;
+        *out_n = lay.sorted_cols.size();
+        if (out_cols)
+            for (size_t i = 0; i < lay.sorted_cols.size(); i++) {
+                auto& s = lay.sorted_cols[i];
+                out_cols[5 * i + 0] = s.mat_idx;
+                out_cols[5 * i + 1] = s.col_in_mat;
+                out_cols[5 * i + 2] = s.slice.col_idx;
+                out_cols[5 * i + 3] = s.slice.row_idx;
+                out_cols[5 * i + 4] = (uint64_t)s.slice.log_height;
+            }
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+
+static std::vector<ColMajor> wrap_traces(size_t n, const uint32_t* const* ptrs, const uint64_t* heights,
+                                         const uint64_t* widths) {
+    std::vector<ColMajor> v(n);
+    for (size_t i = 0; i < n; i++) {
+        v[i] = ColMajor(heights[i], widths[i]);
+        memcpy(v[i].values.data(), ptrs[i], heights[i] * widths[i] * 4);
+    }
+    return v;
+}
+
+// out must hold 2^(l_skip+n_stack) * (*out_width) words; call with out == NULL to get width.
+int orc_stacked_matrix(int l_skip, int n_stack, size_t n, const uint32_t* const* ptrs,
+                       const uint64_t* heights, const uint64_t* widths, uint64_t* out_width, uint32_t* out) {
+    try {
+        std::vector<ColMajor> tr = wrap_traces(n, ptrs, heights, widths);
+        std::vector<const ColMajor*> refs;
+        for (auto& t : tr) refs.push_back(&t);
+        StackedLayout lay;
+        ColMajor q = stacked_matrix(l_skip, n_stack, refs, &lay);
+        *out_width = q.width;
+        if (out) memcpy(out, q.values.data(), q.values.size() * 4);
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+
+// ---- RS encode ---------------------------------------------------------------------------
+int orc_eval_to_coeff_rs_message(int l_skip, uint32_t* a, size_t n) {
+    ORC_TRY(eval_to_coeff_rs_message_inplace(l_skip, reinterpret_cast<F*>(a), n));
+}
+int orc_rs_code_matrix(int l_skip, int log_blowup, const uint32_t* evals, size_t height, size_t width,
+                       uint32_t* out) {
+    try {
+        ColMajor m(height, width);
+        memcpy(m.values.data(), evals, height * width * 4);
+        ColMajor r = rs_code_matrix(l_skip, log_blowup, m);
+        memcpy(out, r.values.data(), r.values.size() * 4);
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+
+// ---- Merkle ------------------------------------------------------------------------------
+// out_layers: all digest layers concatenated, layer 0 (query_stride digests) first, root last;
+// total digests = 2*query_stride - 1.
+int orc_merkle_tree(const uint32_t* matrix, size_t height, size_t width, size_t rows_per_query,
+                    uint32_t* out_layers) {
+    try {
+        ColMajor m(height, width);
+        memcpy(m.values.data(), matrix, height * width * 4);
+        MerkleTree t = merkle_tree_new(std::move(m), rows_per_query);
+        uint32_t* o = out_layers;
+        for (auto& l : t.layers) {
+            memcpy(o, l.data(), l.size() * 32);
+            o += l.size() * 8;
+        }
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+
+// Whole commitment.  out_codeword (optional) receives the (H << log_blowup) x W matrix,
+// out_layers (optional) the concatenated digest layers, out_root the 8-word root.
+int orc_stacked_commit(int l_skip, int n_stack, int log_blowup, int k_whir, size_t n,
+                       const uint32_t* const* ptrs, const uint64_t* heights, const uint64_t* widths,
+                       uint32_t out_root[8], uint64_t* out_width, uint32_t* out_codeword,
+                       uint32_t* out_layers) {
+    try {
+        std::vector<ColMajor> tr = wrap_traces(n, ptrs, heights, widths);
+        std::vector<const ColMajor*> refs;
+        for (auto& t : tr) refs.push_back(&t);
+        StackedPcsData d;
+        Digest root = stacked_commit(l_skip, n_stack, log_blowup, k_whir, refs, &d);
+        memcpy(out_root, &root, 32);
+        if (out_width) *out_width = d.matrix.width;
+        if (out_codeword) memcpy(out_codeword, d.tree.backing.values.data(), d.tree.backing.values.size() * 4);
+        if (out_layers) {
+            uint32_t* o = out_layers;
+            for (auto& l : d.tree.layers) {
+                memcpy(o, l.data(), l.size() * 32);
+                o += l.size() * 8;
+            }
+        }
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+
+// ---- transcript --------------------------------------------------------------------------
+// state layout: 16 words + absorb_idx + sample_idx  (== DeviceSpongeState, sponge.cu:13-17)
+static DuplexSponge load_sponge(const uint32_t* s) {
+    DuplexSponge d;
+    memcpy(d.state, s, 64);
+    d.absorb_idx = s[16];
+    d.sample_idx = s[17];
+    return d;
+}
+static void store_sponge(const DuplexSponge& d, uint32_t* s) {
+    memcpy(s, d.state, 64);
+    s[16] = d.absorb_idx;
+    s[17] = d.sample_idx;
+}
+void orc_sponge_observe(uint32_t* st, const uint32_t* vals, size_t n) {
+    DuplexSponge d = load_sponge(st);
+    for (size_t i = 0; i < n; i++) d.observe(F::raw(vals[i]));
+    store_sponge(d, st);
+}
+void orc_sponge_sample(uint32_t* st, uint32_t* out, size_t n) {
+    DuplexSponge d = load_sponge(st);
+    for (size_t i = 0; i < n; i++) out[i] = d.sample().v;
+    store_sponge(d, st);
+}
+uint64_t orc_sponge_sample_bits(uint32_t* st, int bits) {
+    DuplexSponge d = load_sponge(st);
+    uint64_t r = d.sample_bits(bits);
+    store_sponge(d, st);
+    return r;
+}
+int orc_sponge_check_witness(uint32_t* st, int bits, uint32_t w) {
+    DuplexSponge d = load_sponge(st);
+    bool ok = d.check_witness(bits, F::raw(w));
+    store_sponge(d, st);
+    return ok ? 1 : 0;
+}
+// returns the (Montgomery) witness; canonical value is the smallest valid one >= start
+uint32_t orc_sponge_grind(uint32_t* st, int bits, uint32_t start) {
+    DuplexSponge d = load_sponge(st);
+    F w = d.grind(bits, start);
+    store_sponge(d, st);
+    return w.v;
+}
+
+}  // extern "C"

@@ -1,0 +1,378 @@
+"""Host-side mirror of the reference's prover-device interface for the commit path.
+
+Names follow the reference (crates/stark-backend/src/prover/hal.rs:65-138,
+crates/cuda-backend/src/gpu_backend.rs:59-212, cuda-backend/src/base.rs:8-12,
+cuda-backend/src/stacked_pcs.rs:30-46): ``B200Device.commit(traces) -> (commitment, pcs_data)``,
+``DeviceMatrix``, ``StackedPcsData`` (layout / matrix / tree), ``StackedLayout``.
+PyTorch is plumbing only: it owns device buffers and the CUDA context; every computation goes
+through the C ABI of libswirl_b200.so.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .lib import MatrixC, PcsParamsC, check
+
+P = 0x78000001
+_R = (1 << 32) % P
+_RINV = pow(_R, P - 2, P)
+
+
+def to_mont(x):
+    """canonical -> Montgomery words (numpy, host side helper for tests / fixtures)."""
+    a = np.asarray(x, dtype=np.uint64) % P
+    return ((a << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
+
+
+def from_mont(m):
+    a = np.asarray(m, dtype=np.uint64)
+    return ((a * np.uint64(_RINV)) % np.uint64(P)).astype(np.uint32)
+
+
+@dataclass(frozen=True)
+class PcsParams:
+    """The SystemParams fields the commitment depends on (reference: config.rs:52-65)."""
+
+    l_skip: int
+    n_stack: int
+    log_blowup: int
+    k_whir: int
+
+    def c(self):
+        return PcsParamsC(self.l_skip, self.n_stack, self.log_blowup, self.k_whir)
+
+
+def _as_i32_tensor(arr):
+    a = np.ascontiguousarray(arr, dtype=np.uint32)
+    return torch.from_numpy(a.view(np.int32))
+
+
+class DeviceMatrix:
+    """Column-major base-field matrix resident in HBM (reference: DeviceMatrix, base.rs:8-12).
+    ``buffer`` is a flat int32 CUDA tensor of Montgomery words, values[col*height + row]."""
+
+    def __init__(self, buffer, height, width):
+        assert buffer.is_cuda and buffer.dtype in (torch.int32, torch.uint32)
+        assert buffer.numel() == height * width
+        self.buffer, self._h, self._w = buffer, int(height), int(width)
+
+    @classmethod
+    def from_host(cls, values, height, width, device="cuda:0"):
+        """transport_matrix_to_device (data_transporter.rs:93-106): plain H2D memcpy."""
+        t = _as_i32_tensor(np.asarray(values).reshape(-1))
+        return cls(t.to(device), height, width)
+
+    def height(self):
+        return self._h
+
+    def width(self):
+        return self._w
+
+    def to_host(self):
+        return self.buffer.cpu().numpy().view(np.uint32).copy()
+
+    def ptr(self):
+        return self.buffer.data_ptr()
+
+
+@dataclass
+class StackedSlice:
+    col_idx: int
+    row_idx: int
+    log_height: int
+
+
+@dataclass
+class StackedLayout:
+    """reference: prover/stacked_pcs.rs:18-42."""
+
+    l_skip: int
+    height: int
+    width: int
+    sorted_cols: list  # (mat_idx, col_in_mat, StackedSlice)
+
+    @classmethod
+    def new(cls, l_skip, log_stacked_height, sorted_meta):
+        """StackedLayout::new (prover/stacked_pcs.rs:144-203); host-only, no GPU needed."""
+        lib = _lib.load_library()
+        n = len(sorted_meta)
+        widths = (C.c_uint64 * max(n, 1))(*[w for w, _ in sorted_meta])
+        lhs = (C.c_int32 * max(n, 1))(*[h for _, h in sorted_meta])
+        ow, on = C.c_uint64(), C.c_uint64()
+        check(lib.swirl_stacked_layout(l_skip, log_stacked_height, n, widths, lhs, C.byref(ow), C.byref(on), None))
+        buf = (C.c_uint64 * max(5 * on.value, 1))()
+        check(lib.swirl_stacked_layout(l_skip, log_stacked_height, n, widths, lhs, C.byref(ow), C.byref(on), buf))
+        cols = [
+            (int(buf[5 * i]), int(buf[5 * i + 1]), StackedSlice(int(buf[5 * i + 2]), int(buf[5 * i + 3]), int(buf[5 * i + 4])))
+            for i in range(on.value)
+        ]
+        return cls(l_skip, 1 << log_stacked_height, int(ow.value), cols)
+
+
+class MerkleTree:
+    """View of the device-resident tree (reference: MerkleTreeGpu, merkle_tree.rs:76-88)."""
+
+    def __init__(self, device, codeword_ptr, height, width, layers_ptr, query_stride, log_rpq):
+        self._dev = device
+        self.codeword_ptr, self.height, self.width = codeword_ptr, height, width
+        self.layers_ptr, self._qs, self.log_rows_per_query = layers_ptr, query_stride, log_rpq
+
+    def query_stride(self):
+        return self._qs
+
+    def rows_per_query(self):
+        return 1 << self.log_rows_per_query
+
+    def proof_depth(self):
+        return self._qs.bit_length() - 1
+
+    def digest_layers(self):
+        """All layers on the host: list of (n_l, 8) uint32 arrays, layer 0 first, root last."""
+        total = 2 * self._qs - 1
+        flat = self._dev._d2h(self.layers_ptr, total * 8)
+        out, off, n = [], 0, self._qs
+        while n >= 1:
+            out.append(flat[off * 8 : (off + n) * 8].reshape(n, 8))
+            off += n
+            n >>= 1
+        return out
+
+    def root(self):
+        return self._dev._d2h(self.layers_ptr + (2 * self._qs - 2) * 32, 8)
+
+    def backing_matrix(self):
+        return self._dev._d2h(self.codeword_ptr, self.height * self.width)
+
+    def query_merkle_proofs(self, indices):
+        """batch of query_merkle_proof (stacked_pcs.rs:388-405): (num_queries, depth, 8)."""
+        return self._dev.merkle_query_proofs(self.layers_ptr, self._qs, indices)
+
+    def get_opened_rows(self, indices):
+        """batch of get_opened_rows (stacked_pcs.rs:516-540): (num_queries, rows_per_query, width)."""
+        return self._dev.matrix_open_rows(
+            self.codeword_ptr, self.height, self.width, self._qs, self.log_rows_per_query, indices
+        )
+
+
+class StackedPcsData:
+    """reference: StackedPcsDataGpu (cuda-backend/src/stacked_pcs.rs:30-46)."""
+
+    def __init__(self, device, handle, params, keepalive):
+        self._dev, self._h, self.params, self._keep = device, handle, params, keepalive
+        lib = device.lib
+        self.height = int(lib.swirl_pcs_stacked_height(handle))
+        self.width = int(lib.swirl_pcs_stacked_width(handle))
+        n = int(lib.swirl_pcs_layout(handle, None))
+        buf = (C.c_uint64 * max(5 * n, 1))()
+        lib.swirl_pcs_layout(handle, buf)
+        cols = [
+            (int(buf[5 * i]), int(buf[5 * i + 1]), StackedSlice(int(buf[5 * i + 2]), int(buf[5 * i + 3]), int(buf[5 * i + 4])))
+            for i in range(n)
+        ]
+        self.layout = StackedLayout(params.l_skip, self.height, self.width, cols)
+        self.tree = MerkleTree(
+            device,
+            lib.swirl_pcs_codeword(handle),
+            int(lib.swirl_pcs_codeword_height(handle)),
+            self.width,
+            lib.swirl_pcs_layers(handle),
+            int(lib.swirl_pcs_query_stride(handle)),
+            params.k_whir,
+        )
+
+    def matrix(self):
+        """The stacked evaluation matrix (height x width, column-major) on the host."""
+        return self._dev._d2h(self._dev.lib.swirl_pcs_stacked_matrix(self._h), self.height * self.width)
+
+    def commit(self):
+        return self.tree.root()
+
+    def free(self):
+        if self._h:
+            check(self._dev.lib.swirl_pcs_free(self._dev.ctx, self._h))
+            self._h = None
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class B200Device:
+    """reference: GpuDevice (cuda-backend/src/device.rs:52-110) — one CUDA device, one stream."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200Device needs a CUDA device: there is no CPU fallback")
+        self.device = int(device)
+        self.torch_device = torch.device(f"cuda:{self.device}")
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.torch_device)  # make sure the primary context exists
+        h = C.c_void_p()
+        check(self.lib.swirl_ctx_create(self.device, C.byref(h)))
+        self.ctx = h
+
+    def close(self):
+        if self.ctx:
+            self.lib.swirl_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing -------------------------------------------------------------------------
+    def synchronize(self):
+        check(self.lib.swirl_ctx_synchronize(self.ctx))
+
+    def stream_ptr(self):
+        return self.lib.swirl_ctx_stream(self.ctx)
+
+    def torch_stream(self):
+        return torch.cuda.ExternalStream(self.stream_ptr(), device=self.torch_device)
+
+    def launch_count(self):
+        return int(self.lib.swirl_ctx_launch_count(self.ctx))
+
+    def set_ntt_plan(self, max_log_radix, scratch_bytes=0):
+        check(self.lib.swirl_ctx_set_ntt_plan(self.ctx, max_log_radix, scratch_bytes))
+
+    TIMING_SLOTS = {"leaf": 0, "tree": 1, "chunk": 2, "ntt_pass": 3, "ntt_final": 4, "stack": 5}
+
+    def timing_enable(self, on=True):
+        check(self.lib.swirl_ctx_timing_enable(self.ctx, 1 if on else 0))
+
+    def timing_read(self):
+        """{family: (total_ms, launches)} since timing_enable(True)."""
+        out = {}
+        for name, slot in self.TIMING_SLOTS.items():
+            ms, n = C.c_double(), C.c_uint64()
+            check(self.lib.swirl_ctx_timing_read(self.ctx, slot, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, int(n.value))
+        return out
+
+    def alloc(self, n_words):
+        return torch.empty(int(n_words), dtype=torch.int32, device=self.torch_device)
+
+    def h2d(self, arr):
+        return _as_i32_tensor(np.asarray(arr).reshape(-1)).to(self.torch_device)
+
+    def _d2h(self, ptr, n_words):
+        """Device pointer -> numpy uint32 (synchronises the ctx stream first)."""
+        out = np.empty(int(n_words), dtype=np.uint32)
+        check(self.lib.swirl_memcpy_d2h(self.ctx, out.ctypes.data, int(ptr), int(n_words) * 4))
+        return out
+
+    def _sync_torch(self):
+        # torch work on its current stream must be visible to the ctx stream
+        torch.cuda.current_stream(self.torch_device).synchronize()
+
+    # -- kernel-level primitives ------------------------------------------------------------
+    def poseidon2_permute(self, states):
+        """states: CUDA int32 tensor of n*16 words, permuted in place."""
+        self._sync_torch()
+        check(self.lib.swirl_poseidon2_permute(self.ctx, states.data_ptr(), states.numel() // 16))
+
+    def poseidon2_compress(self, pairs):
+        n = pairs.numel() // 16
+        out = self.alloc(n * 8)
+        self._sync_torch()
+        check(self.lib.swirl_poseidon2_compress(self.ctx, pairs.data_ptr(), out.data_ptr(), n))
+        return out
+
+    def ntt_batch(self, data, log_n, cols, inverse=False):
+        self._sync_torch()
+        check(self.lib.swirl_ntt_batch(self.ctx, data.data_ptr(), log_n, cols, 1 if inverse else 0))
+
+    def rs_encode(self, matrix, l_skip, log_blowup, out=None):
+        """rs_code_matrix: DeviceMatrix (H x W) -> DeviceMatrix ((H << log_blowup) x W)."""
+        h, w = matrix.height(), matrix.width()
+        if out is None:
+            out = self.alloc((h << log_blowup) * w)
+        self._sync_torch()
+        check(self.lib.swirl_rs_encode(self.ctx, matrix.ptr(), h, w, l_skip, log_blowup, out.data_ptr()))
+        return DeviceMatrix(out, h << log_blowup, w)
+
+    def merkle_tree(self, matrix, log_rows_per_query, out=None):
+        """Digest layers (concatenated, device tensor) of the tree over `matrix`."""
+        h = matrix.height()
+        leaves = 1 << max(h - 1, 0).bit_length() if h > 1 else 1
+        qs = leaves >> log_rows_per_query
+        if out is None:
+            out = self.alloc((2 * qs - 1) * 8)
+        self._sync_torch()
+        check(
+            self.lib.swirl_merkle_tree(self.ctx, matrix.ptr(), h, matrix.width(), log_rows_per_query, out.data_ptr())
+        )
+        return out
+
+    def merkle_query_proofs(self, layers_ptr, query_stride, indices):
+        idx = self.h2d(np.asarray(indices, dtype=np.uint32))
+        depth = query_stride.bit_length() - 1
+        out = self.alloc(len(indices) * depth * 8)
+        self._sync_torch()
+        check(self.lib.swirl_merkle_query_proofs(self.ctx, layers_ptr, query_stride, idx.data_ptr(), len(indices), out.data_ptr()))
+        self.synchronize()
+        return out.cpu().numpy().view(np.uint32).reshape(len(indices), depth, 8)
+
+    def matrix_open_rows(self, matrix_ptr, height, width, query_stride, log_rpq, indices):
+        idx = self.h2d(np.asarray(indices, dtype=np.uint32))
+        out = self.alloc(len(indices) * (width << log_rpq))
+        self._sync_torch()
+        check(
+            self.lib.swirl_matrix_open_rows(
+                self.ctx, matrix_ptr, height, width, query_stride, log_rpq, idx.data_ptr(), len(indices), out.data_ptr()
+            )
+        )
+        self.synchronize()
+        return out.cpu().numpy().view(np.uint32).reshape(len(indices), 1 << log_rpq, width)
+
+    def sponge_grind(self, state18, bits, min_w=0, max_w=P):
+        """Smallest canonical PoW witness for the 18-word sponge state, or None."""
+        st = (C.c_uint32 * 18)(*[int(x) for x in state18])
+        w = C.c_uint32()
+        check(self.lib.swirl_sponge_grind(self.ctx, st, bits, min_w, max_w, C.byref(w)))
+        return None if w.value == 0xFFFFFFFF else int(w.value)
+
+    # -- TraceCommitter::commit ---------------------------------------------------------------
+    def commit(self, params, traces):
+        """stacked_commit over device-resident, height-sorted traces.
+        Returns (root: uint32[8] Montgomery words, StackedPcsData)."""
+        n = len(traces)
+        arr = (MatrixC * max(n, 1))()
+        for i, t in enumerate(traces):
+            arr[i] = MatrixC(t.ptr(), t.height(), t.width())
+        root = np.zeros(8, dtype=np.uint32)
+        h = C.c_void_p()
+        pc = params.c()
+        self._sync_torch()
+        check(self.lib.swirl_commit(self.ctx, C.byref(pc), arr, n, root.ctypes.data, C.byref(h)))
+        return root, StackedPcsData(self, h, params, list(traces))
+
+    def commit_host(self, params, host_traces):
+        """Same through host buffers: host_traces = [(uint32 ndarray col-major flat, height, width)].
+        The H2D transport happens inside the call (the e2e path bench.py times)."""
+        n = len(host_traces)
+        arr = (MatrixC * max(n, 1))()
+        keep = []
+        for i, (vals, hh, ww) in enumerate(host_traces):
+            if isinstance(vals, torch.Tensor):
+                ptr = vals.data_ptr()
+            else:
+                vals = np.ascontiguousarray(vals, dtype=np.uint32)
+                ptr = vals.ctypes.data
+            keep.append(vals)
+            arr[i] = MatrixC(ptr, hh, ww)
+        root = np.zeros(8, dtype=np.uint32)
+        h = C.c_void_p()
+        pc = params.c()
+        check(self.lib.swirl_commit_host(self.ctx, C.byref(pc), arr, n, root.ctypes.data, C.byref(h)))
+        return root, StackedPcsData(self, h, params, None)

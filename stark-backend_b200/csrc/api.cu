@@ -1,0 +1,217 @@
+// C-ABI glue: context lifetime, error text, and the thin extern "C" wrappers over the kernel-level
+// primitives (include/swirl_b200.h).  Phase-level entry points live next to their orchestration
+// (commit.cu, sponge.cu).
+#include <string>
+
+#include "kernels.cuh"
+
+namespace swirl {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    g_last_error = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") in " + what +
+                   " at " + file + ":" + std::to_string(line);
+    return (int)e;
+}
+
+}  // namespace swirl
+
+using namespace swirl;
+
+extern "C" {
+static void timing_clear(swirl_ctx* ctx);
+}
+
+static int ctx_init(int device, cudaStream_t stream, bool owns, swirl_ctx** out) {
+    SWIRL_REQUIRE(out, "null out");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available: libswirl_b200 has no CPU fallback");
+        return SWIRL_ERR_NO_DEVICE;
+    }
+    SWIRL_REQUIRE(device >= 0 && device < count, "device index");
+    SWIRL_CUDA(cudaSetDevice(device));
+    swirl_ctx* ctx = new swirl_ctx();
+    ctx->device = device;
+    ctx->stream = stream;
+    ctx->owns_stream = owns;
+    if (owns) {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+        }
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    int rc = ntt_init_twiddles(ctx);
+    if (rc == 0) {
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "twiddle init", __FILE__, __LINE__);
+    }
+    if (rc != 0) {
+        swirl_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" {
+
+int swirl_ctx_create(int device, swirl_ctx** out) { return ctx_init(device, nullptr, true, out); }
+
+int swirl_ctx_create_on_stream(int device, void* cuda_stream, swirl_ctx** out) {
+    return ctx_init(device, (cudaStream_t)cuda_stream, false, out);
+}
+
+int swirl_ctx_destroy(swirl_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream || !ctx->owns_stream) cudaStreamSynchronize(ctx->stream);
+    timing_clear(ctx);
+    if (ctx->tw_lo) cudaFree(ctx->tw_lo);
+    if (ctx->tw_hi) cudaFree(ctx->tw_hi);
+    if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int swirl_ctx_synchronize(swirl_ctx* ctx) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void* swirl_ctx_stream(swirl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t swirl_ctx_launch_count(swirl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int swirl_ctx_set_ntt_plan(swirl_ctx* ctx, int max_log_radix, size_t scratch_bytes) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    SWIRL_REQUIRE(max_log_radix >= 1 && max_log_radix <= 13, "max_log_radix must be in [1, 13]");
+    ctx->ntt_max_log_radix = max_log_radix;
+    if (scratch_bytes) ctx->ntt_scratch_bytes = scratch_bytes;
+    return 0;
+}
+
+const char* swirl_last_error(void) { return g_last_error.c_str(); }
+
+static void timing_clear(swirl_ctx* ctx) {
+    for (auto& s : ctx->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    ctx->spans.clear();
+}
+
+int swirl_ctx_timing_enable(swirl_ctx* ctx, int on) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    timing_clear(ctx);
+    ctx->timing = on != 0;
+    return 0;
+}
+
+int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* count) {
+    SWIRL_REQUIRE(ctx && total_ms && count, "null argument");
+    SWIRL_REQUIRE(slot >= 0 && slot < SWIRL_T_SLOTS, "slot");
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot = 0;
+    uint64_t n = 0;
+    for (auto& s : ctx->spans)
+        if (s.slot == slot) {
+            float ms = 0;
+            SWIRL_CUDA(cudaEventElapsedTime(&ms, s.a, s.b));
+            tot += ms;
+            n++;
+        }
+    *total_ms = tot;
+    *count = n;
+    return 0;
+}
+
+int swirl_malloc(swirl_ctx* ctx, size_t bytes, void** d_out) {
+    SWIRL_REQUIRE(ctx && d_out, "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    SWIRL_CUDA(cudaMallocAsync(d_out, bytes ? bytes : 1, ctx->stream));
+    return 0;
+}
+
+int swirl_free(swirl_ctx* ctx, void* d_ptr) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    if (d_ptr) SWIRL_CUDA(cudaFreeAsync(d_ptr, ctx->stream));
+    return 0;
+}
+
+int swirl_memcpy_h2d(swirl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    SWIRL_REQUIRE(ctx && ((d_dst && h_src) || bytes == 0), "null argument");
+    if (bytes) SWIRL_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int swirl_memcpy_d2h(swirl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    SWIRL_REQUIRE(ctx && ((h_dst && d_src) || bytes == 0), "null argument");
+    if (bytes) SWIRL_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int swirl_poseidon2_permute(swirl_ctx* ctx, uint32_t* d_states, size_t n) {
+    SWIRL_REQUIRE(ctx && (d_states || n == 0), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return poseidon2_permute_batch(ctx, d_states, n);
+}
+
+int swirl_poseidon2_compress(swirl_ctx* ctx, const uint32_t* d_pairs, uint32_t* d_out, size_t n) {
+    SWIRL_REQUIRE(ctx && ((d_pairs && d_out) || n == 0), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return poseidon2_compress_batch(ctx, d_pairs, d_out, n);
+}
+
+int swirl_ntt_batch(swirl_ctx* ctx, uint32_t* d_data, int log_n, size_t cols, int inverse) {
+    SWIRL_REQUIRE(ctx && (d_data || cols == 0), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return ntt_batch(ctx, d_data, log_n, cols, inverse != 0);
+}
+
+int swirl_rs_encode(swirl_ctx* ctx, const uint32_t* d_in, size_t height, size_t width, int l_skip, int log_blowup,
+                    uint32_t* d_out) {
+    SWIRL_REQUIRE(ctx && ((d_in && d_out) || width == 0), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return rs_encode(ctx, d_in, height, height, width, l_skip, log_blowup, d_out);
+}
+
+int swirl_merkle_tree(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, int log_rows_per_query,
+                      uint32_t* d_layers) {
+    SWIRL_REQUIRE(ctx && d_layers && (d_matrix || width == 0), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return merkle_commit(ctx, d_matrix, height, width, log_rows_per_query, d_layers);
+}
+
+int swirl_merkle_query_proofs(swirl_ctx* ctx, const uint32_t* d_layers, size_t query_stride, const uint32_t* d_indices,
+                              size_t num_queries, uint32_t* d_out) {
+    SWIRL_REQUIRE(ctx && d_layers && (num_queries == 0 || (d_indices && d_out)), "null argument");
+    SWIRL_REQUIRE(is_pow2(query_stride), "query_stride must be a power of two");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return merkle_query_proofs(ctx, d_layers, query_stride, d_indices, num_queries, d_out);
+}
+
+int swirl_matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, size_t query_stride,
+                           int log_rows_per_query, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out) {
+    SWIRL_REQUIRE(ctx && (num_queries == 0 || width == 0 || (d_matrix && d_indices && d_out)), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return matrix_open_rows(ctx, d_matrix, height, width, query_stride, log_rows_per_query, d_indices, num_queries,
+                            d_out);
+}
+
+}  // extern "C"

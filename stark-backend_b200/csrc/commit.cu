@@ -1,0 +1,261 @@
+// TraceCommitter::commit for the stacked PCS: layout -> stacked matrix -> Reed–Solomon codeword ->
+// Poseidon2 Merkle tree.  Host orchestration in C++ (the reference's is Rust) + the stacking
+// kernel.
+//
+// Replaces (reference, relative to /root/reference):
+//   crates/cuda-backend/src/stacked_pcs.rs:50-88      stacked_commit
+//   crates/cuda-backend/src/stacked_pcs.rs:108-220    get_stacked_layout / stack_traces_into_expanded
+//   crates/cuda-backend/cuda/src/matrix.cu            batch_expand_pad(_wide) for short traces
+//   crates/stark-backend/src/prover/stacked_pcs.rs:144-203  StackedLayout::new (host logic)
+// Observation used here: because heights are powers of two sorted in descending order, greedy
+// stacking never leaves a gap, so the flat column-major stacked matrix is just the concatenation
+// of the flat trace buffers (traces shorter than 2^l_skip are first expanded by striding).  A
+// single trace that exactly fills its stacked columns is therefore used in place, with no copy.
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace swirl {
+
+struct LayoutCol {
+    uint64_t mat_idx, col_in_mat, col_idx, row_idx;
+    int log_height;
+};
+
+struct Layout {
+    int l_skip = 0;
+    uint64_t height = 0, width = 0;
+    std::vector<LayoutCol> cols;
+};
+
+// sorted = (width, log_height), descending log_height
+static int make_layout(int l_skip, int log_stacked_height, size_t n, const uint64_t* widths,
+                       const int32_t* log_heights, Layout* out) {
+    out->l_skip = l_skip;
+    out->height = uint64_t(1) << log_stacked_height;
+    out->cols.clear();
+    uint64_t col = 0, row = 0;
+    for (size_t m = 0; m < n; m++) {
+        if (widths[m] == 0) continue;
+        const int lh = log_heights[m];
+        if (lh > log_stacked_height) {
+            set_error("LayoutHeightExceeded: trace taller than the stacked height");
+            return SWIRL_ERR_LAYOUT;
+        }
+        const uint64_t slen = uint64_t(1) << (lh > l_skip ? lh : l_skip);
+        for (uint64_t j = 0; j < widths[m]; j++) {
+            if (row + slen > out->height) {
+                if (row != out->height) {
+                    set_error("LayoutRowOverflow: traces are not sorted by descending height");
+                    return SWIRL_ERR_LAYOUT;
+                }
+                col++;
+                row = 0;
+            }
+            out->cols.push_back({(uint64_t)m, j, col, row, lh});
+            row += slen;
+        }
+    }
+    out->width = col + (row != 0 ? 1 : 0);
+    return 0;
+}
+
+// dst[i << log_stride] = src[i] for a trace shorter than 2^l_skip (dst pre-zeroed);
+// one launch per short trace, all its columns at once: element e of the flat trace buffer lands
+// at flat offset e << log_stride because every column is expanded by the same factor.
+__global__ void expand_strided_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n,
+                                      int log_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i << log_stride] = src[i];
+}
+
+}  // namespace swirl
+
+using namespace swirl;
+
+struct swirl_pcs {
+    swirl_pcs_params params{};
+    Layout layout;
+    uint64_t codeword_height = 0, query_stride = 0;
+    const uint32_t* stacked = nullptr;  // device; owned iff owns_stacked
+    bool owns_stacked = false;
+    uint32_t* codeword = nullptr;  // device, owned
+    uint32_t* layers = nullptr;    // device, owned
+    std::vector<uint32_t*> owned_traces;  // device copies made by swirl_commit_host
+};
+
+static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* traces, size_t n,
+                       uint32_t h_root[8], swirl_pcs* pcs) {
+    const int l_skip = params->l_skip, n_stack = params->n_stack;
+    SWIRL_REQUIRE(l_skip >= 0 && n_stack >= 0 && l_skip + n_stack <= 27, "l_skip / n_stack");
+    SWIRL_REQUIRE(params->log_blowup >= 0 && params->k_whir >= 0, "log_blowup / k_whir");
+    std::vector<uint64_t> widths(n);
+    std::vector<int32_t> lhs(n);
+    uint64_t total_cells = 0;
+    for (size_t i = 0; i < n; i++) {
+        SWIRL_REQUIRE(is_pow2(traces[i].height), "trace height must be a power of two");
+        widths[i] = traces[i].width;
+        lhs[i] = ilog2(traces[i].height);
+        if (i) SWIRL_REQUIRE(lhs[i] <= lhs[i - 1], "traces must be sorted by descending height");
+        const uint64_t lifted = traces[i].height > (uint64_t(1) << l_skip) ? traces[i].height : (uint64_t(1) << l_skip);
+        total_cells += lifted * traces[i].width;
+    }
+    pcs->params = *params;
+    SWIRL_TRY(make_layout(l_skip, l_skip + n_stack, n, widths.data(), lhs.data(), &pcs->layout));
+    const uint64_t H = pcs->layout.height;
+    const uint64_t W = (total_cells + H - 1) / H;
+    SWIRL_REQUIRE(W == pcs->layout.width, "layout width mismatch");
+    SWIRL_REQUIRE(W > 0, "nothing to commit");
+
+    // ---- stacked matrix ----
+    size_t nonempty = 0, only = 0;
+    for (size_t i = 0; i < n; i++)
+        if (traces[i].width) {
+            nonempty++;
+            only = i;
+        }
+    if (nonempty == 1 && lhs[only] >= l_skip && total_cells == W * H) {
+        pcs->stacked = traces[only].data;  // the trace *is* the stacked matrix
+        pcs->owns_stacked = false;
+    } else {
+        uint32_t* q = nullptr;
+        SWIRL_CUDA(dev_alloc(ctx, &q, W * H));
+        pcs->stacked = q;
+        pcs->owns_stacked = true;
+        uint64_t off = 0;  // flat element offset == col*H + row of the next slice
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t cells = traces[i].height * traces[i].width;
+            if (!cells) continue;
+            if (lhs[i] >= l_skip) {
+                SWIRL_CUDA(cudaMemcpyAsync(q + off, traces[i].data, cells * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                off += cells;
+            } else {
+                const int ls = l_skip - lhs[i];
+                SWIRL_CUDA(cudaMemsetAsync(q + off, 0, (cells << ls) * 4, ctx->stream));
+                expand_strided_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(traces[i].data, q + off,
+                                                                                               cells, ls);
+                SWIRL_LAUNCH_CHECK(ctx);
+                off += cells << ls;
+            }
+        }
+        if (off < W * H) SWIRL_CUDA(cudaMemsetAsync(q + off, 0, (W * H - off) * 4, ctx->stream));
+    }
+
+    // ---- codeword + tree ----
+    const uint64_t N = H << params->log_blowup;
+    SWIRL_REQUIRE((uint64_t(1) << params->k_whir) <= N, "MerkleTreeRowsPerQueryExceeded");
+    pcs->codeword_height = N;
+    pcs->query_stride = N >> params->k_whir;
+    SWIRL_CUDA(dev_alloc(ctx, &pcs->codeword, N * W));
+    SWIRL_CUDA(dev_alloc(ctx, &pcs->layers, (2 * pcs->query_stride - 1) * 8 + 8));
+    SWIRL_TRY(rs_encode(ctx, pcs->stacked, H, H, W, l_skip, params->log_blowup, pcs->codeword));
+    SWIRL_TRY(merkle_commit(ctx, pcs->codeword, N, W, params->k_whir, pcs->layers));
+    SWIRL_CUDA(cudaMemcpyAsync(h_root, pcs->layers + (2 * pcs->query_stride - 2) * 8, 32, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static void pcs_release(swirl_ctx* ctx, swirl_pcs* pcs) {
+    if (!pcs) return;
+    if (pcs->owns_stacked) dev_free(ctx, const_cast<uint32_t*>(pcs->stacked));
+    dev_free(ctx, pcs->codeword);
+    dev_free(ctx, pcs->layers);
+    for (uint32_t* p : pcs->owned_traces) dev_free(ctx, p);
+    delete pcs;
+}
+
+extern "C" {
+
+int swirl_commit(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* d_traces, size_t n_traces,
+                 uint32_t h_root[8], swirl_pcs** out) {
+    SWIRL_REQUIRE(ctx && params && d_traces && h_root && out, "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    swirl_pcs* pcs = new swirl_pcs();
+    int rc = commit_impl(ctx, params, d_traces, n_traces, h_root, pcs);
+    if (rc != 0) {
+        pcs_release(ctx, pcs);
+        *out = nullptr;
+        return rc;
+    }
+    *out = pcs;
+    return 0;
+}
+
+int swirl_commit_host(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* h_traces, size_t n_traces,
+                      uint32_t h_root[8], swirl_pcs** out) {
+    SWIRL_REQUIRE(ctx && params && h_traces && h_root && out, "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    swirl_pcs* pcs = new swirl_pcs();
+    std::vector<swirl_matrix> dev(n_traces);
+    int rc = 0;
+    for (size_t i = 0; i < n_traces && rc == 0; i++) {
+        dev[i] = h_traces[i];
+        const size_t cells = h_traces[i].height * h_traces[i].width;
+        uint32_t* p = nullptr;
+        if (cells) {
+            cudaError_t e = dev_alloc(ctx, &p, cells);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(p, h_traces[i].data, cells * 4, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "H2D trace transport", __FILE__, __LINE__);
+            if (p) pcs->owned_traces.push_back(p);
+        }
+        dev[i].data = p;
+    }
+    if (rc == 0) rc = commit_impl(ctx, params, dev.data(), n_traces, h_root, pcs);
+    if (rc != 0) {
+        pcs_release(ctx, pcs);
+        *out = nullptr;
+        return rc;
+    }
+    *out = pcs;
+    return 0;
+}
+
+int swirl_pcs_free(swirl_ctx* ctx, swirl_pcs* pcs) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    pcs_release(ctx, pcs);
+    return 0;
+}
+
+uint64_t swirl_pcs_stacked_height(const swirl_pcs* pcs) { return pcs->layout.height; }
+uint64_t swirl_pcs_stacked_width(const swirl_pcs* pcs) { return pcs->layout.width; }
+uint64_t swirl_pcs_codeword_height(const swirl_pcs* pcs) { return pcs->codeword_height; }
+uint64_t swirl_pcs_query_stride(const swirl_pcs* pcs) { return pcs->query_stride; }
+const uint32_t* swirl_pcs_stacked_matrix(const swirl_pcs* pcs) { return pcs->stacked; }
+const uint32_t* swirl_pcs_codeword(const swirl_pcs* pcs) { return pcs->codeword; }
+const uint32_t* swirl_pcs_layers(const swirl_pcs* pcs) { return pcs->layers; }
+uint64_t swirl_pcs_layout(const swirl_pcs* pcs, uint64_t* h_out) {
+    const auto& c = pcs->layout.cols;
+    if (h_out)
+        for (size_t i = 0; i < c.size(); i++) {
+            h_out[5 * i + 0] = c[i].mat_idx;
+            h_out[5 * i + 1] = c[i].col_in_mat;
+            h_out[5 * i + 2] = c[i].col_idx;
+            h_out[5 * i + 3] = c[i].row_idx;
+            h_out[5 * i + 4] = (uint64_t)c[i].log_height;
+        }
+    return c.size();
+}
+
+int swirl_stacked_layout(int l_skip, int log_stacked_height, size_t n_mats, const uint64_t* widths,
+                         const int32_t* log_heights, uint64_t* out_width, uint64_t* out_n, uint64_t* out_cols) {
+    SWIRL_REQUIRE(out_width && out_n, "null argument");
+    SWIRL_REQUIRE(l_skip >= 0 && l_skip <= log_stacked_height && log_stacked_height < 63, "l_skip / height");
+    Layout lay;
+    SWIRL_TRY(make_layout(l_skip, log_stacked_height, n_mats, widths, log_heights, &lay));
+    *out_width = lay.width;
+    *out_n = lay.cols.size();
+    if (out_cols)
+        for (size_t i = 0; i < lay.cols.size(); i++) {
+            out_cols[5 * i + 0] = lay.cols[i].mat_idx;
+            out_cols[5 * i + 1] = lay.cols[i].col_in_mat;
+            out_cols[5 * i + 2] = lay.cols[i].col_idx;
+            out_cols[5 * i + 3] = lay.cols[i].row_idx;
+            out_cols[5 * i + 4] = (uint64_t)lay.cols[i].log_height;
+        }
+    return 0;
+}
+
+}  // extern "C"

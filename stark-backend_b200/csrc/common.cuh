@@ -1,0 +1,119 @@
+// Shared host-side plumbing for the swirl_b200 library: the context object behind the C ABI,
+// error capture, stream-ordered scratch allocation.
+//
+// Reference counterparts (relative to /root/reference): cuda-common/src/stream.rs:132-151
+// (one explicit non-blocking stream per device ctx), cuda-common/src/d_buffer.rs (DeviceBuffer),
+// cuda-common/include/launcher.cuh:43-55 (CHECK_KERNEL).  We use the driver's stream-ordered pool
+// (cudaMallocAsync with an unbounded release threshold) instead of the reference's VPMM pool.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/swirl_b200.h"
+
+struct swirl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    // twiddle tables: W = two_adic_generator(27) in Montgomery form
+    //   tw_lo[i] = W^i            (i < 2^14)
+    //   tw_hi[i] = W^(i * 2^14)   (i < 2^13)   == powers of the 2^13-th root of unity
+    uint32_t* tw_lo = nullptr;
+    uint32_t* tw_hi = nullptr;
+    uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
+    int ntt_max_log_radix = 11;               // largest single-pass radix (log2)
+    size_t ntt_scratch_bytes = size_t(48) << 20;  // inter-pass scratch per column group (L2 resident)
+    // optional per-kernel-family CUDA-event timing (bench.py's roofline numbers)
+    bool timing = false;
+    struct TimedSpan {
+        int slot;
+        cudaEvent_t a, b;
+    };
+    std::vector<TimedSpan> spans;
+};
+
+// kernel families for swirl_ctx_timing_read
+enum {
+    SWIRL_T_LEAF = 0,      // fused row sponge + strided tree levels (leaf_tree_kernel)
+    SWIRL_T_TREE = 1,      // upper adjacent compression layers
+    SWIRL_T_CHUNK = 2,     // 2^l_skip chunk iDFT + zeta
+    SWIRL_T_NTT_PASS = 3,  // strided NTT passes
+    SWIRL_T_NTT_FINAL = 4, // final NTT pass (natural-order store)
+    SWIRL_T_STACK = 5,     // stacking copies
+    SWIRL_T_SLOTS = 6
+};
+
+struct SwirlTimed {  // RAII: records an event pair around a launch when ctx->timing is on
+    swirl_ctx* ctx;
+    cudaEvent_t b = nullptr;
+    SwirlTimed(swirl_ctx* c, int slot) : ctx(c) {
+        if (!c->timing) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+        c->spans.push_back({slot, a, b});
+    }
+    ~SwirlTimed() {
+        if (b) cudaEventRecord(b, ctx->stream);
+    }
+};
+
+namespace swirl {
+
+constexpr int TW_LO_BITS = 14;
+constexpr int TW_HI_BITS = 13;
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+// stream-ordered allocation helpers
+template <class T>
+inline cudaError_t dev_alloc(swirl_ctx* ctx, T** p, size_t count) {
+    return cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
+}
+template <class T>
+inline void dev_free(swirl_ctx* ctx, T* p) {
+    if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+
+inline int ilog2(size_t n) {
+    int l = 0;
+    while ((size_t(1) << l) < n) l++;
+    return l;
+}
+inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+
+}  // namespace swirl
+
+#define SWIRL_CUDA(expr)                                                         \
+    do {                                                                         \
+        cudaError_t _e = (expr);                                                 \
+        if (_e != cudaSuccess) return swirl::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define SWIRL_LAUNCH_CHECK(ctx)                                                  \
+    do {                                                                         \
+        (ctx)->launches++;                                                       \
+        cudaError_t _e = cudaGetLastError();                                     \
+        if (_e != cudaSuccess) return swirl::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define SWIRL_REQUIRE(cond, msg)                       \
+    do {                                               \
+        if (!(cond)) {                                 \
+            swirl::set_error(std::string("invalid argument: ") + (msg)); \
+            return SWIRL_ERR_INVALID;                  \
+        }                                              \
+    } while (0)
+
+#define SWIRL_TRY(expr)            \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != 0) return _rc;  \
+    } while (0)

@@ -1,0 +1,38 @@
+// Internal (non-ABI) entry points shared between the translation units of libswirl_b200.
+#pragma once
+#include "common.cuh"
+
+namespace swirl {
+
+// ---- merkle.cu ---------------------------------------------------------------------------
+// Digest layers of the tree over `matrix` (column-major, `height` x `width`, rows >= height up to
+// the next power of two hash as zero rows).  `d_layers` receives all layers concatenated: layer 0
+// (query_stride = num_leaves >> log_rpq digests) first, the root last; 2*query_stride-1 digests.
+int merkle_commit(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, int log_rpq,
+                  uint32_t* d_layers);
+int poseidon2_permute_batch(swirl_ctx* ctx, uint32_t* d_states, size_t n);
+int poseidon2_compress_batch(swirl_ctx* ctx, const uint32_t* d_pairs, uint32_t* d_out, size_t n);
+int merkle_query_proofs(swirl_ctx* ctx, const uint32_t* d_layers, size_t query_stride,
+                        const uint32_t* d_indices, size_t num_queries, uint32_t* d_out);
+int matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width,
+                     size_t query_stride, int log_rpq, const uint32_t* d_indices, size_t num_queries,
+                     uint32_t* d_out);
+
+// ---- ntt.cu ------------------------------------------------------------------------------
+int ntt_init_twiddles(swirl_ctx* ctx);
+// Natural-order (i)DFT of `cols` contiguous columns of length 2^log_n, in place.
+int ntt_batch(swirl_ctx* ctx, uint32_t* d_data, int log_n, size_t cols, bool inverse);
+// Reed–Solomon encode: every column of the H x W column-major `d_in` (column stride in_stride)
+// -> column of length H << log_blowup in `d_out` (column stride H << log_blowup).
+int rs_encode(swirl_ctx* ctx, const uint32_t* d_in, size_t in_stride, size_t H, size_t W, int l_skip,
+              int log_blowup, uint32_t* d_out);
+
+// ---- stacking.cu -------------------------------------------------------------------------
+struct StackCopy {  // one unstacked column -> its slot in the stacked matrix
+    const uint32_t* src;  // device pointer to the column (height = 1 << log_height)
+    uint64_t dst_offset;  // element offset in the stacked matrix (col * H + row)
+    uint32_t log_height;
+    uint32_t log_stride;  // 0 unless log_height < l_skip
+};
+
+}  // namespace swirl

@@ -1,0 +1,90 @@
+// Proof-of-work grinding for the duplex-sponge transcript.
+//
+// Replaces (reference, relative to /root/reference):
+//   crates/cuda-backend/cuda/src/sponge.cu:65-117     grind_kernel / _sponge_grind
+//   crates/cuda-backend/src/sponge.rs:267-300          DuplexSpongeGpu::grind_gpu
+// Semantics = crates/stark-backend/src/transcript/traits.rs:63-86 (check_witness / grind) over
+// transcript/duplex_sponge.rs:60-83.  Whatever the absorb position, observing the witness and then
+// sampling costs exactly one permutation and the sampled word is state[7] of the permuted state
+// (observe fills slot absorb_idx; either that completes the rate block and permutes, or the
+// following sample permutes; both leave sample_idx = 8 -> returns state[7]).
+//
+// Unlike the reference (first finder wins, non-deterministic) this search is deterministic: it
+// returns the smallest valid witness, scanning ascending windows and taking an atomicMin inside
+// the first window that contains a hit.
+#include "kernels.cuh"
+#include "poseidon2.cuh"
+
+namespace swirl {
+
+struct GrindState {
+    uint32_t s[16];
+    uint32_t slot;
+};
+
+__global__ void __launch_bounds__(256)
+grind_kernel(GrindState st, uint32_t mask, uint32_t w0, uint32_t w_end, uint32_t* __restrict__ result) {
+    const uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= w_end) return;
+    uint32_t s[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = st.s[i];
+    const uint32_t wm = bb::to_mont(w);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if ((uint32_t)i == st.slot) s[i] = wm;
+    p2::permute(s);
+    if ((bb::from_mont(s[7]) & mask) == 0) atomicMin(result, w);
+}
+
+}  // namespace swirl
+
+using namespace swirl;
+
+extern "C" int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], int bits, uint32_t min_w,
+                                  uint32_t max_w, uint32_t* h_witness) {
+    SWIRL_REQUIRE(ctx && h_state && h_witness, "null argument");
+    SWIRL_REQUIRE(bits >= 0 && bits < 31, "bits");
+    SWIRL_REQUIRE(h_state[16] < 8 && h_state[17] <= 8, "sponge indices");
+    if (max_w > bb::P) max_w = bb::P;
+    *h_witness = 0xffffffffu;
+    if (bits == 0) {
+        *h_witness = 0;  // grind(0) returns ZERO without touching the transcript (traits.rs:78-80)
+        return 0;
+    }
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    GrindState st;
+    for (int i = 0; i < 16; i++) st.s[i] = h_state[i];
+    st.slot = h_state[16];
+    const uint32_t mask = (1u << bits) - 1;
+    uint32_t* d_res = nullptr;
+    SWIRL_CUDA(dev_alloc(ctx, &d_res, 1));
+    uint64_t window = uint64_t(4) << bits;
+    if (window < (1u << 16)) window = 1u << 16;
+    if (window > (1u << 24)) window = 1u << 24;
+    int rc = 0;
+    for (uint64_t w0 = min_w; w0 < max_w; w0 += window) {
+        const uint32_t w_end = (uint32_t)(w0 + window < max_w ? w0 + window : max_w);
+        cudaError_t e = cudaMemsetAsync(d_res, 0xff, 4, ctx->stream);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "memset", __FILE__, __LINE__);
+            break;
+        }
+        const uint32_t cnt = w_end - (uint32_t)w0;
+        grind_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(st, mask, (uint32_t)w0, w_end, d_res);
+        ctx->launches++;
+        uint32_t found = 0xffffffffu;
+        e = cudaMemcpyAsync(&found, d_res, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "grind", __FILE__, __LINE__);
+            break;
+        }
+        if (found != 0xffffffffu) {
+            *h_witness = found;
+            break;
+        }
+    }
+    dev_free(ctx, d_res);
+    return rc;
+}

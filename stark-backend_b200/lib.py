@@ -1,0 +1,98 @@
+"""ctypes binding of ``libswirl_b200.so`` (declarations follow include/swirl_b200.h one to one).
+
+This is the Python stand-in for the Rust ``extern "C"`` block a reference-side crate would hold
+(reference: crates/cuda-backend/src/cuda/*.rs); see INTEGRATION.md.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class SwirlError(RuntimeError):
+    """A non-zero return code from the C ABI (reference: CudaError::from_result,
+    cuda-common/src/error.rs:53-60)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"swirl_b200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "libswirl_b200.so")
+
+
+class PcsParamsC(C.Structure):
+    _fields_ = [("l_skip", C.c_int32), ("n_stack", C.c_int32), ("log_blowup", C.c_int32), ("k_whir", C.c_int32)]
+
+
+class MatrixC(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("height", C.c_uint64), ("width", C.c_uint64)]
+
+
+_vp, _sz, _i, _u32, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64
+
+# name -> (restype, argtypes); every prototype of include/swirl_b200.h
+PROTOTYPES = {
+    "swirl_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "swirl_ctx_create_on_stream": (_i, [_i, _vp, C.POINTER(_vp)]),
+    "swirl_ctx_destroy": (_i, [_vp]),
+    "swirl_ctx_synchronize": (_i, [_vp]),
+    "swirl_ctx_stream": (_vp, [_vp]),
+    "swirl_ctx_launch_count": (_u64, [_vp]),
+    "swirl_ctx_set_ntt_plan": (_i, [_vp, _i, _sz]),
+    "swirl_last_error": (C.c_char_p, []),
+    "swirl_ctx_timing_enable": (_i, [_vp, _i]),
+    "swirl_ctx_timing_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "swirl_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "swirl_free": (_i, [_vp, _vp]),
+    "swirl_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz]),
+    "swirl_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "swirl_poseidon2_permute": (_i, [_vp, _vp, _sz]),
+    "swirl_poseidon2_compress": (_i, [_vp, _vp, _vp, _sz]),
+    "swirl_ntt_batch": (_i, [_vp, _vp, _i, _sz, _i]),
+    "swirl_rs_encode": (_i, [_vp, _vp, _sz, _sz, _i, _i, _vp]),
+    "swirl_merkle_tree": (_i, [_vp, _vp, _sz, _sz, _i, _vp]),
+    "swirl_merkle_query_proofs": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "swirl_matrix_open_rows": (_i, [_vp, _vp, _sz, _sz, _sz, _i, _vp, _sz, _vp]),
+    "swirl_sponge_grind": (_i, [_vp, _vp, _i, _u32, _u32, C.POINTER(_u32)]),
+    "swirl_commit": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
+    "swirl_commit_host": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
+    "swirl_pcs_free": (_i, [_vp, _vp]),
+    "swirl_pcs_stacked_height": (_u64, [_vp]),
+    "swirl_pcs_stacked_width": (_u64, [_vp]),
+    "swirl_pcs_codeword_height": (_u64, [_vp]),
+    "swirl_pcs_query_stride": (_u64, [_vp]),
+    "swirl_pcs_stacked_matrix": (_vp, [_vp]),
+    "swirl_pcs_codeword": (_vp, [_vp]),
+    "swirl_pcs_layers": (_vp, [_vp]),
+    "swirl_pcs_layout": (_u64, [_vp, _vp]),
+    "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
+}
+
+
+def load_library():
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C stark-backend_b200`). There is no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().swirl_last_error()
+        raise SwirlError(rc, msg.decode() if msg else "")

@@ -1,0 +1,209 @@
+"""ctypes wrapper of the CPU oracle (oracle/capi.cpp).  Test infrastructure only."""
+import ctypes as C
+
+import numpy as np
+
+P = 0x78000001
+_vp, _sz, _i, _u32, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp)
+
+
+class Oracle:
+    def __init__(self, path):
+        L = self.L = C.CDLL(path)
+        for n in ("orc_from_canonical", "orc_to_canonical", "orc_f_inv", "orc_two_adic_generator", "orc_sponge_grind"):
+            getattr(L, n).restype = _u32
+        for n in ("orc_f_add", "orc_f_sub", "orc_f_mul"):
+            getattr(L, n).restype = _u32
+            getattr(L, n).argtypes = [_u32, _u32]
+        L.orc_sponge_sample_bits.restype = _u64
+        L.orc_poseidon2_permute.argtypes = [_vp, _sz]
+        L.orc_hash_slice.argtypes = [_vp, _vp, _sz]
+        L.orc_dft.argtypes = [_vp, _sz, _i]
+        L.orc_dft_batch.argtypes = [_vp, _sz, _sz, _i]
+        L.orc_coset_dft.argtypes = [_vp, _sz, _u32]
+        L.orc_stacked_layout.argtypes = [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]
+        L.orc_stacked_matrix.argtypes = [_i, _i, _sz, _vp, _vp, _vp, C.POINTER(_u64), _vp]
+        L.orc_eval_to_coeff_rs_message.argtypes = [_i, _vp, _sz]
+        L.orc_rs_code_matrix.argtypes = [_i, _i, _vp, _sz, _sz, _vp]
+        L.orc_merkle_tree.argtypes = [_vp, _sz, _sz, _sz, _vp]
+        L.orc_stacked_commit.argtypes = [_i, _i, _i, _i, _sz, _vp, _vp, _vp, _vp, C.POINTER(_u64), _vp, _vp]
+        L.orc_sponge_observe.argtypes = [_vp, _vp, _sz]
+        L.orc_sponge_sample.argtypes = [_vp, _vp, _sz]
+        L.orc_sponge_sample_bits.argtypes = [_vp, _i]
+        L.orc_sponge_check_witness.argtypes = [_vp, _i, _u32]
+        L.orc_sponge_grind.argtypes = [_vp, _i, _u32]
+        L.orc_from_canonical_vec.argtypes = [_vp, _sz]
+        L.orc_to_canonical_vec.argtypes = [_vp, _sz]
+        L.orc_ef_mul.argtypes = [_vp, _vp, _vp]
+        L.orc_ef_inv.argtypes = [_vp, _vp]
+
+    # ---- field ----
+    def to_mont(self, x):
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64) % P, dtype=np.uint32).copy()
+        self.L.orc_from_canonical_vec(_p(a), a.size)
+        return a
+
+    def from_mont(self, m):
+        a = np.ascontiguousarray(m, dtype=np.uint32).copy()
+        self.L.orc_to_canonical_vec(_p(a), a.size)
+        return a
+
+    def random_field(self, rng, shape):
+        """uniform canonical values -> Montgomery words"""
+        return self.to_mont(rng.integers(0, P, size=shape, dtype=np.uint64)).reshape(shape)
+
+    def ef_mul(self, a, b):
+        a, b = np.ascontiguousarray(a, np.uint32), np.ascontiguousarray(b, np.uint32)
+        out = np.zeros(4, np.uint32)
+        self.L.orc_ef_mul(_p(out), _p(a), _p(b))
+        return out
+
+    def ef_inv(self, a):
+        a = np.ascontiguousarray(a, np.uint32)
+        out = np.zeros(4, np.uint32)
+        self.L.orc_ef_inv(_p(out), _p(a))
+        return out
+
+    # ---- poseidon2 ----
+    def permute(self, states):
+        s = np.ascontiguousarray(states, dtype=np.uint32).copy()
+        self.L.orc_poseidon2_permute(_p(s), s.size // 16)
+        return s
+
+    def hash_slice(self, vals):
+        v = np.ascontiguousarray(vals, dtype=np.uint32)
+        out = np.zeros(8, np.uint32)
+        self.L.orc_hash_slice(_p(out), _p(v), v.size)
+        return out
+
+    def compress(self, l, r):
+        l, r = np.ascontiguousarray(l, np.uint32), np.ascontiguousarray(r, np.uint32)
+        out = np.zeros(8, np.uint32)
+        self.L.orc_compress(_p(out), _p(l), _p(r))
+        return out
+
+    # ---- dft ----
+    def dft(self, a, inverse=False):
+        v = np.ascontiguousarray(a, dtype=np.uint32).copy()
+        assert self.L.orc_dft(_p(v), v.size, 1 if inverse else 0) == 0
+        return v
+
+    def dft_batch(self, a, n, cols, inverse=False):
+        v = np.ascontiguousarray(a, dtype=np.uint32).copy()
+        assert self.L.orc_dft_batch(_p(v), n, cols, 1 if inverse else 0) == 0
+        return v
+
+    def coset_dft(self, a, shift):
+        v = np.ascontiguousarray(a, dtype=np.uint32).copy()
+        assert self.L.orc_coset_dft(_p(v), v.size, int(shift)) == 0
+        return v
+
+    # ---- stacking / rs / merkle ----
+    def stacked_layout(self, l_skip, log_h, meta):
+        n = len(meta)
+        w = np.array([m[0] for m in meta] or [0], dtype=np.uint64)
+        lh = np.array([m[1] for m in meta] or [0], dtype=np.int32)
+        ow, on = _u64(), _u64()
+        rc = self.L.orc_stacked_layout(l_skip, log_h, n, _p(w), _p(lh), C.byref(ow), C.byref(on), None)
+        if rc:
+            return None
+        buf = np.zeros(max(5 * on.value, 1), dtype=np.uint64)
+        self.L.orc_stacked_layout(l_skip, log_h, n, _p(w), _p(lh), C.byref(ow), C.byref(on), _p(buf))
+        return int(ow.value), buf[: 5 * on.value].reshape(-1, 5)
+
+    @staticmethod
+    def _trace_args(traces):
+        n = len(traces)
+        arrs = [np.ascontiguousarray(t[0], dtype=np.uint32) for t in traces]
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        hs = np.array([t[1] for t in traces] or [0], dtype=np.uint64)
+        ws = np.array([t[2] for t in traces] or [0], dtype=np.uint64)
+        return arrs, ptrs, hs, ws
+
+    def stacked_matrix(self, l_skip, n_stack, traces):
+        """traces: list of (flat col-major uint32 array, height, width). Returns (flat, width)."""
+        arrs, ptrs, hs, ws = self._trace_args(traces)
+        ow = _u64()
+        assert self.L.orc_stacked_matrix(l_skip, n_stack, len(traces), ptrs, _p(hs), _p(ws), C.byref(ow), None) == 0
+        out = np.zeros((1 << (l_skip + n_stack)) * ow.value, dtype=np.uint32)
+        self.L.orc_stacked_matrix(l_skip, n_stack, len(traces), ptrs, _p(hs), _p(ws), C.byref(ow), _p(out))
+        return out, int(ow.value)
+
+    def eval_to_coeff_rs_message(self, l_skip, a):
+        v = np.ascontiguousarray(a, dtype=np.uint32).copy()
+        assert self.L.orc_eval_to_coeff_rs_message(l_skip, _p(v), v.size) == 0
+        return v
+
+    def rs_code_matrix(self, l_skip, log_blowup, evals, height, width):
+        e = np.ascontiguousarray(evals, dtype=np.uint32)
+        out = np.zeros((height << log_blowup) * width, dtype=np.uint32)
+        assert self.L.orc_rs_code_matrix(l_skip, log_blowup, _p(e), height, width, _p(out)) == 0
+        return out
+
+    def merkle_tree(self, matrix, height, width, rows_per_query):
+        """returns list of layers [(n,8) ...] or None on a parameter error"""
+        m = np.ascontiguousarray(matrix, dtype=np.uint32)
+        leaves = 1
+        while leaves < height:
+            leaves <<= 1
+        if rows_per_query > leaves or height == 0:
+            return None
+        qs = leaves // rows_per_query
+        out = np.zeros((2 * qs - 1) * 8, dtype=np.uint32)
+        if self.L.orc_merkle_tree(_p(m), height, width, rows_per_query, _p(out)) != 0:
+            return None
+        return split_layers(out, qs)
+
+    def stacked_commit(self, l_skip, n_stack, log_blowup, k_whir, traces, want_codeword=True):
+        arrs, ptrs, hs, ws = self._trace_args(traces)
+        H = 1 << (l_skip + n_stack)
+        cells = sum(max(t[1], 1 << l_skip) * t[2] for t in traces)
+        W = (cells + H - 1) // H
+        N = H << log_blowup
+        qs = N >> k_whir
+        root = np.zeros(8, np.uint32)
+        cw = np.zeros(N * W, np.uint32) if want_codeword else None
+        layers = np.zeros((2 * qs - 1) * 8, np.uint32)
+        ow = _u64()
+        rc = self.L.orc_stacked_commit(
+            l_skip, n_stack, log_blowup, k_whir, len(traces), ptrs, _p(hs), _p(ws), _p(root), C.byref(ow),
+            _p(cw) if want_codeword else None, _p(layers),
+        )
+        assert rc == 0
+        assert ow.value == W
+        return root, cw, split_layers(layers, qs), W
+
+    # ---- transcript ----
+    def sponge_new(self):
+        return np.zeros(18, dtype=np.uint32)
+
+    def sponge_observe(self, st, vals):
+        v = np.ascontiguousarray(vals, dtype=np.uint32)
+        self.L.orc_sponge_observe(_p(st), _p(v), v.size)
+
+    def sponge_sample(self, st, n=1):
+        out = np.zeros(n, np.uint32)
+        self.L.orc_sponge_sample(_p(st), _p(out), n)
+        return out
+
+    def sponge_sample_bits(self, st, bits):
+        return int(self.L.orc_sponge_sample_bits(_p(st), bits))
+
+    def sponge_check_witness(self, st, bits, w_mont):
+        return bool(self.L.orc_sponge_check_witness(_p(st), bits, int(w_mont)))
+
+    def sponge_grind(self, st, bits, start=0):
+        return int(self.L.orc_sponge_grind(_p(st), bits, start))
+
+
+def split_layers(flat, qs):
+    out, off, n = [], 0, qs
+    while n >= 1:
+        out.append(flat[off * 8 : (off + n) * 8].reshape(n, 8).copy())
+        off += n
+        n >>= 1
+    return out
