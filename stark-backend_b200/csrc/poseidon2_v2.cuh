@@ -1,0 +1,191 @@
+// Poseidon2 over BabyBear, width 16, x^7, 4 + 13 + 4 rounds — second-generation permutation for
+// sm_100a, tuned against the measured integer issue rates (tools/int_roofline.cu):
+//   IMAD 1 fma-pipe slot, IMAD.WIDE 2, IMAD.HI 2, IADD3/LOP3/SHF/VIADDMNMX 1 alu-pipe slot,
+//   64 lanes/clk/SM per pipe.  A canonical Montgomery product is 5 fma slots + 2 alu ops; the
+//   permutation has 564 S-box products, so the fma pipe is the floor and everything else is
+//   arranged to stay off it and to use as few alu ops as possible:
+//   * S-box in *signed* Montgomery form (x = a*b; q = lo(x)*p^-1; r = hi(x) - hi(q*p)): closed on
+//     int32 with |r| <= |a||b|/2^32 + p/2, so the three intermediate powers need no correction and
+//     only x^7 is brought back to [0,p) with one VIADDMNMX;
+//   * the round constant is stored as rc - p in (-p, 0], which makes `state + rc` a single add
+//     with a result in [-p, p), and for the external layers the last add of the linear layer and
+//     the next round's constant are one 3-input IADD3;
+//   * multiplications by 2^-k in the internal diagonal use p = 15*2^27 + 1:
+//     x*2^-k = (x >> k) - 15*2^(27-k) * (x mod 2^k), one shift, one mask, one IMAD;
+//   * round loops stay rolled (`#pragma unroll 1`) so the body is ~20 KB of code and lives in
+//     the instruction cache instead of streaming 100+ KB of straight-line SASS per warp.
+// Replaces (reference, relative to /root/reference):
+//   crates/cuda-common/include/poseidon2.cuh:77-202         poseidon2::poseidon2_mix
+// Bit-exact with p2::permute (poseidon2.cuh) and the CPU oracle; canonical Montgomery words in
+// and out.
+#pragma once
+#include "bb31.cuh"
+#include "poseidon2_constants.cuh"
+
+namespace p2v2 {
+
+constexpr int32_t P = (int32_t)bb::P;
+
+// rc - p as signed words (rc Montgomery canonical)
+#define M(x) ((int32_t)bb::mont(x) - (int32_t)bb::P)
+// a fifth block of "zero" constants (0 - p) lets the last external layer of each half run the same
+// fused code; its outputs are canonicalised afterwards
+#define Z4 -P, -P, -P, -P
+#define Z16 Z4, Z4, Z4, Z4
+static __device__ __constant__ int32_t C_EXT_INIT[80] = {P2_EXT_INIT_VALUES Z16};
+static __device__ __constant__ int32_t C_INTERNAL[13] = {P2_INTERNAL_VALUES};
+static __device__ __constant__ int32_t C_EXT_TERM[80] = {P2_EXT_TERM_VALUES Z16};
+static const int32_t H_EXT_INIT[80] = {P2_EXT_INIT_VALUES Z16};
+static const int32_t H_INTERNAL[13] = {P2_INTERNAL_VALUES};
+static const int32_t H_EXT_TERM[80] = {P2_EXT_TERM_VALUES Z16};
+#undef Z16
+#undef Z4
+#undef M
+
+#ifdef __CUDA_ARCH__
+#define P2V2_RC_INIT(i) C_EXT_INIT[i]
+#define P2V2_RC_INT(i) C_INTERNAL[i]
+#define P2V2_RC_TERM(i) C_EXT_TERM[i]
+#else
+#define P2V2_RC_INIT(i) H_EXT_INIT[i]
+#define P2V2_RC_INT(i) H_INTERNAL[i]
+#define P2V2_RC_TERM(i) H_EXT_TERM[i]
+#endif
+
+__host__ __device__ __forceinline__ int32_t mulhi_s32(int32_t a, int32_t b) {
+#ifdef __CUDA_ARCH__
+    return __mulhi(a, b);
+#else
+    return (int32_t)(((int64_t)a * b) >> 32);
+#endif
+}
+
+// signed Montgomery product: a*b*2^-32 (mod p), any int32 inputs, |r| <= |a||b|/2^32 + p/2
+__host__ __device__ __forceinline__ int32_t smul(int32_t a, int32_t b) {
+    const int64_t x = (int64_t)a * b;
+    const int32_t q = (int32_t)((uint32_t)x * bb::PINV);
+    return (int32_t)(x >> 32) - mulhi_s32(q, P);
+}
+
+// v in (-p, p) -> canonical [0, p)
+__host__ __device__ __forceinline__ uint32_t canon(int32_t v) {
+    const uint32_t u = (uint32_t)v, w = u + bb::P;
+    return u < w ? u : w;
+}
+
+// s in [-p, p) (state word plus signed round constant) -> s^7 canonical
+__host__ __device__ __forceinline__ uint32_t sbox7(int32_t s) {
+    const int32_t x2 = smul(s, s);    // |.| < 0.97 p
+    const int32_t x3 = smul(x2, s);   // < 0.96 p
+    const int32_t x4 = smul(x2, x2);  // < 0.95 p
+    return canon(smul(x3, x4));       // < 0.93 p
+}
+
+// y = M4 x, M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]; 11 canonical additions
+__host__ __device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
+    const uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3);
+    const uint32_t t0123 = bb::add(t01, t23);
+    const uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
+    const uint32_t y3 = bb::add(t01233, bb::dbl(x0));
+    const uint32_t y1 = bb::add(t01123, bb::dbl(x2));
+    x0 = bb::add(t01123, t01);
+    x2 = bb::add(t01233, t23);
+    x1 = y1;
+    x3 = y3;
+}
+
+// External linear layer fused with the next round's constants: the outputs are
+// state + (rc - p) in [-p, p), ready for the S-box (one IADD3 per word).
+__host__ __device__ __forceinline__ void external_linear_rc(uint32_t s[16], const int32_t* rc) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) m4(s[i], s[i + 1], s[i + 2], s[i + 3]);
+    uint32_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) t[j] = bb::add(bb::add(s[j], s[4 + j]), bb::add(s[8 + j], s[12 + j]));
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = s[i] + t[i & 3] + (uint32_t)rc[i];  // [0,p) + [0,p) + [-p,0)
+}
+
+// x * 2^-k for canonical x, 1 <= k <= 27:  (x >> k) - 15 * 2^(27-k) * (x mod 2^k), in (-p, 2^30]
+template <int K>
+__host__ __device__ __forceinline__ int32_t mul_2exp_neg_signed(uint32_t x) {
+    const uint32_t hi = x >> K, lo = x & ((1u << K) - 1);
+    return (int32_t)(hi - lo * (15u << (27 - K)));
+}
+template <int K>
+__host__ __device__ __forceinline__ uint32_t mul_2exp_neg(uint32_t x) {
+    return canon(mul_2exp_neg_signed<K>(x));
+}
+// -(x * 2^-k), canonical
+template <int K>
+__host__ __device__ __forceinline__ uint32_t mul_neg_2exp_neg(uint32_t x) {
+    const uint32_t hi = x >> K, lo = x & ((1u << K) - 1);
+    return canon((int32_t)(lo * (15u << (27 - K)) - hi));  // in [-2^30, p)
+}
+
+// s <- (J + diag(d)) s, d = (-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 2^-8, 1/4, 1/8, 2^-27, -2^-8, -1/16, -2^-27)
+__host__ __device__ __forceinline__ void internal_linear(uint32_t s[16]) {
+    using bb::add;
+    using bb::sub;
+    const uint32_t r1 = add(add(add(s[1], s[2]), add(s[3], s[4])), add(add(s[5], s[6]), add(s[7], s[8])));
+    const uint32_t r2 = add(add(add(s[9], s[10]), add(s[11], s[12])), add(add(s[13], s[14]), s[15]));
+    const uint32_t rest = add(r1, r2);
+    const uint32_t sum = add(rest, s[0]);
+    s[0] = sub(rest, s[0]);
+    s[1] = add(sum, s[1]);
+    s[2] = add(add(sum, s[2]), s[2]);
+    s[3] = add(sum, bb::halve(s[3]));
+    s[4] = add(add(sum, s[4]), bb::dbl(s[4]));
+    {
+        const uint32_t d = bb::dbl(s[5]);
+        s[5] = add(add(sum, d), d);
+    }
+    s[6] = sub(sum, bb::halve(s[6]));
+    s[7] = sub(sub(sum, s[7]), bb::dbl(s[7]));
+    {
+        const uint32_t d = bb::dbl(s[8]);
+        s[8] = sub(sub(sum, d), d);
+    }
+    s[9] = add(sum, mul_2exp_neg<8>(s[9]));
+    s[10] = add(sum, mul_2exp_neg<2>(s[10]));
+    s[11] = add(sum, mul_2exp_neg<3>(s[11]));
+    s[12] = add(sum, mul_2exp_neg<27>(s[12]));
+    s[13] = add(sum, mul_neg_2exp_neg<8>(s[13]));
+    s[14] = add(sum, mul_neg_2exp_neg<4>(s[14]));
+    s[15] = add(sum, mul_neg_2exp_neg<27>(s[15]));
+}
+
+#ifdef P2V2_UNROLL_ROUNDS
+#define P2V2_ROUND_LOOP _Pragma("unroll")
+#else
+#define P2V2_ROUND_LOOP _Pragma("unroll 1")
+#endif
+
+__host__ __device__ __forceinline__ void permute(uint32_t s[16]) {
+    external_linear_rc(s, &P2V2_RC_INIT(0));
+    P2V2_ROUND_LOOP
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox7((int32_t)s[i]);
+        external_linear_rc(s, &P2V2_RC_INIT((r + 1) * 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = canon((int32_t)s[i]);
+    P2V2_ROUND_LOOP
+    for (int r = 0; r < 13; r++) {
+        s[0] = sbox7((int32_t)s[0] + P2V2_RC_INT(r));
+        internal_linear(s);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = (uint32_t)((int32_t)s[i] + P2V2_RC_TERM(i));
+    P2V2_ROUND_LOOP
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = sbox7((int32_t)s[i]);
+        external_linear_rc(s, &P2V2_RC_TERM((r + 1) * 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) s[i] = canon((int32_t)s[i]);
+}
+
+}  // namespace p2v2

@@ -1,0 +1,77 @@
+// Poseidon2 permutation throughput of the candidate implementations (perms/s on the whole chip),
+// checked for equality against p2::permute on the same states.
+//   nvcc -O3 -std=c++17 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -I../stark-backend_b200/csrc -o p2_bench.bin p2_bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+#include "poseidon2.cuh"
+#include "poseidon2_v2.cuh"
+
+template <int V>
+__device__ __forceinline__ void perm(uint32_t s[16]) {
+    if (V == 0) p2::permute(s);
+    if (V == 1) p2v2::permute(s);
+}
+
+// every thread iterates the permutation `iters` times on its own state (issue-bound measurement)
+template <int V>
+__global__ void __launch_bounds__(256) iterate(uint32_t* states, int iters) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint4* p = reinterpret_cast<uint4*>(states + i * 16);
+    uint4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
+    uint32_t s[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+    for (int it = 0; it < iters; it++) perm<V>(s);
+    p[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    p[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    p[2] = make_uint4(s[8], s[9], s[10], s[11]);
+    p[3] = make_uint4(s[12], s[13], s[14], s[15]);
+}
+
+template <int V>
+double run(const char* name, const std::vector<uint32_t>& init, std::vector<uint32_t>& out, int threads_per_sm, int sms, int iters) {
+    const size_t n = (size_t)threads_per_sm * sms;
+    uint32_t* d;
+    cudaMalloc(&d, n * 64);
+    cudaMemcpy(d, init.data(), n * 64, cudaMemcpyHostToDevice);
+    iterate<V><<<n / 256, 256>>>(d, 2);
+    cudaMemcpy(d, init.data(), n * 64, cudaMemcpyHostToDevice);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a);
+    iterate<V><<<n / 256, 256>>>(d, iters);
+    cudaEventRecord(b);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    out.resize(n * 16);
+    cudaMemcpy(out.data(), d, n * 64, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    double gps = (double)n * iters / (ms * 1e-3) / 1e9;
+    printf("{\"impl\": \"%s\", \"threads_per_sm\": %d, \"gperm_per_s\": %.3f, \"ms\": %.3f, \"err\": \"%s\"}\n", name, threads_per_sm, gps, ms,
+           cudaGetErrorString(e));
+    return gps;
+}
+
+int main() {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (sms <= 0) return 1;
+    const int iters = 64;
+    for (int tps : {512, 1024, 2048}) {
+        const size_t n = (size_t)tps * sms;
+        std::vector<uint32_t> init(n * 16), o0, o1;
+        uint64_t x = 88172645463325252ull;
+        for (auto& v : init) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            v = (uint32_t)(x % bb::P);
+        }
+        run<0>("p2 (v1, unrolled, canonical)", init, o0, tps, sms, iters);
+        run<1>("p2v2", init, o1, tps, sms, iters);
+        size_t bad = 0;
+        for (size_t i = 0; i < o0.size(); i++) bad += o0[i] != o1[i];
+        printf("{\"check\": \"p2v2 == p2\", \"mismatches\": %zu}\n", bad);
+    }
+    return 0;
+}
