@@ -139,6 +139,20 @@ def run_reference(args):
     }))
 
 
+def int_pipe_roofline(perms, ms, clocks):
+    """Integer-multiplier roofline of a Poseidon2 kernel.  Measured on B200 (tools/int_roofline.cu,
+    profiles/r1_p2_iterate_ncu.txt): 32-bit integer multiplies issue only on the fma-heavy pipe,
+    64 lanes/clk/SM, IMAD 1 pass, IMAD.WIDE / IMAD.HI 2 passes.  A Montgomery product needs
+    IMAD.WIDE + IMAD + IMAD.HI = 5 passes; one permutation has 564 S-box products and 91 IMADs of
+    the internal diagonal => 2911 passes minimum."""
+    passes = 564 * 5 + 91
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 64 * 148 * mhz * 1e6 / passes / 1e9
+    ach = perms / (ms / 1e3) / 1e9 if ms else 0.0
+    return {"perms_per_launch": perms, "gperm_per_s": ach, "peak_gperm_per_s": peak, "frac": ach / peak,
+            "model": "fma-heavy pipe, 64 lanes/clk/SM x 148 SM x sm_max_mhz / 2911 multiplier passes per permutation"}
+
+
 def run_swirl(args):
     import torch
     import torch.distributed as dist
@@ -247,7 +261,7 @@ def run_swirl(args):
                 "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "peak_source": pk_kind, "traffic": None, "ms_per_launch": leaf_avg, "launches": leaf_n,
                 "note": "kernel is INT32-issue bound (Poseidon2), not HBM bound; see int_pipe",
-                "int_pipe": {"perms_per_launch": leaf_perms, "gperm_per_s": leaf_perms / (leaf_avg / 1e3) / 1e9 if leaf_avg else 0.0},
+                "int_pipe": int_pipe_roofline(leaf_perms, leaf_avg, clocks),
             },
             "phases_ms_per_step": {k: v[0] / args.steps for k, v in spans.items()},
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,

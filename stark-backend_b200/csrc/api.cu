@@ -82,6 +82,8 @@ int swirl_ctx_destroy(swirl_ctx* ctx) {
     timing_clear(ctx);
     if (ctx->tw_lo) cudaFree(ctx->tw_lo);
     if (ctx->tw_hi) cudaFree(ctx->tw_hi);
+    for (uint32_t* t : ctx->tw_lo_scaled)
+        if (t) cudaFree(t);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

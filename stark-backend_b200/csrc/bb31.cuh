@@ -48,6 +48,28 @@ __host__ __device__ __forceinline__ uint32_t reduce(uint64_t x) {
 __host__ __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return reduce((uint64_t)a * b); }
 __host__ __device__ __forceinline__ uint32_t sqr(uint32_t a) { return mul(a, a); }
 
+// Signed Montgomery product a*b*2^-32 (mod p) for ANY int32 inputs: x = a*b, q = lo(x)*p^-1,
+// r = hi(x) - hi(q*p); |r| <= |a||b|/2^32 + p/2, so it is closed on int32 and needs no correction
+// between chained products.  IMAD.WIDE + IMAD + IMAD.HI + IADD: 5 fma-heavy passes, 1 alu op.
+__host__ __device__ __forceinline__ int32_t smul(int32_t a, int32_t b) {
+    const int64_t x = (int64_t)a * b;
+    const int32_t q = (int32_t)((uint32_t)x * PINV);
+#ifdef __CUDA_ARCH__
+    return (int32_t)(x >> 32) - __mulhi(q, (int32_t)P);
+#else
+    return (int32_t)(x >> 32) - (int32_t)(((int64_t)q * (int32_t)P) >> 32);
+#endif
+}
+// v in (-p, p) -> canonical [0, p): one VIADDMNMX
+__host__ __device__ __forceinline__ uint32_t canon(int32_t v) {
+    const uint32_t u = (uint32_t)v, w = u + P;
+    return u < w ? u : w;
+}
+// (u - v) * w for canonical u, v, w: the difference is used unreduced (butterfly lower leg)
+__host__ __device__ __forceinline__ uint32_t mul_diff(uint32_t u, uint32_t v, uint32_t w) {
+    return canon(smul((int32_t)(u - v), (int32_t)w));
+}
+
 __host__ __device__ __forceinline__ uint32_t halve(uint32_t a) {
     // (a + (a odd ? p : 0)) / 2 ; a + p < 2^32
     return (a + ((a & 1u) ? P : 0u)) >> 1;

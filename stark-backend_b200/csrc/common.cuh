@@ -25,9 +25,10 @@ struct swirl_ctx {
     //   tw_hi[i] = W^(i * 2^14)   (i < 2^13)   == powers of the 2^13-th root of unity
     uint32_t* tw_lo = nullptr;
     uint32_t* tw_hi = nullptr;
+    uint32_t* tw_lo_scaled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // tw_lo * 2^-l, built on demand
     uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
     int ntt_max_log_radix = 11;               // largest single-pass radix (log2)
-    size_t ntt_scratch_bytes = size_t(48) << 20;  // inter-pass scratch per column group (L2 resident)
+    size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)
     // optional per-kernel-family CUDA-event timing (bench.py's roofline numbers)
     bool timing = false;
     struct TimedSpan {

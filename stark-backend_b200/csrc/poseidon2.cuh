@@ -93,7 +93,9 @@ __host__ __device__ __forceinline__ void internal_linear(uint32_t s[16]) {
     s[15] = bb::sub(sum, bb::mul(s[15], INV_2_27));
 }
 
-__host__ __device__ __forceinline__ void permute(uint32_t s[16]) {
+// First-generation permutation (every value canonical, unsigned Montgomery products); kept as the
+// in-library cross-check of p2v2::permute (tools/p2_bench.cu compares them on device).
+__host__ __device__ __forceinline__ void permute_v1(uint32_t s[16]) {
     external_linear(s);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -114,4 +116,11 @@ __host__ __device__ __forceinline__ void permute(uint32_t s[16]) {
     }
 }
 
+}  // namespace p2
+
+#include "poseidon2_v2.cuh"
+
+namespace p2 {
+// The permutation every kernel and the host transcript use (3.85 vs 2.89 Gperm/s for v1 on B200).
+__host__ __device__ __forceinline__ void permute(uint32_t s[16]) { p2v2::permute(s); }
 }  // namespace p2

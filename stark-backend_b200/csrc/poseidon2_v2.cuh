@@ -52,26 +52,8 @@ static const int32_t H_EXT_TERM[80] = {P2_EXT_TERM_VALUES Z16};
 #define P2V2_RC_TERM(i) H_EXT_TERM[i]
 #endif
 
-__host__ __device__ __forceinline__ int32_t mulhi_s32(int32_t a, int32_t b) {
-#ifdef __CUDA_ARCH__
-    return __mulhi(a, b);
-#else
-    return (int32_t)(((int64_t)a * b) >> 32);
-#endif
-}
-
-// signed Montgomery product: a*b*2^-32 (mod p), any int32 inputs, |r| <= |a||b|/2^32 + p/2
-__host__ __device__ __forceinline__ int32_t smul(int32_t a, int32_t b) {
-    const int64_t x = (int64_t)a * b;
-    const int32_t q = (int32_t)((uint32_t)x * bb::PINV);
-    return (int32_t)(x >> 32) - mulhi_s32(q, P);
-}
-
-// v in (-p, p) -> canonical [0, p)
-__host__ __device__ __forceinline__ uint32_t canon(int32_t v) {
-    const uint32_t u = (uint32_t)v, w = u + bb::P;
-    return u < w ? u : w;
-}
+using bb::canon;
+using bb::smul;
 
 // s in [-p, p) (state word plus signed round constant) -> s^7 canonical
 __host__ __device__ __forceinline__ uint32_t sbox7(int32_t s) {
@@ -103,7 +85,7 @@ __host__ __device__ __forceinline__ void external_linear_rc(uint32_t s[16], cons
 #pragma unroll
     for (int j = 0; j < 4; j++) t[j] = bb::add(bb::add(s[j], s[4 + j]), bb::add(s[8 + j], s[12 + j]));
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = s[i] + t[i & 3] + (uint32_t)rc[i];  // [0,p) + [0,p) + [-p,0)
+    for (int i = 0; i < 16; i++) s[i] = bb::add(s[i], t[i & 3]) + (uint32_t)rc[i];  // [0,p) + [-p,0)
 }
 
 // x * 2^-k for canonical x, 1 <= k <= 27:  (x >> k) - 15 * 2^(27-k) * (x mod 2^k), in (-p, 2^30]

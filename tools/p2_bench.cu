@@ -10,14 +10,15 @@
 
 template <int V>
 __device__ __forceinline__ void perm(uint32_t s[16]) {
-    if (V == 0) p2::permute(s);
+    if (V == 0) p2::permute_v1(s);
     if (V == 1) p2v2::permute(s);
 }
 
 // every thread iterates the permutation `iters` times on its own state (issue-bound measurement)
 template <int V>
-__global__ void __launch_bounds__(256) iterate(uint32_t* states, int iters) {
+__global__ void __launch_bounds__(256) iterate(uint32_t* states, int iters, long long* cyc) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t0 = clock64();
     uint4* p = reinterpret_cast<uint4*>(states + i * 16);
     uint4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];
     uint32_t s[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(256) iterate(uint32_t* states, int iters) {
     p[1] = make_uint4(s[4], s[5], s[6], s[7]);
     p[2] = make_uint4(s[8], s[9], s[10], s[11]);
     p[3] = make_uint4(s[12], s[13], s[14], s[15]);
+    if (cyc && threadIdx.x == 0) cyc[blockIdx.x] = clock64() - t0;
 }
 
 template <int V>
@@ -34,13 +36,15 @@ double run(const char* name, const std::vector<uint32_t>& init, std::vector<uint
     uint32_t* d;
     cudaMalloc(&d, n * 64);
     cudaMemcpy(d, init.data(), n * 64, cudaMemcpyHostToDevice);
-    iterate<V><<<n / 256, 256>>>(d, 2);
+    long long* cyc;
+    cudaMalloc(&cyc, (n / 256) * 8);
+    iterate<V><<<n / 256, 256>>>(d, 4 * iters, nullptr);  // warm the clocks
     cudaMemcpy(d, init.data(), n * 64, cudaMemcpyHostToDevice);
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     cudaEventRecord(a);
-    iterate<V><<<n / 256, 256>>>(d, iters);
+    iterate<V><<<n / 256, 256>>>(d, iters, cyc);
     cudaEventRecord(b);
     cudaError_t e = cudaDeviceSynchronize();
     float ms;
@@ -49,8 +53,13 @@ double run(const char* name, const std::vector<uint32_t>& init, std::vector<uint
     cudaMemcpy(out.data(), d, n * 64, cudaMemcpyDeviceToHost);
     cudaFree(d);
     double gps = (double)n * iters / (ms * 1e-3) / 1e9;
-    printf("{\"impl\": \"%s\", \"threads_per_sm\": %d, \"gperm_per_s\": %.3f, \"ms\": %.3f, \"err\": \"%s\"}\n", name, threads_per_sm, gps, ms,
-           cudaGetErrorString(e));
+    std::vector<long long> hc(n / 256);
+    cudaMemcpy(hc.data(), cyc, (n / 256) * 8, cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (auto c : hc) mx = c > mx ? c : mx;
+    cudaFree(cyc);
+    printf("{\"impl\": \"%s\", \"threads_per_sm\": %d, \"gperm_per_s\": %.3f, \"ms\": %.3f, \"clk_per_perm_per_sm\": %.2f, \"eff_mhz\": %.0f, \"err\": \"%s\"}\n", name, threads_per_sm, gps, ms,
+           (double)mx / ((double)threads_per_sm * iters), (double)mx / (ms * 1e3), cudaGetErrorString(e));
     return gps;
 }
 
@@ -58,7 +67,7 @@ int main() {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     if (sms <= 0) return 1;
-    const int iters = 64;
+    const int iters = 256;
     for (int tps : {512, 1024, 2048}) {
         const size_t n = (size_t)tps * sms;
         std::vector<uint32_t> init(n * 16), o0, o1;
