@@ -35,6 +35,8 @@ extern "C" {
 #define SWIRL_ERR_LAYOUT 10002      /* StackedPcsError::Layout* (prover/stacked_pcs.rs:160-174) */
 #define SWIRL_ERR_UNSUPPORTED 10003
 #define SWIRL_ERR_NO_DEVICE 10004
+#define SWIRL_ERR_NONZERO_ROOT_SUM 10005 /* LogupZerocheckError::NonZeroRootSum (fractional_sumcheck_gkr.rs:88-91) */
+#define SWIRL_ERR_POW 10006              /* no proof-of-work witness exists in the field */
 
 typedef struct swirl_ctx swirl_ctx; /* one per (device, stream); reference: GpuDeviceCtx, cuda-common/src/stream.rs:132-151 */
 typedef struct swirl_pcs swirl_pcs; /* reference: StackedPcsDataGpu, cuda-backend/src/stacked_pcs.rs:30-46 */
@@ -113,6 +115,38 @@ int swirl_matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t heig
  * returns *a* witness; the smallest one is among its admissible answers). */
 int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], int bits, uint32_t min_w,
                        uint32_t max_w, uint32_t* h_witness);
+
+/* ---- Fiat–Shamir transcript (reference: FiatShamirTranscript, transcript/traits.rs:11-90 over
+ *      DuplexSponge, transcript/duplex_sponge.rs:16-115).  The struct is the reference's
+ *      DeviceSpongeState (cuda-backend/cuda/src/sponge.cu:13-17): 16 Montgomery state words,
+ *      absorb_idx in [0,8), sample_idx in [0,8].  All-zero = a fresh transcript.  Host-resident;
+ *      the phase-level prover entry points below read and advance it. -------------------------- */
+typedef struct {
+    uint32_t state[16];
+    uint32_t absorb_idx;
+    uint32_t sample_idx;
+} swirl_transcript;
+int swirl_transcript_observe(swirl_transcript* ts, const uint32_t* words, size_t n); /* Montgomery words */
+int swirl_transcript_sample(swirl_transcript* ts, uint32_t* out, size_t n);
+int swirl_transcript_sample_bits(swirl_transcript* ts, int bits, uint32_t* out);
+/* check_witness (traits.rs:63-69): *ok = 1 iff the canonical witness passes; advances the transcript. */
+int swirl_transcript_check_witness(swirl_transcript* ts, int bits, uint32_t witness, int* ok);
+/* grind (traits.rs:71-86): finds the smallest canonical witness, observes it, writes it (canonical). */
+int swirl_transcript_grind(swirl_ctx* ctx, swirl_transcript* ts, int bits, uint32_t* witness);
+
+/* ---- phase level: LogUp-GKR fractional sumcheck (reference: fractional_sumcheck,
+ *      prover/logup_zerocheck/fractional_sumcheck_gkr.rs:60-213; GPU fractional_sumcheck_gpu,
+ *      cuda-backend/src/logup_zerocheck/fractional.rs:649-) --------------------------------------
+ * d_leaves: 2^log_n fractions Frac<EF> = {p[4], q[4]} (32 bytes, repr(C), :29-35), device.
+ * Outputs (host, Montgomery words):
+ *   h_frac_sum[8]              (p0, q0) root of the fraction tree
+ *   h_claims[log_n][16]        GkrLayerClaims {p_xi_0, q_xi_0, p_xi_1, q_xi_1} per layer
+ *   h_polys[sum_{j<log_n} j][12]  s(1), s(2), s(3) per sumcheck round, layer-major (may be NULL iff log_n == 1)
+ *   h_xi[log_n][4]             the final evaluation point xi
+ * Returns SWIRL_ERR_NONZERO_ROOT_SUM when assert_zero is set and the numerator sum is not zero. */
+int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves, int log_n,
+                                  int assert_zero, uint32_t h_frac_sum[8], uint32_t* h_claims,
+                                  uint32_t* h_polys, uint32_t* h_xi);
 
 /* ---- phase level: TraceCommitter::commit (hal.rs:84-87) ------------------------------------- */
 

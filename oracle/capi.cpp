@@ -6,6 +6,7 @@
 #include <stdexcept>
 
 #include "commit.hpp"
+#include "gkr.hpp"
 #include "transcript.hpp"
 
 using namespace orc;
@@ -260,4 +261,71 @@ uint32_t orc_sponge_grind(uint32_t* st, int bits, uint32_t start) {
     return w.v;
 }
 
+
+// ---- LogUp-GKR fractional sumcheck ----------------------------------------------------------------
+// Flat formats as in include/swirl_b200.h (swirl_gkr_fractional_sumcheck).  Returns 0 ok,
+// 2 NonZeroRootSum, 1 other error.
+int orc_gkr_prove(uint32_t* st, const uint32_t* leaves, int log_n, int assert_zero, uint32_t* frac_sum,
+                  uint32_t* claims, uint32_t* polys, uint32_t* xi) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        std::vector<Frac> ev(size_t(1) << log_n);
+        memcpy(ev.data(), leaves, ev.size() * sizeof(Frac));
+        std::vector<EF> xi_v;
+        FracSumcheckProof pr = fractional_sumcheck(ts, ev, assert_zero != 0, &xi_v);
+        memcpy(frac_sum, &pr.frac_sum_p, 16);
+        memcpy(frac_sum + 4, &pr.frac_sum_q, 16);
+        for (size_t i = 0; i < pr.claims_per_layer.size(); i++) memcpy(claims + 16 * i, &pr.claims_per_layer[i], 64);
+        size_t off = 0;
+        for (auto& layer : pr.sumcheck_polys)
+            for (auto& s : layer) {
+                memcpy(polys + 12 * off, s.data(), 48);
+                off++;
+            }
+        for (size_t i = 0; i < xi_v.size(); i++) memcpy(xi + 4 * i, &xi_v[i], 16);
+        store_sponge(ts, st);
+        return 0;
+    } catch (const NonZeroRootSum&) {
+        return 2;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+// Returns 1 when the verifier accepts (then numer/denom/xi are filled), 0 otherwise.
+int orc_gkr_verify(uint32_t* st, int total_rounds, const uint32_t* frac_sum, const uint32_t* claims,
+                   const uint32_t* polys, uint32_t* numer, uint32_t* denom, uint32_t* xi) {
+    DuplexSponge ts = load_sponge(st);
+    FracSumcheckProof pr;
+    memcpy(&pr.frac_sum_p, frac_sum, 16);
+    memcpy(&pr.frac_sum_q, frac_sum + 4, 16);
+    pr.claims_per_layer.resize(total_rounds);
+    for (int i = 0; i < total_rounds; i++) memcpy(&pr.claims_per_layer[i], claims + 16 * i, 64);
+    size_t off = 0;
+    for (int round = 1; round < total_rounds; round++) {
+        std::vector<std::array<EF, 3>> layer(round);
+        for (int sr = 0; sr < round; sr++) memcpy(layer[sr].data(), polys + 12 * (off++), 48);
+        pr.sumcheck_polys.push_back(layer);
+    }
+    EF n, d;
+    std::vector<EF> xi_v;
+    if (!verify_gkr(pr, ts, total_rounds, &n, &d, &xi_v)) return 0;
+    memcpy(numer, &n, 16);
+    memcpy(denom, &d, 16);
+    for (size_t i = 0; i < xi_v.size(); i++) memcpy(xi + 4 * i, &xi_v[i], 16);
+    store_sponge(ts, st);
+    return 1;
+}
+// MLE evaluation of a table of 2^n EF values at an EF point (poly_common.rs:42-54)
+void orc_eval_mle_evals_at_point(const uint32_t* evals, int n, const uint32_t* x, uint32_t* out) {
+    std::vector<EF> e(size_t(1) << n);
+    memcpy(e.data(), evals, e.size() * 16);
+    size_t len = e.size();
+    for (int j = n; j-- > 0;) {
+        EF xj;
+        memcpy(&xj, x + 4 * j, 16);
+        len >>= 1;
+        for (size_t i = 0; i < len; i++) e[i] = e[i] * (ef_one() - xj) + e[len + i] * xj;
+    }
+    memcpy(out, &e[0], 16);
+}
 }  // extern "C"

@@ -5,6 +5,7 @@ CUDA device."""
 from .lib import load_library, library_path, SwirlError  # noqa: F401
 from .backend import (  # noqa: F401
     B200Device,
+    Transcript,
     DeviceMatrix,
     PcsParams,
     StackedLayout,

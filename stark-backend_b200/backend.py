@@ -203,6 +203,47 @@ class StackedPcsData:
             pass
 
 
+class Transcript:
+    """reference: DuplexSponge as FiatShamirTranscript (transcript/duplex_sponge.rs:16-115,
+    transcript/traits.rs:11-90).  Host-resident POD state (`swirl_transcript`)."""
+
+    def __init__(self, words18=None):
+        self.lib = _lib.load_library()
+        self.c = _lib.TranscriptC()
+        if words18 is not None:
+            self.load(words18)
+
+    def load(self, words18):
+        for i in range(16):
+            self.c.state[i] = int(words18[i])
+        self.c.absorb_idx, self.c.sample_idx = int(words18[16]), int(words18[17])
+
+    def words(self):
+        return np.array(list(self.c.state) + [self.c.absorb_idx, self.c.sample_idx], dtype=np.uint32)
+
+    def observe(self, mont_words):
+        a = np.ascontiguousarray(mont_words, dtype=np.uint32).reshape(-1)
+        check(self.lib.swirl_transcript_observe(C.byref(self.c), a.ctypes.data, a.size))
+
+    def sample(self, n=1):
+        out = np.zeros(n, dtype=np.uint32)
+        check(self.lib.swirl_transcript_sample(C.byref(self.c), out.ctypes.data, n))
+        return out
+
+    def sample_ext(self):
+        return self.sample(4)
+
+    def sample_bits(self, bits):
+        v = C.c_uint32()
+        check(self.lib.swirl_transcript_sample_bits(C.byref(self.c), bits, C.byref(v)))
+        return int(v.value)
+
+    def check_witness(self, bits, witness):
+        ok = C.c_int()
+        check(self.lib.swirl_transcript_check_witness(C.byref(self.c), bits, int(witness), C.byref(ok)))
+        return bool(ok.value)
+
+
 class B200Device:
     """reference: GpuDevice (cuda-backend/src/device.rs:52-110) — one CUDA device, one stream."""
 
@@ -341,6 +382,25 @@ class B200Device:
         w = C.c_uint32()
         check(self.lib.swirl_sponge_grind(self.ctx, st, bits, min_w, max_w, C.byref(w)))
         return None if w.value == 0xFFFFFFFF else int(w.value)
+
+    def transcript_grind(self, ts, bits):
+        w = C.c_uint32()
+        check(self.lib.swirl_transcript_grind(self.ctx, C.byref(ts.c), bits, C.byref(w)))
+        return int(w.value)
+
+    # -- LogUp-GKR (fractional_sumcheck, fractional_sumcheck_gkr.rs:60-213) ---------------------------
+    def gkr_fractional_sumcheck(self, ts, leaves, log_n, assert_zero=True):
+        """leaves: CUDA int32 tensor of 2^log_n Frac<EF> (8 words each).  Returns dict(frac_sum,
+        claims[log_n,16], polys[log_n(log_n-1)/2,12], xi[log_n,4]) of Montgomery words."""
+        n_polys = log_n * (log_n - 1) // 2
+        frac_sum = np.zeros(8, np.uint32)
+        claims = np.zeros((log_n, 16), np.uint32)
+        polys = np.zeros((max(n_polys, 1), 12), np.uint32)
+        xi = np.zeros((log_n, 4), np.uint32)
+        self._sync_torch()
+        check(self.lib.swirl_gkr_fractional_sumcheck(self.ctx, C.byref(ts.c), leaves.data_ptr(), log_n, 1 if assert_zero else 0,
+                                                     frac_sum.ctypes.data, claims.ctypes.data, polys.ctypes.data, xi.ctypes.data))
+        return dict(frac_sum=frac_sum, claims=claims, polys=polys[:n_polys], xi=xi)
 
     # -- TraceCommitter::commit ---------------------------------------------------------------
     def commit(self, params, traces):

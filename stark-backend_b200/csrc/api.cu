@@ -84,6 +84,7 @@ int swirl_ctx_destroy(swirl_ctx* ctx) {
     if (ctx->tw_hi) cudaFree(ctx->tw_hi);
     for (uint32_t* t : ctx->tw_lo_scaled)
         if (t) cudaFree(t);
+    round_scratch_free(ctx);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

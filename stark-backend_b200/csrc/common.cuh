@@ -26,6 +26,7 @@ struct swirl_ctx {
     uint32_t* tw_lo = nullptr;
     uint32_t* tw_hi = nullptr;
     uint32_t* tw_lo_scaled[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // tw_lo * 2^-l, built on demand
+    void* round_scratch = nullptr;  // swirl::RoundScratch (ext.cuh), created on first use
     uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
     int ntt_max_log_radix = 11;               // largest single-pass radix (log2)
     size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)

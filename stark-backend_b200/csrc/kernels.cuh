@@ -18,6 +18,9 @@ int matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, si
                      size_t query_stride, int log_rpq, const uint32_t* d_indices, size_t num_queries,
                      uint32_t* d_out);
 
+// ---- sponge.cu ---------------------------------------------------------------------------
+void round_scratch_free(swirl_ctx* ctx);
+
 // ---- ntt.cu ------------------------------------------------------------------------------
 int ntt_init_twiddles(swirl_ctx* ctx);
 // Natural-order (i)DFT of `cols` contiguous columns of length 2^log_n, in place.

@@ -88,3 +88,106 @@ extern "C" int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], in
     dev_free(ctx, d_res);
     return rc;
 }
+
+// ---- host transcript entry points (transcript.hpp) --------------------------------------------
+#include "ext.cuh"
+#include "transcript.hpp"
+
+namespace swirl {
+
+int round_scratch_get(swirl_ctx* ctx, RoundScratch** out) {
+    if (!ctx->round_scratch) {
+        RoundScratch* rs = new RoundScratch();
+        rs->max_blocks = 8192;
+        SWIRL_CUDA(cudaMalloc((void**)&rs->d_partials, (size_t)rs->max_blocks * 64 * sizeof(uint32_t)));
+        SWIRL_CUDA(cudaMalloc((void**)&rs->d_ticket, sizeof(unsigned int)));
+        SWIRL_CUDA(cudaMemset(rs->d_ticket, 0, sizeof(unsigned int)));
+        SWIRL_CUDA(cudaHostAlloc((void**)&rs->h_result, 65536, cudaHostAllocMapped));
+        SWIRL_CUDA(cudaHostGetDevicePointer((void**)&rs->d_result, rs->h_result, 0));
+        ctx->round_scratch = rs;
+    }
+    *out = (RoundScratch*)ctx->round_scratch;
+    return 0;
+}
+
+void round_scratch_free(swirl_ctx* ctx) {
+    RoundScratch* rs = (RoundScratch*)ctx->round_scratch;
+    if (!rs) return;
+    cudaFree(rs->d_partials);
+    cudaFree(rs->d_ticket);
+    cudaFreeHost(rs->h_result);
+    delete rs;
+    ctx->round_scratch = nullptr;
+}
+
+int transcript_grind(swirl_ctx* ctx, swirl_transcript* t, int bits, uint32_t* w_mont) {
+    *w_mont = 0;
+    if (bits == 0) return 0;  // traits.rs:78-80: no transcript interaction
+    SWIRL_REQUIRE(bits > 0 && bits < 31, "pow bits");
+    uint32_t w = 0xffffffffu;
+    if (bits <= 10) {
+        // expected 2^bits scalar permutations (~1 us each) beat a launch + sync
+        for (uint32_t c = 0; c < bb::P; c++) {
+            swirl_transcript probe = *t;
+            if (Transcript(&probe).check_witness(bits, bb::to_mont(c))) {
+                w = c;
+                break;
+            }
+        }
+    } else {
+        uint32_t st[18];
+        for (int i = 0; i < 16; i++) st[i] = t->state[i];
+        st[16] = t->absorb_idx;
+        st[17] = t->sample_idx;
+        SWIRL_TRY(swirl_sponge_grind(ctx, st, bits, 0, bb::P, &w));
+    }
+    if (w == 0xffffffffu) {
+        set_error("failed to find proof-of-work witness");
+        return SWIRL_ERR_POW;
+    }
+    *w_mont = bb::to_mont(w);
+    if (!Transcript(t).check_witness(bits, *w_mont)) {
+        set_error("internal error: grind witness rejected");
+        return SWIRL_ERR_POW;
+    }
+    return 0;
+}
+
+}  // namespace swirl
+
+extern "C" int swirl_transcript_observe(swirl_transcript* ts, const uint32_t* words, size_t n) {
+    SWIRL_REQUIRE(ts && (words || n == 0), "null argument");
+    SWIRL_REQUIRE(ts->absorb_idx < 8 && ts->sample_idx <= 8, "sponge indices");
+    Transcript tr(ts);
+    for (size_t i = 0; i < n; i++) {
+        SWIRL_REQUIRE(words[i] < bb::P, "non-canonical Montgomery word");
+        tr.observe(words[i]);
+    }
+    return 0;
+}
+extern "C" int swirl_transcript_sample(swirl_transcript* ts, uint32_t* out, size_t n) {
+    SWIRL_REQUIRE(ts && (out || n == 0), "null argument");
+    SWIRL_REQUIRE(ts->absorb_idx < 8 && ts->sample_idx <= 8, "sponge indices");
+    Transcript tr(ts);
+    for (size_t i = 0; i < n; i++) out[i] = tr.sample();
+    return 0;
+}
+extern "C" int swirl_transcript_sample_bits(swirl_transcript* ts, int bits, uint32_t* out) {
+    SWIRL_REQUIRE(ts && out, "null argument");
+    SWIRL_REQUIRE(bits >= 0 && bits < 31, "bits");
+    *out = Transcript(ts).sample_bits(bits);
+    return 0;
+}
+extern "C" int swirl_transcript_check_witness(swirl_transcript* ts, int bits, uint32_t witness, int* ok) {
+    SWIRL_REQUIRE(ts && ok, "null argument");
+    SWIRL_REQUIRE(bits >= 0 && bits < 31 && witness < bb::P, "bits / witness");
+    *ok = Transcript(ts).check_witness(bits, bb::to_mont(witness)) ? 1 : 0;
+    return 0;
+}
+extern "C" int swirl_transcript_grind(swirl_ctx* ctx, swirl_transcript* ts, int bits, uint32_t* witness) {
+    SWIRL_REQUIRE(ctx && ts && witness, "null argument");
+    uint32_t wm = 0;
+    SWIRL_TRY(transcript_grind(ctx, ts, bits, &wm));
+    *witness = bb::from_mont(wm);
+    return 0;
+}

@@ -27,6 +27,12 @@ class PcsParamsC(C.Structure):
     _fields_ = [("l_skip", C.c_int32), ("n_stack", C.c_int32), ("log_blowup", C.c_int32), ("k_whir", C.c_int32)]
 
 
+class TranscriptC(C.Structure):
+    """swirl_transcript == the reference's DeviceSpongeState (cuda-backend/cuda/src/sponge.cu:13-17)."""
+
+    _fields_ = [("state", C.c_uint32 * 16), ("absorb_idx", C.c_uint32), ("sample_idx", C.c_uint32)]
+
+
 class MatrixC(C.Structure):
     _fields_ = [("data", C.c_void_p), ("height", C.c_uint64), ("width", C.c_uint64)]
 
@@ -57,6 +63,12 @@ PROTOTYPES = {
     "swirl_merkle_query_proofs": (_i, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "swirl_matrix_open_rows": (_i, [_vp, _vp, _sz, _sz, _sz, _i, _vp, _sz, _vp]),
     "swirl_sponge_grind": (_i, [_vp, _vp, _i, _u32, _u32, C.POINTER(_u32)]),
+    "swirl_transcript_observe": (_i, [C.POINTER(TranscriptC), _vp, _sz]),
+    "swirl_transcript_sample": (_i, [C.POINTER(TranscriptC), _vp, _sz]),
+    "swirl_transcript_sample_bits": (_i, [C.POINTER(TranscriptC), _i, C.POINTER(_u32)]),
+    "swirl_transcript_check_witness": (_i, [C.POINTER(TranscriptC), _i, _u32, C.POINTER(_i)]),
+    "swirl_transcript_grind": (_i, [_vp, C.POINTER(TranscriptC), _i, C.POINTER(_u32)]),
+    "swirl_gkr_fractional_sumcheck": (_i, [_vp, C.POINTER(TranscriptC), _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "swirl_commit": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_commit_host": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_pcs_free": (_i, [_vp, _vp]),

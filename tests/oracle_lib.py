@@ -40,6 +40,9 @@ class Oracle:
         L.orc_to_canonical_vec.argtypes = [_vp, _sz]
         L.orc_ef_mul.argtypes = [_vp, _vp, _vp]
         L.orc_ef_inv.argtypes = [_vp, _vp]
+        L.orc_gkr_prove.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]
+        L.orc_gkr_verify.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.orc_eval_mle_evals_at_point.argtypes = [_vp, _i, _vp, _vp]
 
     # ---- field ----
     def to_mont(self, x):
@@ -199,6 +202,36 @@ class Oracle:
     def sponge_grind(self, st, bits, start=0):
         return int(self.L.orc_sponge_grind(_p(st), bits, start))
 
+
+    # ---- LogUp-GKR ----
+    def gkr_prove(self, sponge, leaves, log_n, assert_zero):
+        """leaves: uint32[2^log_n * 8] (Frac<EF> = p[4], q[4]).  Returns dict or raises
+        ValueError('NonZeroRootSum').  `sponge` (uint32[18]) is advanced in place."""
+        leaves = np.ascontiguousarray(leaves, np.uint32)
+        n_polys = log_n * (log_n - 1) // 2
+        out = dict(frac_sum=np.zeros(8, np.uint32), claims=np.zeros((log_n, 16), np.uint32),
+                   polys=np.zeros((max(n_polys, 1), 12), np.uint32), xi=np.zeros((log_n, 4), np.uint32))
+        rc = self.L.orc_gkr_prove(_p(sponge), _p(leaves), log_n, int(assert_zero), _p(out["frac_sum"]),
+                                  _p(out["claims"]), _p(out["polys"]), _p(out["xi"]))
+        if rc == 2:
+            raise ValueError("NonZeroRootSum")
+        assert rc == 0
+        out["polys"] = out["polys"][:n_polys]
+        return out
+
+    def gkr_verify(self, sponge, log_n, proof):
+        numer, denom = np.zeros(4, np.uint32), np.zeros(4, np.uint32)
+        xi = np.zeros((log_n, 4), np.uint32)
+        polys = np.ascontiguousarray(proof["polys"] if len(proof["polys"]) else np.zeros((1, 12)), np.uint32)
+        ok = self.L.orc_gkr_verify(_p(sponge), log_n, _p(np.ascontiguousarray(proof["frac_sum"], np.uint32)),
+                                   _p(np.ascontiguousarray(proof["claims"], np.uint32)), _p(polys), _p(numer), _p(denom), _p(xi))
+        return bool(ok), numer, denom, xi
+
+    def eval_mle_evals_at_point(self, evals, n, x):
+        out = np.zeros(4, np.uint32)
+        self.L.orc_eval_mle_evals_at_point(_p(np.ascontiguousarray(evals, np.uint32)), n,
+                                           _p(np.ascontiguousarray(x, np.uint32)), _p(out))
+        return out
 
 def split_layers(flat, qs):
     out, off, n = [], 0, qs
