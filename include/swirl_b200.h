@@ -193,6 +193,33 @@ int swirl_stacked_layout(int l_skip, int log_stacked_height, size_t n_mats, cons
                          const int32_t* log_heights, uint64_t* out_width, uint64_t* out_n,
                          uint64_t* out_cols);
 
+/* ---- phase level: WHIR opening (reference: prove_whir_opening, prover/whir.rs:78-341; GPU
+ *      prove_whir_opening_gpu, cuda-backend/src/whir.rs:63-560; config: WhirConfig, config.rs:172-197) */
+typedef struct {
+    int32_t k;               /* folding factor, must equal the commitments' k_whir */
+    int32_t num_rounds;      /* WhirConfig::rounds.len(), <= 32 */
+    int32_t num_queries[32]; /* WhirRoundConfig::num_queries per round */
+    int32_t mu_pow_bits;
+    int32_t query_phase_pow_bits;
+    int32_t folding_pow_bits;
+} swirl_whir_config;
+/* Length in 32-bit words of the flat WhirProof for commitments of the given stacked widths.
+ * Layout (field elements as Montgomery words, R = num_rounds, m = l_skip + n_stack), in the field
+ * order of WhirProof (proof.rs):
+ *   mu_pow_witness[1] | whir_sumcheck_polys[R*k][2][4] | codeword_commits[R-1][8] | ood_values[R-1][4]
+ *   | folding_pow_witnesses[R*k] | query_phase_pow_witnesses[R]
+ *   | initial_round_opened_rows: per commit, per query [2^k][width]
+ *   | initial_round_merkle_proofs: per commit, per query [m + log_blowup - k][8]
+ *   | codeword_opened_values: per round r = 1..R-1, per query [2^k][4]
+ *   | codeword_merkle_proofs: per round r = 1..R-1, per query [m + log_blowup - r - k][8]
+ *   | final_poly[2^(m - R*k)][4].   Returns 0 for an invalid configuration. */
+size_t swirl_whir_proof_words(const swirl_pcs_params* params, const swirl_whir_config* cfg, size_t n_commits,
+                              const uint64_t* widths);
+/* Opens all columns of the commitments (common main first, then cached / preprocessed, as in
+ * WhirProver::prove_whir) at the point h_u (m EF, = u_cube of cpu_backend.rs:203-210). */
+int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl_whir_config* cfg, const swirl_pcs* const* pcs,
+                    size_t n_commits, const uint32_t* h_u, uint32_t* h_proof, size_t proof_words);
+
 #ifdef __cplusplus
 }
 #endif

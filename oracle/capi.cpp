@@ -8,6 +8,7 @@
 #include "commit.hpp"
 #include "gkr.hpp"
 #include "transcript.hpp"
+#include "whir.hpp"
 
 using namespace orc;
 
@@ -327,5 +328,94 @@ void orc_eval_mle_evals_at_point(const uint32_t* evals, int n, const uint32_t* x
         for (size_t i = 0; i < len; i++) e[i] = e[i] * (ef_one() - xj) + e[len + i] * xj;
     }
     memcpy(out, &e[0], 16);
+}
+
+// ---- WHIR ------------------------------------------------------------------------------------------
+static WhirConfig mk_whir_cfg(int k, int rounds, const int32_t* num_queries, int mu_pow, int query_pow, int fold_pow) {
+    WhirConfig c;
+    c.k = k;
+    c.num_queries.assign(num_queries, num_queries + rounds);
+    c.mu_pow_bits = mu_pow;
+    c.query_phase_pow_bits = query_pow;
+    c.folding_pow_bits = fold_pow;
+    return c;
+}
+size_t orc_whir_proof_words(int m, int log_blowup, int k, int rounds, const int32_t* num_queries, size_t n_commits,
+                            const uint64_t* widths) {
+    std::vector<size_t> w(widths, widths + n_commits);
+    return whir_proof_words(m, log_blowup, mk_whir_cfg(k, rounds, num_queries, 0, 0, 0), w);
+}
+// Each commit is given by its stacked matrix (height x widths[i], column-major).  roots: n_commits x 8.
+int orc_whir_prove(uint32_t* st, int l_skip, int log_blowup, int k, int rounds, const int32_t* num_queries, int mu_pow,
+                   int query_pow, int fold_pow, size_t n_commits, const uint32_t* const* mats, const uint64_t* widths,
+                   size_t height, const uint32_t* u, uint32_t* roots, uint32_t* proof_out) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        WhirConfig cfg = mk_whir_cfg(k, rounds, num_queries, mu_pow, query_pow, fold_pow);
+        std::vector<StackedPcsData> data(n_commits);
+        std::vector<const StackedPcsData*> ptrs;
+        for (size_t i = 0; i < n_commits; i++) {
+            data[i].matrix = ColMajor(height, widths[i]);
+            memcpy(data[i].matrix.values.data(), mats[i], height * widths[i] * 4);
+            data[i].tree = merkle_tree_new(rs_code_matrix(l_skip, log_blowup, data[i].matrix), size_t(1) << k);
+            Digest r = data[i].tree.root();
+            memcpy(roots + 8 * i, &r, 32);
+            ptrs.push_back(&data[i]);
+        }
+        const int m = log2_strict(height);
+        std::vector<EF> uv(m);
+        memcpy(uv.data(), u, (size_t)m * 16);
+        std::vector<uint32_t> pr = prove_whir_opening(ts, l_skip, log_blowup, cfg, ptrs, uv);
+        memcpy(proof_out, pr.data(), pr.size() * 4);
+        store_sponge(ts, st);
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+// openings[j] = MLE with coefficient table eval_to_coeff_rs_message(column j), evaluated at u
+void orc_whir_stacking_openings(int l_skip, const uint32_t* mat, size_t height, size_t width, const uint32_t* u,
+                                uint32_t* out) {
+    const int m = log2_strict(height);
+    for (size_t c = 0; c < width; c++) {
+        std::vector<F> x(height);
+        memcpy(x.data(), mat + c * height, height * 4);
+        eval_to_coeff_rs_message_inplace(l_skip, x.data(), height);
+        std::vector<EF> e(height);
+        for (size_t i = 0; i < height; i++) e[i] = ef_from(x[i]);
+        size_t len = height;
+        for (int j = m; j-- > 0;) {
+            EF xj;
+            memcpy(&xj, u + 4 * j, 16);
+            len >>= 1;
+            for (size_t i = 0; i < len; i++) e[i] = e[i] * (ef_one() - xj) + e[len + i] * xj;
+        }
+        memcpy(out + 4 * c, &e[0], 16);
+    }
+}
+int orc_whir_verify(uint32_t* st, int l_skip, int n_stack, int log_blowup, int k, int rounds, const int32_t* num_queries,
+                    int mu_pow, int query_pow, int fold_pow, const uint32_t* proof, size_t proof_words, size_t n_commits,
+                    const uint64_t* widths, const uint32_t* openings, const uint32_t* roots, const uint32_t* u) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        WhirConfig cfg = mk_whir_cfg(k, rounds, num_queries, mu_pow, query_pow, fold_pow);
+        std::vector<uint32_t> pr(proof, proof + proof_words);
+        std::vector<std::vector<EF>> so(n_commits);
+        std::vector<Digest> com(n_commits);
+        size_t off = 0;
+        for (size_t i = 0; i < n_commits; i++) {
+            so[i].resize(widths[i]);
+            memcpy(so[i].data(), openings + 4 * off, widths[i] * 16);
+            off += widths[i];
+            memcpy(&com[i], roots + 8 * i, 32);
+        }
+        std::vector<EF> uv(l_skip + n_stack);
+        memcpy(uv.data(), u, uv.size() * 16);
+        bool ok = verify_whir(ts, l_skip, n_stack, log_blowup, cfg, pr, so, com, uv);
+        if (ok) store_sponge(ts, st);
+        return ok ? 1 : 0;
+    } catch (const std::exception&) {
+        return 0;
+    }
 }
 }  // extern "C"

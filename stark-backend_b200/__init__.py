@@ -6,6 +6,7 @@ from .lib import load_library, library_path, SwirlError  # noqa: F401
 from .backend import (  # noqa: F401
     B200Device,
     Transcript,
+    WhirConfig,
     DeviceMatrix,
     PcsParams,
     StackedLayout,

@@ -203,6 +203,22 @@ class StackedPcsData:
             pass
 
 
+class WhirConfig:
+    """reference: WhirConfig / WhirRoundConfig (config.rs:172-197)."""
+
+    def __init__(self, k, num_queries, mu_pow_bits=0, query_phase_pow_bits=0, folding_pow_bits=0):
+        self.k, self.num_queries = int(k), [int(q) for q in num_queries]
+        self.mu_pow_bits, self.query_phase_pow_bits, self.folding_pow_bits = mu_pow_bits, query_phase_pow_bits, folding_pow_bits
+
+    def c(self):
+        c = _lib.WhirConfigC()
+        c.k, c.num_rounds = self.k, len(self.num_queries)
+        for i, q in enumerate(self.num_queries):
+            c.num_queries[i] = q
+        c.mu_pow_bits, c.query_phase_pow_bits, c.folding_pow_bits = self.mu_pow_bits, self.query_phase_pow_bits, self.folding_pow_bits
+        return c
+
+
 class Transcript:
     """reference: DuplexSponge as FiatShamirTranscript (transcript/duplex_sponge.rs:16-115,
     transcript/traits.rs:11-90).  Host-resident POD state (`swirl_transcript`)."""
@@ -401,6 +417,23 @@ class B200Device:
         check(self.lib.swirl_gkr_fractional_sumcheck(self.ctx, C.byref(ts.c), leaves.data_ptr(), log_n, 1 if assert_zero else 0,
                                                      frac_sum.ctypes.data, claims.ctypes.data, polys.ctypes.data, xi.ctypes.data))
         return dict(frac_sum=frac_sum, claims=claims, polys=polys[:n_polys], xi=xi)
+
+    # -- WHIR opening (prove_whir_opening, prover/whir.rs:78-341) -----------------------------------
+    def whir_open(self, ts, cfg, params, pcs_list, u):
+        """pcs_list: StackedPcsData (common main first).  u: (l_skip+n_stack, 4) Montgomery words.
+        Returns the flat WhirProof words (layout in include/swirl_b200.h)."""
+        cc, pc = cfg.c(), params.c()
+        widths = np.array([d.width for d in pcs_list], dtype=np.uint64)
+        n = int(self.lib.swirl_whir_proof_words(C.byref(pc), C.byref(cc), len(pcs_list), widths.ctypes.data))
+        if n == 0:
+            raise _lib.SwirlError(10001, "invalid WHIR configuration")
+        proof = np.zeros(n, dtype=np.uint32)
+        handles = (C.c_void_p * len(pcs_list))(*[d._h for d in pcs_list])
+        u = np.ascontiguousarray(u, dtype=np.uint32)
+        self._sync_torch()
+        check(self.lib.swirl_whir_open(self.ctx, C.byref(ts.c), C.byref(cc), handles, len(pcs_list), u.ctypes.data,
+                                       proof.ctypes.data, n))
+        return proof
 
     # -- TraceCommitter::commit ---------------------------------------------------------------
     def commit(self, params, traces):

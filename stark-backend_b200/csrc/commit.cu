@@ -15,19 +15,9 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "pcs.cuh"
 
 namespace swirl {
-
-struct LayoutCol {
-    uint64_t mat_idx, col_in_mat, col_idx, row_idx;
-    int log_height;
-};
-
-struct Layout {
-    int l_skip = 0;
-    uint64_t height = 0, width = 0;
-    std::vector<LayoutCol> cols;
-};
 
 // sorted = (width, log_height), descending log_height
 static int make_layout(int l_skip, int log_stacked_height, size_t n, const uint64_t* widths,
@@ -73,17 +63,6 @@ __global__ void expand_strided_kernel(const uint32_t* __restrict__ src, uint32_t
 }  // namespace swirl
 
 using namespace swirl;
-
-struct swirl_pcs {
-    swirl_pcs_params params{};
-    Layout layout;
-    uint64_t codeword_height = 0, query_stride = 0;
-    const uint32_t* stacked = nullptr;  // device; owned iff owns_stacked
-    bool owns_stacked = false;
-    uint32_t* codeword = nullptr;  // device, owned
-    uint32_t* layers = nullptr;    // device, owned
-    std::vector<uint32_t*> owned_traces;  // device copies made by swirl_commit_host
-};
 
 static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* traces, size_t n,
                        uint32_t h_root[8], swirl_pcs* pcs) {

@@ -30,6 +30,20 @@ int ntt_batch(swirl_ctx* ctx, uint32_t* d_data, int log_n, size_t cols, bool inv
 int rs_encode(swirl_ctx* ctx, const uint32_t* d_in, size_t in_stride, size_t H, size_t W, int l_skip,
               int log_blowup, uint32_t* d_out);
 
+// 2^l_skip chunk iDFT + subset-zeta of `cols` columns of height H (poly.rs:325-348), src -> dst.
+int chunk_coeffs(swirl_ctx* ctx, const uint32_t* src, size_t src_stride, uint32_t* dst, size_t dst_stride, size_t H,
+                 size_t cols, int l_skip);
+
+// ---- mle.cu ------------------------------------------------------------------------------
+struct TensorArgs {  // per variable b: the factor for bit b clear (w0) / set (w1), EF Montgomery words
+    uint32_t w0[28][4];
+    uint32_t w1[28][4];
+};
+int mle_tensor_table(swirl_ctx* ctx, const TensorArgs& t, int n_vars, uint32_t* d_out);
+int mle_zeta(swirl_ctx* ctx, uint32_t* d_data, size_t col_stride, int log_n, size_t cols, bool inverse);
+int ext_aos_to_soa(swirl_ctx* ctx, const uint32_t* aos, uint32_t* soa, size_t n, size_t col_stride);
+int ext_soa_to_aos(swirl_ctx* ctx, const uint32_t* soa, uint32_t* aos, size_t n, size_t col_stride);
+
 // ---- stacking.cu -------------------------------------------------------------------------
 struct StackCopy {  // one unstacked column -> its slot in the stacked matrix
     const uint32_t* src;  // device pointer to the column (height = 1 << log_height)

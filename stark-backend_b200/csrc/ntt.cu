@@ -629,6 +629,22 @@ int ntt_batch(swirl_ctx* ctx, uint32_t* d_data, int log_n, size_t cols, bool inv
     return rc;
 }
 
+int chunk_coeffs(swirl_ctx* ctx, const uint32_t* src, size_t src_stride, uint32_t* dst, size_t dst_stride, size_t H,
+                 size_t cols, int l_skip) {
+    SWIRL_REQUIRE(is_pow2(H), "height must be a power of two");
+    const int log_h = ilog2(H);
+    SWIRL_REQUIRE(l_skip >= 0 && l_skip <= log_h && l_skip <= 11, "l_skip");
+    if (cols == 0) return 0;
+    int log_te = std::min(log_h, 11);
+    if (log_te < l_skip) log_te = l_skip;
+    const size_t grid = cols << (log_h - log_te);
+    SWIRL_REQUIRE(grid < (size_t(1) << 31), "grid too large");
+    chunk_coeffs_kernel<<<(unsigned)grid, 256, size_t(4) << log_te, ctx->stream>>>(
+        src, src_stride, dst, dst_stride, log_h, l_skip, log_te, bb::inv(bb::to_mont(1u << l_skip)), ctx->tw_hi);
+    SWIRL_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int rs_encode(swirl_ctx* ctx, const uint32_t* d_in, size_t in_stride, size_t H, size_t W, int l_skip,
               int log_blowup, uint32_t* d_out) {
     SWIRL_REQUIRE(is_pow2(H), "stacked height must be a power of two");

@@ -33,6 +33,11 @@ class TranscriptC(C.Structure):
     _fields_ = [("state", C.c_uint32 * 16), ("absorb_idx", C.c_uint32), ("sample_idx", C.c_uint32)]
 
 
+class WhirConfigC(C.Structure):
+    _fields_ = [("k", C.c_int32), ("num_rounds", C.c_int32), ("num_queries", C.c_int32 * 32), ("mu_pow_bits", C.c_int32),
+                ("query_phase_pow_bits", C.c_int32), ("folding_pow_bits", C.c_int32)]
+
+
 class MatrixC(C.Structure):
     _fields_ = [("data", C.c_void_p), ("height", C.c_uint64), ("width", C.c_uint64)]
 
@@ -80,6 +85,8 @@ PROTOTYPES = {
     "swirl_pcs_codeword": (_vp, [_vp]),
     "swirl_pcs_layers": (_vp, [_vp]),
     "swirl_pcs_layout": (_u64, [_vp, _vp]),
+    "swirl_whir_proof_words": (_sz, [C.POINTER(PcsParamsC), C.POINTER(WhirConfigC), _sz, _vp]),
+    "swirl_whir_open": (_i, [_vp, C.POINTER(TranscriptC), C.POINTER(WhirConfigC), _vp, _sz, _vp, _vp, _sz]),
     "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
 }
 

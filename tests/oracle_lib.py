@@ -43,6 +43,11 @@ class Oracle:
         L.orc_gkr_prove.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]
         L.orc_gkr_verify.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
         L.orc_eval_mle_evals_at_point.argtypes = [_vp, _i, _vp, _vp]
+        L.orc_whir_proof_words.restype = _sz
+        L.orc_whir_proof_words.argtypes = [_i, _i, _i, _i, _vp, _sz, _vp]
+        L.orc_whir_prove.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _sz, _vp, _vp, _vp]
+        L.orc_whir_stacking_openings.argtypes = [_i, _vp, _sz, _sz, _vp, _vp]
+        L.orc_whir_verify.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _sz, _sz, _vp, _vp, _vp, _vp]
 
     # ---- field ----
     def to_mont(self, x):
@@ -232,6 +237,44 @@ class Oracle:
         self.L.orc_eval_mle_evals_at_point(_p(np.ascontiguousarray(evals, np.uint32)), n,
                                            _p(np.ascontiguousarray(x, np.uint32)), _p(out))
         return out
+
+    # ---- WHIR ----
+    def whir_proof_words(self, m, log_blowup, cfg, widths):
+        nq = np.asarray(cfg["num_queries"], np.int32)
+        w = np.asarray(widths, np.uint64)
+        return int(self.L.orc_whir_proof_words(m, log_blowup, cfg["k"], len(nq), _p(nq), len(w), _p(w)))
+
+    def whir_prove(self, sponge, l_skip, log_blowup, cfg, mats, height, u):
+        """mats: list of (uint32 col-major flat, width).  Returns (roots[n,8], proof words)."""
+        nq = np.asarray(cfg["num_queries"], np.int32)
+        widths = np.asarray([w for _, w in mats], np.uint64)
+        arrs = [np.ascontiguousarray(v, np.uint32) for v, _ in mats]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        m = height.bit_length() - 1
+        proof = np.zeros(self.whir_proof_words(m, log_blowup, cfg, widths), np.uint32)
+        roots = np.zeros((len(arrs), 8), np.uint32)
+        u = np.ascontiguousarray(u, np.uint32)
+        rc = self.L.orc_whir_prove(_p(sponge), l_skip, log_blowup, cfg["k"], len(nq), _p(nq), cfg["mu_pow_bits"],
+                                   cfg["query_phase_pow_bits"], cfg["folding_pow_bits"], len(arrs), ptrs, _p(widths),
+                                   height, _p(u), _p(roots), _p(proof))
+        assert rc == 0
+        return roots, proof
+
+    def whir_stacking_openings(self, l_skip, mat, height, width, u):
+        out = np.zeros((width, 4), np.uint32)
+        self.L.orc_whir_stacking_openings(l_skip, _p(np.ascontiguousarray(mat, np.uint32)), height, width,
+                                          _p(np.ascontiguousarray(u, np.uint32)), _p(out))
+        return out
+
+    def whir_verify(self, sponge, l_skip, n_stack, log_blowup, cfg, proof, widths, openings, roots, u):
+        nq = np.asarray(cfg["num_queries"], np.int32)
+        w = np.asarray(widths, np.uint64)
+        proof = np.ascontiguousarray(proof, np.uint32)
+        return bool(self.L.orc_whir_verify(_p(sponge), l_skip, n_stack, log_blowup, cfg["k"], len(nq), _p(nq),
+                                           cfg["mu_pow_bits"], cfg["query_phase_pow_bits"], cfg["folding_pow_bits"],
+                                           _p(proof), proof.size, len(w), _p(w),
+                                           _p(np.ascontiguousarray(openings, np.uint32)),
+                                           _p(np.ascontiguousarray(roots, np.uint32)), _p(np.ascontiguousarray(u, np.uint32))))
 
 def split_layers(flat, qs):
     out, off, n = [], 0, qs
