@@ -220,6 +220,22 @@ size_t swirl_whir_proof_words(const swirl_pcs_params* params, const swirl_whir_c
 int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl_whir_config* cfg, const swirl_pcs* const* pcs,
                     size_t n_commits, const uint32_t* h_u, uint32_t* h_proof, size_t proof_words);
 
+/* ---- phase level: stacked opening reduction (reference: prove_stacked_opening_reduction,
+ *      prover/stacked_reduction.rs:67-127 with StackedReductionCpu :129-506; GPU
+ *      cuda-backend/src/stacked_reduction.rs:188) -------------------------------------------------
+ * pcs: common main first, then preprocessed / cached commitments in the order of
+ * StackedReductionProver::new (stacked_reduction.rs:36-50).  need_rot[c][mat] != 0 iff matrix
+ * `mat` of commitment c is opened with its rotation.  h_r: r_len >= 1 + n_max EF words, the
+ * point produced by the batch constraint sumcheck.  Flat proof (Montgomery words), in the field
+ * order of StackingProof (proof.rs:155-163):
+ *   univariate_round_coeffs[2(2^l_skip - 1) + 1][4] | sumcheck_round_polys[n_stack][2][4]
+ *   | stacking_openings: per commitment [stacked width][4].
+ * h_u receives u (n_stack + 1 EF). */
+size_t swirl_stacked_reduction_proof_words(const swirl_pcs* const* pcs, size_t n_commits);
+int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, const swirl_pcs* const* pcs, size_t n_commits,
+                            const uint8_t* const* need_rot, const uint32_t* h_r, size_t r_len, uint32_t* h_proof,
+                            size_t proof_words, uint32_t* h_u);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 
 #include "commit.hpp"
 #include "gkr.hpp"
+#include "stacked_reduction.hpp"
 #include "transcript.hpp"
 #include "whir.hpp"
 
@@ -414,6 +415,127 @@ int orc_whir_verify(uint32_t* st, int l_skip, int n_stack, int log_blowup, int k
         bool ok = verify_whir(ts, l_skip, n_stack, log_blowup, cfg, pr, so, com, uv);
         if (ok) store_sponge(ts, st);
         return ok ? 1 : 0;
+    } catch (const std::exception&) {
+        return 0;
+    }
+}
+
+// ---- stacked opening reduction -------------------------------------------------------------------
+// Commit c stacks traces [trace_off[c], trace_off[c+1]) (already height-sorted).  Flat proof:
+// univariate_round_coeffs[2(2^l_skip-1)+1][4] | sumcheck_round_polys[n_stack][2][4] | per commit openings[width][4].
+static void build_commits(int l_skip, int n_stack, size_t n_commits, const uint64_t* trace_off, const uint32_t* const* ptrs,
+                          const uint64_t* heights, const uint64_t* widths, std::vector<std::vector<ColMajor>>& traces,
+                          std::vector<StackedPcsData>& data) {
+    traces.resize(n_commits);
+    data.resize(n_commits);
+    for (size_t c = 0; c < n_commits; c++) {
+        std::vector<const ColMajor*> tp;
+        for (uint64_t t = trace_off[c]; t < trace_off[c + 1]; t++) {
+            ColMajor m(heights[t], widths[t]);
+            if (ptrs) memcpy(m.values.data(), ptrs[t], heights[t] * widths[t] * 4);
+            traces[c].push_back(std::move(m));
+        }
+        for (auto& m : traces[c]) tp.push_back(&m);
+        data[c].matrix = stacked_matrix(l_skip, n_stack, tp, &data[c].layout);
+    }
+}
+size_t orc_stacked_reduction_proof_words(int l_skip, int n_stack, size_t n_commits, const uint64_t* stacked_widths) {
+    size_t n = (2 * ((size_t(1) << l_skip) - 1) + 1) * 4 + (size_t)n_stack * 8;
+    for (size_t c = 0; c < n_commits; c++) n += stacked_widths[c] * 4;
+    return n;
+}
+int orc_stacked_reduction_prove(uint32_t* st, int l_skip, int n_stack, size_t n_commits, const uint64_t* trace_off,
+                                const uint32_t* const* ptrs, const uint64_t* heights, const uint64_t* widths,
+                                const uint8_t* need_rot, const uint32_t* r, size_t r_len, uint64_t* stacked_widths,
+                                uint32_t* proof_out, uint32_t* u_out) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        std::vector<std::vector<ColMajor>> traces;
+        std::vector<StackedPcsData> data;
+        build_commits(l_skip, n_stack, n_commits, trace_off, ptrs, heights, widths, traces, data);
+        std::vector<const StackedPcsData*> cp;
+        std::vector<std::vector<bool>> rot(n_commits);
+        for (size_t c = 0; c < n_commits; c++) {
+            cp.push_back(&data[c]);
+            stacked_widths[c] = data[c].matrix.width;
+            for (uint64_t t = trace_off[c]; t < trace_off[c + 1]; t++) rot[c].push_back(need_rot[t] != 0);
+        }
+        std::vector<EF> rv(r_len), u;
+        memcpy(rv.data(), r, r_len * 16);
+        StackingProof pr = prove_stacked_opening_reduction(ts, l_skip, n_stack, cp, rot, rv, &u);
+        uint32_t* p = proof_out;
+        for (auto& c : pr.univariate_round_coeffs) { memcpy(p, &c, 16); p += 4; }
+        for (auto& s : pr.sumcheck_round_polys) { memcpy(p, s.data(), 32); p += 8; }
+        for (auto& v : pr.stacking_openings)
+            for (auto& c : v) { memcpy(p, &c, 16); p += 4; }
+        memcpy(u_out, u.data(), u.size() * 16);
+        store_sponge(ts, st);
+        return 0;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+// Opening claim of one (possibly rotated) trace column at r = (r_0, r_1..): fold_ple_evals at r_0
+// then MLE folds (what prove_zerocheck_and_logup leaves as column_openings; cpu.rs:430-445,582-587,644-694).
+void orc_column_opening(int l_skip, const uint32_t* col, size_t height, int is_rot, const uint32_t* r, uint32_t* out) {
+    MatPart p;
+    p.values = reinterpret_cast<const F*>(col);
+    p.height = height;
+    p.width = 1;
+    p.col_stride = 0;
+    p.is_rot = is_rot != 0;
+    EF r0;
+    memcpy(&r0, r, 16);
+    size_t h;
+    std::vector<EF> v = fold_ple_evals(l_skip, p, r0, &h);
+    int j = 1;
+    while (h > 1) {
+        EF rj;
+        memcpy(&rj, r + 4 * j, 16);
+        fold_mle_evals(v, h, 1, rj);
+        j++;
+    }
+    memcpy(out, &v[0], 16);
+}
+int orc_stacked_reduction_verify(uint32_t* st, int l_skip, int n_stack, size_t n_commits, const uint64_t* trace_off,
+                                 const uint64_t* heights, const uint64_t* widths, const uint8_t* need_rot,
+                                 const uint32_t* t_claims, const uint32_t* r, size_t r_len, const uint32_t* proof,
+                                 uint32_t* u_out) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        std::vector<std::vector<ColMajor>> traces;
+        std::vector<StackedPcsData> data;
+        build_commits(l_skip, n_stack, n_commits, trace_off, nullptr, heights, widths, traces, data);
+        std::vector<const StackedLayout*> layouts;
+        std::vector<std::vector<bool>> rot(n_commits);
+        size_t n_claims = 0;
+        for (size_t c = 0; c < n_commits; c++) {
+            layouts.push_back(&data[c].layout);
+            n_claims += data[c].layout.sorted_cols.size();
+            for (uint64_t t = trace_off[c]; t < trace_off[c + 1]; t++) rot[c].push_back(need_rot[t] != 0);
+        }
+        std::vector<std::pair<EF, EF>> claims(n_claims);
+        for (size_t i = 0; i < n_claims; i++) {
+            memcpy(&claims[i].first, t_claims + 8 * i, 16);
+            memcpy(&claims[i].second, t_claims + 8 * i + 4, 16);
+        }
+        StackingProof pr;
+        const uint32_t* p = proof;
+        pr.univariate_round_coeffs.resize(2 * ((size_t(1) << l_skip) - 1) + 1);
+        for (auto& c : pr.univariate_round_coeffs) { memcpy(&c, p, 16); p += 4; }
+        pr.sumcheck_round_polys.resize(n_stack);
+        for (auto& s : pr.sumcheck_round_polys) { memcpy(s.data(), p, 32); p += 8; }
+        for (size_t c = 0; c < n_commits; c++) {
+            std::vector<EF> v(data[c].matrix.width);
+            for (auto& x : v) { memcpy(&x, p, 16); p += 4; }
+            pr.stacking_openings.push_back(v);
+        }
+        std::vector<EF> rv(r_len), u;
+        memcpy(rv.data(), r, r_len * 16);
+        if (!verify_stacked_reduction(ts, pr, layouts, rot, l_skip, n_stack, claims, rv, &u)) return 0;
+        memcpy(u_out, u.data(), u.size() * 16);
+        store_sponge(ts, st);
+        return 1;
     } catch (const std::exception&) {
         return 0;
     }

@@ -418,6 +418,30 @@ class B200Device:
                                                      frac_sum.ctypes.data, claims.ctypes.data, polys.ctypes.data, xi.ctypes.data))
         return dict(frac_sum=frac_sum, claims=claims, polys=polys[:n_polys], xi=xi)
 
+    # -- stacked opening reduction (prove_stacked_opening_reduction, prover/stacked_reduction.rs:67-127) --
+    def stacked_reduction(self, ts, pcs_list, need_rot_per_commit, r):
+        """need_rot_per_commit[c][mat] -> bool.  r: (>= 1 + n_max, 4) Montgomery words.
+        Returns dict(univariate_round_coeffs, sumcheck_round_polys, stacking_openings (list per commit), u, flat)."""
+        handles = (C.c_void_p * len(pcs_list))(*[d._h for d in pcs_list])
+        n = int(self.lib.swirl_stacked_reduction_proof_words(handles, len(pcs_list)))
+        proof = np.zeros(n, dtype=np.uint32)
+        rots = [np.asarray([1 if b else 0 for b in rr], dtype=np.uint8) for rr in need_rot_per_commit]
+        rot_ptrs = (C.c_void_p * len(rots))(*[a.ctypes.data for a in rots])
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        p0 = pcs_list[0].params
+        u = np.zeros((p0.n_stack + 1, 4), dtype=np.uint32)
+        self._sync_torch()
+        check(self.lib.swirl_stacked_reduction(self.ctx, C.byref(ts.c), handles, len(pcs_list), rot_ptrs, r.ctypes.data,
+                                               r.size // 4, proof.ctypes.data, n, u.ctypes.data))
+        n0 = (2 * ((1 << p0.l_skip) - 1) + 1) * 4
+        n1 = n0 + p0.n_stack * 8
+        openings, off = [], n1
+        for d in pcs_list:
+            openings.append(proof[off : off + d.width * 4].reshape(d.width, 4))
+            off += d.width * 4
+        return dict(univariate_round_coeffs=proof[:n0].reshape(-1, 4), sumcheck_round_polys=proof[n0:n1].reshape(-1, 2, 4),
+                    stacking_openings=openings, u=u, flat=proof)
+
     # -- WHIR opening (prove_whir_opening, prover/whir.rs:78-341) -----------------------------------
     def whir_open(self, ts, cfg, params, pcs_list, u):
         """pcs_list: StackedPcsData (common main first).  u: (l_skip+n_stack, 4) Montgomery words.

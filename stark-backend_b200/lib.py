@@ -87,6 +87,8 @@ PROTOTYPES = {
     "swirl_pcs_layout": (_u64, [_vp, _vp]),
     "swirl_whir_proof_words": (_sz, [C.POINTER(PcsParamsC), C.POINTER(WhirConfigC), _sz, _vp]),
     "swirl_whir_open": (_i, [_vp, C.POINTER(TranscriptC), C.POINTER(WhirConfigC), _vp, _sz, _vp, _vp, _sz]),
+    "swirl_stacked_reduction_proof_words": (_sz, [_vp, _sz]),
+    "swirl_stacked_reduction": (_i, [_vp, C.POINTER(TranscriptC), _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp]),
     "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
 }
 

@@ -43,6 +43,11 @@ class Oracle:
         L.orc_gkr_prove.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]
         L.orc_gkr_verify.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
         L.orc_eval_mle_evals_at_point.argtypes = [_vp, _i, _vp, _vp]
+        L.orc_stacked_reduction_proof_words.restype = _sz
+        L.orc_stacked_reduction_proof_words.argtypes = [_i, _i, _sz, _vp]
+        L.orc_stacked_reduction_prove.argtypes = [_vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]
+        L.orc_column_opening.argtypes = [_i, _vp, _sz, _i, _vp, _vp]
+        L.orc_stacked_reduction_verify.argtypes = [_vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]
         L.orc_whir_proof_words.restype = _sz
         L.orc_whir_proof_words.argtypes = [_i, _i, _i, _i, _vp, _sz, _vp]
         L.orc_whir_prove.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _sz, _vp, _vp, _vp]
@@ -275,6 +280,54 @@ class Oracle:
                                            _p(proof), proof.size, len(w), _p(w),
                                            _p(np.ascontiguousarray(openings, np.uint32)),
                                            _p(np.ascontiguousarray(roots, np.uint32)), _p(np.ascontiguousarray(u, np.uint32))))
+
+    # ---- stacked opening reduction ----
+    @staticmethod
+    def _commit_meta(commits):
+        """commits: list of lists of (vals, height, width, need_rot)."""
+        off, hs, ws, rot, arrs = [0], [], [], [], []
+        for traces in commits:
+            for v, h, w, nr in traces:
+                arrs.append(np.ascontiguousarray(v, np.uint32))
+                hs.append(h)
+                ws.append(w)
+                rot.append(1 if nr else 0)
+            off.append(len(hs))
+        return (np.asarray(off, np.uint64), arrs, np.asarray(hs, np.uint64), np.asarray(ws, np.uint64),
+                np.asarray(rot, np.uint8))
+
+    def stacked_reduction_prove(self, sponge, l_skip, n_stack, commits, r):
+        off, arrs, hs, ws, rot = self._commit_meta(commits)
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        r = np.ascontiguousarray(r, np.uint32)
+        sw = np.zeros(len(commits), np.uint64)
+        # widths of the stacked matrices are needed for the proof size: ceil(sum cells / H)
+        H = 1 << (l_skip + n_stack)
+        for c, traces in enumerate(commits):
+            cells = sum(max(h, 1 << l_skip) * w for _, h, w, _ in traces)
+            sw[c] = (cells + H - 1) // H
+        n = int(self.L.orc_stacked_reduction_proof_words(l_skip, n_stack, len(commits), _p(sw)))
+        proof = np.zeros(n, np.uint32)
+        u = np.zeros((n_stack + 1, 4), np.uint32)
+        rc = self.L.orc_stacked_reduction_prove(_p(sponge), l_skip, n_stack, len(commits), _p(off), ptrs, _p(hs), _p(ws),
+                                                _p(rot), _p(r), r.size // 4, _p(sw), _p(proof), _p(u))
+        assert rc == 0
+        return proof, u, sw
+
+    def column_opening(self, l_skip, col, is_rot, r):
+        out = np.zeros(4, np.uint32)
+        col = np.ascontiguousarray(col, np.uint32)
+        self.L.orc_column_opening(l_skip, _p(col), col.size, int(is_rot), _p(np.ascontiguousarray(r, np.uint32)), _p(out))
+        return out
+
+    def stacked_reduction_verify(self, sponge, l_skip, n_stack, commits, t_claims, r, proof):
+        off, _, hs, ws, rot = self._commit_meta(commits)
+        u = np.zeros((n_stack + 1, 4), np.uint32)
+        r = np.ascontiguousarray(r, np.uint32)
+        ok = self.L.orc_stacked_reduction_verify(_p(sponge), l_skip, n_stack, len(commits), _p(off), _p(hs), _p(ws), _p(rot),
+                                                 _p(np.ascontiguousarray(t_claims, np.uint32)), _p(r), r.size // 4,
+                                                 _p(np.ascontiguousarray(proof, np.uint32)), _p(u))
+        return bool(ok), u
 
 def split_layers(flat, qs):
     out, off, n = [], 0, qs
