@@ -7,6 +7,7 @@
 
 #include "commit.hpp"
 #include "gkr.hpp"
+#include "logup_zerocheck.hpp"
 #include "stacked_reduction.hpp"
 #include "transcript.hpp"
 #include "whir.hpp"
@@ -534,6 +535,175 @@ int orc_stacked_reduction_verify(uint32_t* st, int l_skip, int n_stack, size_t n
         memcpy(rv.data(), r, r_len * 16);
         if (!verify_stacked_reduction(ts, pr, layouts, rot, l_skip, n_stack, claims, rv, &u)) return 0;
         memcpy(u_out, u.data(), u.size() * 16);
+        store_sponge(ts, st);
+        return 1;
+    } catch (const std::exception&) {
+        return 0;
+    }
+}
+
+// ---- batch constraints (LogUp-GKR + zerocheck) ---------------------------------------------------
+// air_meta[i] = {n_nodes, n_constraints, n_interactions, constraint_degree, need_rot, n_public, n_cached, has_prep};
+// nodes / constraint_idx / interactions {count_node, bus_index, msg_off, msg_len} / msg_nodes / public_values are the
+// per-AIR arrays concatenated (msg_off is relative to the AIR's own msg_nodes block, whose length is
+// the sum of its msg_len); matrices per AIR in the order common_main, cached..., preprocessed.
+// Flat proof: logup_pow_witness[1] | q0_claim[4] | claims[L][16] | gkr polys[L(L-1)/2][12] | numer[n][4] | denom[n][4]
+//   | univariate_round_coeffs[(D+1)(2^l-1)+1][4] | sumcheck_round_polys[n_max][D+1][4] | column_openings per air,
+//   per part (common main, preprocessed, cached...) flat EF.   L = l_skip + n_logup (0 without interactions).
+struct BcInputs {
+    std::vector<AirCtx> airs;
+    std::vector<ColMajor> mats;  // storage
+    std::vector<int> n_per_trace;
+};
+static void bc_parse(int l_skip, size_t n_airs, const uint64_t* meta, const uint32_t* nodes, const uint32_t* cidx,
+                     const uint32_t* inter, const uint32_t* msg, const uint32_t* pubs, const uint32_t* const* mat_ptrs,
+                     const uint64_t* mat_h, const uint64_t* mat_w, BcInputs& in) {
+    size_t n_mats = 0;
+    for (size_t i = 0; i < n_airs; i++) n_mats += 1 + meta[8 * i + 6] + meta[8 * i + 7];
+    in.mats.resize(n_mats);
+    for (size_t k = 0; k < n_mats; k++) {
+        in.mats[k] = ColMajor(mat_h[k], mat_w[k]);
+        if (mat_ptrs) memcpy(in.mats[k].values.data(), mat_ptrs[k], mat_h[k] * mat_w[k] * 4);
+    }
+    size_t mi = 0;
+    for (size_t i = 0; i < n_airs; i++) {
+        const uint64_t* m = meta + 8 * i;
+        AirCtx a;
+        for (uint64_t k = 0; k < m[0]; k++, nodes += 4) a.nodes.push_back(DagNode{nodes[0], nodes[1], nodes[2], nodes[3]});
+        a.constraint_idx.assign(cidx, cidx + m[1]);
+        cidx += m[1];
+        size_t msg_total = 0;
+        for (uint64_t k = 0; k < m[2]; k++, inter += 4) {
+            Interaction it;
+            it.count_node = inter[0];
+            it.bus_index = inter[1];
+            it.message.assign(msg + inter[2], msg + inter[2] + inter[3]);
+            msg_total += inter[3];
+            a.interactions.push_back(it);
+        }
+        msg += msg_total;
+        a.constraint_degree = (int)m[3];
+        a.need_rot = m[4] != 0;
+        for (uint64_t k = 0; k < m[5]; k++) a.public_values.push_back(F::raw(pubs[k]));
+        pubs += m[5];
+        a.common_main = &in.mats[mi++];
+        for (uint64_t k = 0; k < m[6]; k++) a.cached_mains.push_back(&in.mats[mi++]);
+        if (m[7]) a.preprocessed = &in.mats[mi++];
+        in.n_per_trace.push_back(log2_strict(a.common_main->height) - l_skip);
+        in.airs.push_back(a);
+    }
+}
+static size_t bc_words(int l_skip, int D, const BcInputs& in, int* L_out, int* n_max_out) {
+    uint64_t total = 0;
+    int n_max = 0;
+    for (size_t t = 0; t < in.airs.size(); t++) {
+        total += (uint64_t)in.airs[t].interactions.size() << (l_skip + std::max(in.n_per_trace[t], 0));
+        n_max = std::max(n_max, in.n_per_trace[t]);
+    }
+    const int L = total ? l_skip + calculate_n_logup(l_skip, total) : 0;
+    size_t n = 1 + 4 + (size_t)L * 16 + (size_t)L * (L > 0 ? L - 1 : 0) / 2 * 12 + in.airs.size() * 8 +
+               ((size_t)(D + 1) * ((size_t(1) << l_skip) - 1) + 1) * 4 + (size_t)n_max * (D + 1) * 4;
+    for (const AirCtx& a : in.airs) {
+        size_t w = a.common_main->width;
+        for (auto* c : a.cached_mains) w += c->width;
+        if (a.preprocessed) w += a.preprocessed->width;
+        n += w * (a.need_rot ? 2 : 1) * 4;
+    }
+    if (L_out) *L_out = L;
+    if (n_max_out) *n_max_out = n_max;
+    return n;
+}
+size_t orc_bc_proof_words(int l_skip, int D, size_t n_airs, const uint64_t* meta, const uint32_t* nodes, const uint32_t* cidx,
+                          const uint32_t* inter, const uint32_t* msg, const uint32_t* pubs, const uint64_t* mat_h,
+                          const uint64_t* mat_w) {
+    try {
+        BcInputs in;
+        bc_parse(l_skip, n_airs, meta, nodes, cidx, inter, msg, pubs, nullptr, mat_h, mat_w, in);
+        return bc_words(l_skip, D, in, nullptr, nullptr);
+    } catch (const std::exception&) {
+        return 0;
+    }
+}
+// returns 0 ok, 2 NonZeroRootSum (unbalanced LogUp), 1 other
+int orc_bc_prove(uint32_t* st, int l_skip, int D, int logup_pow_bits, size_t n_airs, const uint64_t* meta,
+                 const uint32_t* nodes, const uint32_t* cidx, const uint32_t* inter, const uint32_t* msg,
+                 const uint32_t* pubs, const uint32_t* const* mat_ptrs, const uint64_t* mat_h, const uint64_t* mat_w,
+                 uint32_t* proof, uint32_t* r_out) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        BcInputs in;
+        bc_parse(l_skip, n_airs, meta, nodes, cidx, inter, msg, pubs, mat_ptrs, mat_h, mat_w, in);
+        GkrProof g;
+        BatchConstraintProof bc;
+        std::vector<EF> r;
+        prove_zerocheck_and_logup(ts, l_skip, D, logup_pow_bits, in.airs, &g, &bc, &r);
+        uint32_t* p = proof;
+        *p++ = g.logup_pow_witness.v;
+        memcpy(p, &g.q0_claim, 16); p += 4;
+        for (auto& c : g.claims_per_layer) { memcpy(p, &c, 64); p += 16; }
+        for (auto& layer : g.sumcheck_polys)
+            for (auto& sp : layer) { memcpy(p, sp.data(), 48); p += 12; }
+        for (auto& e : bc.numerator_term_per_air) { memcpy(p, &e, 16); p += 4; }
+        for (auto& e : bc.denominator_term_per_air) { memcpy(p, &e, 16); p += 4; }
+        for (auto& e : bc.univariate_round_coeffs) { memcpy(p, &e, 16); p += 4; }
+        for (auto& rp : bc.sumcheck_round_polys)
+            for (auto& e : rp) { memcpy(p, &e, 16); p += 4; }
+        for (auto& ao : bc.column_openings)
+            for (auto& part : ao)
+                for (auto& e : part) { memcpy(p, &e, 16); p += 4; }
+        memcpy(r_out, r.data(), r.size() * 16);
+        store_sponge(ts, st);
+        return 0;
+    } catch (const NonZeroRootSum&) {
+        return 2;
+    } catch (const std::exception&) {
+        return 1;
+    }
+}
+int orc_bc_verify(uint32_t* st, int l_skip, int D, int logup_pow_bits, size_t n_airs, const uint64_t* meta,
+                  const uint32_t* nodes, const uint32_t* cidx, const uint32_t* inter, const uint32_t* msg,
+                  const uint32_t* pubs, const uint64_t* mat_h, const uint64_t* mat_w, const uint32_t* proof,
+                  uint32_t* r_out) {
+    try {
+        DuplexSponge ts = load_sponge(st);
+        BcInputs in;
+        bc_parse(l_skip, n_airs, meta, nodes, cidx, inter, msg, pubs, nullptr, mat_h, mat_w, in);
+        int L = 0, n_max = 0;
+        bc_words(l_skip, D, in, &L, &n_max);
+        GkrProof g;
+        BatchConstraintProof bc;
+        const uint32_t* p = proof;
+        g.logup_pow_witness = F::raw(*p++);
+        memcpy(&g.q0_claim, p, 16); p += 4;
+        g.claims_per_layer.resize(L);
+        for (auto& c : g.claims_per_layer) { memcpy(&c, p, 64); p += 16; }
+        for (int round = 1; round < L; round++) {
+            std::vector<std::array<EF, 3>> layer(round);
+            for (auto& sp : layer) { memcpy(sp.data(), p, 48); p += 12; }
+            g.sumcheck_polys.push_back(layer);
+        }
+        auto rd = [&](std::vector<EF>& v, size_t n) {
+            v.resize(n);
+            for (auto& e : v) { memcpy(&e, p, 16); p += 4; }
+        };
+        rd(bc.numerator_term_per_air, n_airs);
+        rd(bc.denominator_term_per_air, n_airs);
+        rd(bc.univariate_round_coeffs, (size_t)(D + 1) * ((size_t(1) << l_skip) - 1) + 1);
+        bc.sumcheck_round_polys.resize(n_max);
+        for (auto& rp : bc.sumcheck_round_polys) rd(rp, D + 1);
+        for (const AirCtx& a : in.airs) {
+            std::vector<std::vector<EF>> ao;
+            const size_t mul = a.need_rot ? 2 : 1;
+            std::vector<EF> part;
+            rd(part, a.common_main->width * mul);
+            ao.push_back(part);
+            if (a.preprocessed) { rd(part, a.preprocessed->width * mul); ao.push_back(part); }
+            for (auto* c : a.cached_mains) { rd(part, c->width * mul); ao.push_back(part); }
+            bc.column_openings.push_back(ao);
+        }
+        std::vector<EF> r;
+        if (!verify_zerocheck_and_logup(ts, l_skip, D, logup_pow_bits, in.airs, in.n_per_trace, g, bc, &r)) return 0;
+        memcpy(r_out, r.data(), r.size() * 16);
         store_sponge(ts, st);
         return 1;
     } catch (const std::exception&) {

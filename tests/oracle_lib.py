@@ -48,6 +48,10 @@ class Oracle:
         L.orc_stacked_reduction_prove.argtypes = [_vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]
         L.orc_column_opening.argtypes = [_i, _vp, _sz, _i, _vp, _vp]
         L.orc_stacked_reduction_verify.argtypes = [_vp, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]
+        L.orc_bc_proof_words.restype = _sz
+        L.orc_bc_proof_words.argtypes = [_i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.orc_bc_prove.argtypes = [_vp, _i, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.orc_bc_verify.argtypes = [_vp, _i, _i, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.orc_whir_proof_words.restype = _sz
         L.orc_whir_proof_words.argtypes = [_i, _i, _i, _i, _vp, _sz, _vp]
         L.orc_whir_prove.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _sz, _vp, _vp, _sz, _vp, _vp, _vp]
@@ -328,6 +332,39 @@ class Oracle:
                                                  _p(np.ascontiguousarray(t_claims, np.uint32)), _p(r), r.size // 4,
                                                  _p(np.ascontiguousarray(proof, np.uint32)), _p(u))
         return bool(ok), u
+
+    # ---- batch constraints (LogUp-GKR + zerocheck) ----
+    @staticmethod
+    def _bc_args(flat):
+        def pp(a):
+            return _p(a) if a.size else None
+        hs = np.array([m[1] for m in flat["mats"]], np.uint64)
+        ws = np.array([m[2] for m in flat["mats"]], np.uint64)
+        arrs = [np.ascontiguousarray(m[0], np.uint32) for m in flat["mats"]]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        return (pp(flat["meta"]), pp(flat["nodes"]), pp(flat["cidx"]), pp(flat["inter"]), pp(flat["msg"]), pp(flat["pubs"])), ptrs, hs, ws, arrs
+
+    def bc_proof_words(self, l_skip, D, airs_flat, n_airs):
+        a, _, hs, ws, _ = self._bc_args(airs_flat)
+        return int(self.L.orc_bc_proof_words(l_skip, D, n_airs, *a, _p(hs), _p(ws)))
+
+    def bc_prove(self, sponge, l_skip, D, logup_pow_bits, airs_flat, n_airs, n_max):
+        a, ptrs, hs, ws, keep = self._bc_args(airs_flat)
+        n = self.bc_proof_words(l_skip, D, airs_flat, n_airs)
+        proof = np.zeros(n, np.uint32)
+        r = np.zeros((n_max + 1, 4), np.uint32)
+        rc = self.L.orc_bc_prove(_p(sponge), l_skip, D, logup_pow_bits, n_airs, *a, ptrs, _p(hs), _p(ws), _p(proof), _p(r))
+        if rc == 2:
+            raise ValueError("NonZeroRootSum")
+        assert rc == 0
+        return proof, r
+
+    def bc_verify(self, sponge, l_skip, D, logup_pow_bits, airs_flat, n_airs, n_max, proof):
+        a, _, hs, ws, _ = self._bc_args(airs_flat)
+        r = np.zeros((n_max + 1, 4), np.uint32)
+        ok = self.L.orc_bc_verify(_p(sponge), l_skip, D, logup_pow_bits, n_airs, *a, _p(hs), _p(ws),
+                                  _p(np.ascontiguousarray(proof, np.uint32)), _p(r))
+        return bool(ok), r
 
 def split_layers(flat, qs):
     out, off, n = [], 0, qs

@@ -1,0 +1,84 @@
+"""Batch constraint sumcheck = LogUp input layer + GKR + zerocheck/LogUp round 0 + MLE rounds
+(SURVEY §8 a5-a8): oracle prover vs oracle verifier (CPU); CUDA prover vs oracle prover (GPU)."""
+import numpy as np
+import pytest
+
+import airs as A
+import stark_backend_b200 as sb
+
+
+def sorted_airs(airs):
+    return sorted(airs, key=lambda a: -a.height)
+
+
+def case_fib(rng):
+    return 2, 2, 0, [A.fibonacci(5)]
+
+
+def case_fib_short(rng):  # trace shorter than 2^l_skip (lifted)
+    return 3, 2, 1, [A.fibonacci(2)]
+
+
+def case_benchmark(rng):
+    return 2, 2, 2, [A.benchmark(5, 6, 6, 2, rng)]
+
+
+def case_sender_receiver(rng):
+    s, r = A.sender_receiver(5, 3, rng)
+    return 2, 2, 3, sorted_airs([s, r])
+
+
+def case_mixed(rng):
+    s, r = A.sender_receiver(4, 1, rng)
+    return 2, 3, 2, sorted_airs([A.fibonacci(6), A.benchmark(4, 3, 5, 3, rng), s, r, A.with_parts(5, rng)])
+
+
+def case_parts(rng):
+    return 2, 3, 0, [A.with_parts(4, rng)]
+
+
+CASES = [case_fib, case_fib_short, case_benchmark, case_sender_receiver, case_parts, case_mixed]
+
+
+def setup(oracle, case, seed=1):
+    rng = np.random.default_rng(seed)
+    l_skip, D, pow_bits, airs = case(rng)
+    n_max = max(max(a.height.bit_length() - 1 - l_skip for a in airs), 0)
+    st = np.zeros(18, np.uint32)
+    oracle.sponge_observe(st, oracle.to_mont(np.arange(seed, seed + 6)))
+    return l_skip, D, pow_bits, airs, n_max, st
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.__name__)
+def test_oracle_batch_constraints_accepted_by_oracle_verifier(oracle, case):
+    l_skip, D, pow_bits, airs, n_max, st = setup(oracle, case)
+    flat = A.flatten(airs)
+    stv = st.copy()
+    proof, r = oracle.bc_prove(st, l_skip, D, pow_bits, flat, len(airs), n_max)
+    ok, rv = oracle.bc_verify(stv, l_skip, D, pow_bits, flat, len(airs), n_max, proof)
+    assert ok
+    assert np.array_equal(r, rv) and np.array_equal(st, stv)
+    bad = proof.copy()
+    bad[1] ^= 1  # q0_claim
+    assert not oracle.bc_verify(setup(oracle, case)[5], l_skip, D, pow_bits, flat, len(airs), n_max, bad)[0]
+    bad = proof.copy()
+    bad[5 + 8 * len(airs) + (len(proof) - 5 - 8 * len(airs)) // 3] ^= 1
+    rejected = not oracle.bc_verify(setup(oracle, case)[5], l_skip, D, pow_bits, flat, len(airs), n_max, bad)[0]
+    assert rejected or case is case_parts  # (an opening no constraint reads is only bound by the stacked reduction)
+
+
+def test_oracle_violated_constraint_is_rejected(oracle):
+    l_skip, D, pow_bits, airs, n_max, st = setup(oracle, case_fib)
+    airs[0].common_main[0][7] ^= 1  # break the trace
+    flat = A.flatten(airs)
+    stv = st.copy()
+    proof, _ = oracle.bc_prove(st, l_skip, D, pow_bits, flat, 1, n_max)
+    assert not oracle.bc_verify(stv, l_skip, D, pow_bits, flat, 1, n_max, proof)[0]
+
+
+def test_oracle_unbalanced_logup_is_an_error(oracle):
+    rng = np.random.default_rng(4)
+    s, r = A.sender_receiver(4, 2, rng, balanced=False)
+    st = np.zeros(18, np.uint32)
+    with pytest.raises(ValueError):
+        oracle.bc_prove(st, 2, 2, 0, A.flatten([s, r]), 2, 2)
