@@ -236,6 +236,66 @@ int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, const swirl_pc
                             const uint8_t* const* need_rot, const uint32_t* h_r, size_t r_len, uint32_t* h_proof,
                             size_t proof_words, uint32_t* h_u);
 
+/* ---- phase level: MultiRapProver::prove_rap_constraints = LogUp-GKR + batch constraint sumcheck
+ *      (reference: prove_zerocheck_and_logup, prover/logup_zerocheck/mod.rs:40-438 with
+ *      LogupZerocheckCpu, cpu.rs:72-695; GPU prove_zerocheck_and_logup_gpu,
+ *      cuda-backend/src/logup_zerocheck/mod.rs:119-434) ---------------------------------------------
+ * AIR constraints cross the boundary as the reference's serialisable DAG (SymbolicConstraintsDag,
+ * air_builders/symbolic/dag.rs:17-96), nodes in topological order: */
+enum {
+    SWIRL_NODE_VAR_PREP = 0,      /* Entry::Preprocessed: a = column index, b = row offset (0 | 1) */
+    SWIRL_NODE_VAR_MAIN = 1,      /* Entry::Main: a = column index, b = row offset, c = part_index (cached.., common last) */
+    SWIRL_NODE_VAR_PUBLIC = 2,    /* Entry::Public: a = index */
+    SWIRL_NODE_IS_FIRST = 3,
+    SWIRL_NODE_IS_LAST = 4,
+    SWIRL_NODE_IS_TRANSITION = 5,
+    SWIRL_NODE_CONST = 6,         /* a = Montgomery word */
+    SWIRL_NODE_ADD = 7,           /* a, b = node indices */
+    SWIRL_NODE_SUB = 8,
+    SWIRL_NODE_NEG = 9,           /* a = node index */
+    SWIRL_NODE_MUL = 10
+};
+typedef struct {
+    uint32_t op, a, b, c;
+} swirl_dag_node;
+typedef struct {       /* Interaction<usize>, interaction/mod.rs: message / count as node indices */
+    uint32_t count_node;
+    uint32_t bus_index;
+    uint32_t msg_offset; /* into swirl_air_ctx::msg_nodes */
+    uint32_t msg_len;
+} swirl_interaction;
+typedef struct {       /* one present AIR: vk constraint data + AirProvingContext (prover/types.rs:18-73) */
+    const swirl_dag_node* nodes;
+    uint64_t n_nodes;
+    const uint32_t* constraint_idx; /* SymbolicExpressionDag::constraint_idx */
+    uint64_t n_constraints;
+    const swirl_interaction* interactions;
+    uint64_t n_interactions;
+    const uint32_t* msg_nodes;
+    uint32_t constraint_degree;     /* vk.max_constraint_degree of this AIR */
+    uint32_t need_rot;              /* vk.params.need_rot */
+    const uint32_t* public_values;  /* host, Montgomery words */
+    uint64_t n_public_values;
+    swirl_matrix common_main;       /* device */
+    const swirl_matrix* cached_mains; /* device matrices */
+    uint64_t n_cached;
+    const swirl_matrix* preprocessed; /* device matrix or NULL */
+} swirl_air_ctx;
+/* Flat proof (Montgomery words), GkrProof then BatchConstraintProof in field order (proof.rs:70-134):
+ *   logup_pow_witness[1] | q0_claim[4] | claims_per_layer[L][16] | sumcheck_polys[L(L-1)/2][12]
+ *   | numerator_term_per_air[n][4] | denominator_term_per_air[n][4]
+ *   | univariate_round_coeffs[(D+1)(2^l_skip - 1) + 1][4] | sumcheck_round_polys[n_max][D+1][4]
+ *   | column_openings: per AIR, per part (common main, preprocessed, cached..) width * (need_rot ? 2 : 1) EF,
+ *     rotations interleaved (claim, claim_rot).
+ * L = l_skip + n_logup (0 when no AIR has interactions), D = max_constraint_degree, n = n_airs,
+ * n_max = max(log2 height) - l_skip clamped at 0.  AIRs must be sorted by descending height (as
+ * the Coordinator does, prover/types.rs:144-148).  h_r receives r (n_max + 1 EF).
+ * Returns SWIRL_ERR_NONZERO_ROOT_SUM for unbalanced interactions. */
+size_t swirl_batch_constraints_proof_words(int l_skip, int max_constraint_degree, const swirl_air_ctx* airs, size_t n_airs);
+int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* ts, int l_skip, int max_constraint_degree,
+                                  int logup_pow_bits, const swirl_air_ctx* airs, size_t n_airs, uint32_t* h_proof,
+                                  size_t proof_words, uint32_t* h_r);
+
 #ifdef __cplusplus
 }
 #endif

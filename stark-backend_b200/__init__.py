@@ -4,6 +4,7 @@ CPU fallback: loading fails loudly when the library is missing, and every comput
 CUDA device."""
 from .lib import load_library, library_path, SwirlError  # noqa: F401
 from .backend import (  # noqa: F401
+    AirProvingContext,
     B200Device,
     Transcript,
     WhirConfig,

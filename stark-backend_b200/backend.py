@@ -219,6 +219,46 @@ class WhirConfig:
         return c
 
 
+class AirProvingContext:
+    """One present AIR: the constraint DAG of its verifying key (SymbolicConstraintsDag,
+    air_builders/symbolic/dag.rs:17-96) plus its traces (AirProvingContext, prover/types.rs:37-73).
+    nodes: (n, 4) uint32 rows (op, a, b, c) in the swirl_dag_node encoding; interactions: list of
+    (count_node, bus_index, [message nodes]); matrices are DeviceMatrix."""
+
+    def __init__(self, nodes, constraint_idx, interactions, constraint_degree, need_rot, common_main, public_values=(),
+                 cached_mains=(), preprocessed=None):
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.uint32).reshape(-1, 4)
+        self.constraint_idx = np.ascontiguousarray(constraint_idx, dtype=np.uint32)
+        self.interactions = [(int(c), int(b), [int(m) for m in msg]) for c, b, msg in interactions]
+        self.constraint_degree, self.need_rot = int(constraint_degree), bool(need_rot)
+        self.public_values = np.ascontiguousarray(public_values, dtype=np.uint32)
+        self.common_main, self.cached_mains, self.preprocessed = common_main, list(cached_mains), preprocessed
+
+    def c(self, keep):
+        inter = (_lib.InteractionC * max(len(self.interactions), 1))()
+        msg = []
+        for i, (cnt, bus, m) in enumerate(self.interactions):
+            inter[i] = _lib.InteractionC(cnt, bus, len(msg), len(m))
+            msg.extend(m)
+        msg = np.asarray(msg, dtype=np.uint32)
+        cached = (MatrixC * max(len(self.cached_mains), 1))()
+        for i, m in enumerate(self.cached_mains):
+            cached[i] = MatrixC(m.ptr(), m.height(), m.width())
+        prep = MatrixC(self.preprocessed.ptr(), self.preprocessed.height(), self.preprocessed.width()) if self.preprocessed else None
+        keep.extend([inter, msg, cached, prep, self])
+        a = _lib.AirCtxC()
+        a.nodes, a.n_nodes = self.nodes.ctypes.data, len(self.nodes)
+        a.constraint_idx, a.n_constraints = self.constraint_idx.ctypes.data, len(self.constraint_idx)
+        a.interactions, a.n_interactions = C.addressof(inter), len(self.interactions)
+        a.msg_nodes = msg.ctypes.data if len(msg) else None
+        a.constraint_degree, a.need_rot = self.constraint_degree, 1 if self.need_rot else 0
+        a.public_values, a.n_public_values = (self.public_values.ctypes.data if len(self.public_values) else None), len(self.public_values)
+        a.common_main = MatrixC(self.common_main.ptr(), self.common_main.height(), self.common_main.width())
+        a.cached_mains, a.n_cached = C.addressof(cached), len(self.cached_mains)
+        a.preprocessed = C.addressof(prep) if prep is not None else None
+        return a
+
+
 class Transcript:
     """reference: DuplexSponge as FiatShamirTranscript (transcript/duplex_sponge.rs:16-115,
     transcript/traits.rs:11-90).  Host-resident POD state (`swirl_transcript`)."""
@@ -417,6 +457,22 @@ class B200Device:
         check(self.lib.swirl_gkr_fractional_sumcheck(self.ctx, C.byref(ts.c), leaves.data_ptr(), log_n, 1 if assert_zero else 0,
                                                      frac_sum.ctypes.data, claims.ctypes.data, polys.ctypes.data, xi.ctypes.data))
         return dict(frac_sum=frac_sum, claims=claims, polys=polys[:n_polys], xi=xi)
+
+    # -- MultiRapProver::prove_rap_constraints (prove_zerocheck_and_logup, logup_zerocheck/mod.rs:40-438) --
+    def prove_batch_constraints(self, ts, l_skip, max_constraint_degree, logup_pow_bits, airs):
+        """airs: AirProvingContext list sorted by descending height.  Returns (flat proof words, r)."""
+        keep = []
+        arr = (_lib.AirCtxC * len(airs))(*[a.c(keep) for a in airs])
+        n = int(self.lib.swirl_batch_constraints_proof_words(l_skip, max_constraint_degree, arr, len(airs)))
+        if n == 0:
+            raise _lib.SwirlError(10001, "invalid batch constraint inputs")
+        proof = np.zeros(n, dtype=np.uint32)
+        n_max = max(max(a.common_main.height().bit_length() - 1 - l_skip for a in airs), 0)
+        r = np.zeros((n_max + 1, 4), dtype=np.uint32)
+        self._sync_torch()
+        check(self.lib.swirl_prove_batch_constraints(self.ctx, C.byref(ts.c), l_skip, max_constraint_degree, logup_pow_bits,
+                                                     arr, len(airs), proof.ctypes.data, n, r.ctypes.data))
+        return proof, r
 
     # -- stacked opening reduction (prove_stacked_opening_reduction, prover/stacked_reduction.rs:67-127) --
     def stacked_reduction(self, ts, pcs_list, need_rot_per_commit, r):

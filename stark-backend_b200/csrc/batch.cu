@@ -1,0 +1,1142 @@
+// MultiRapProver::prove_rap_constraints: LogUp input layer, GKR, the
+// zerocheck / LogUp univariate round 0 (constraint evaluation on cosets of the skip domain) and the
+// front-loaded batched MLE sumcheck rounds.
+//
+// Replaces (reference, relative to /root/reference):
+//   crates/cuda-backend/src/logup_zerocheck/mod.rs:119-434           prove_zerocheck_and_logup_gpu
+//   crates/cuda-backend/src/logup_zerocheck/rules/mod.rs:27-130      DAG -> three-address rules, register allocation
+//   crates/cuda-backend/cuda/src/logup_zerocheck/{gkr_input,zerocheck_round0,logup_round0,mle,batch_mle}.cu
+//   crates/cuda-backend/cuda/include/{codec.cuh,dag_entry.cuh}       rule encoding / interpreter
+// Semantics = crates/stark-backend/src/prover/logup_zerocheck/{mod.rs,cpu.rs,single.rs,evaluator.rs}.
+//
+// Design.  Every AIR's SymbolicExpressionDag is compiled once on the host into a linear
+// three-address program over a small set of value slots (liveness-based reuse).  Constraint and
+// interaction roots are folded into three EF accumulators as soon as they are produced
+// (sum_k lambda^k C_k, sum eq3b * count, sum eq3b * beta^j * msg_j), so no per-constraint value is
+// ever stored.  The SAME program runs in three kernels: over base-field values at the points of
+// the cosets g^c D (round 0; a column's value at a point is the 2^l_skip-term Lagrange combination
+// of its chunk), over EF values interpolated at X = 1..D between rows 2y, 2y+1 (MLE rounds), and
+// at a single row (the tail terms of the front-loaded batching).  The constant zerofier /
+// normalisation factors and all polynomial bookkeeping stay on the host with the transcript.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "ext.cuh"
+#include "hostpoly.hpp"
+#include "kernels.cuh"
+#include "pcs.cuh"
+#include "transcript.hpp"
+
+// defined in gkr.cu
+extern "C" int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves, int log_n,
+                                             int assert_zero, uint32_t h_frac_sum[8], uint32_t* h_claims,
+                                             uint32_t* h_polys, uint32_t* h_xi);
+
+namespace swirl {
+
+using bb::ext_add;
+using bb::ext_mul;
+using bb::ext_mul_base;
+using bb::ext_sub;
+
+enum : uint32_t { I_VAR = 0, I_CONST, I_ADD, I_SUB, I_MUL, I_NEG, I_ACC };
+struct Instr {
+    uint32_t op_dst;  // op | dst << 8
+    uint32_t a, b, c;
+};
+constexpr int BC_BLOCK = 256;
+constexpr int BC_MAX_SLOTS = 256;
+
+// ---- host: DAG -> program ---------------------------------------------------------------------------
+struct Program {
+    std::vector<Instr> code;
+    int n_slots = 0;
+};
+struct AirLayout {   // how DAG variables map to the row parts [sels, view_mats...]
+    uint32_t stride, prep_base, main_base, n_parts;
+    std::vector<uint32_t> part_col_off;  // global column offset of each row part
+    std::vector<uint32_t> part_width;
+};
+
+static int air_layout(const swirl_air_ctx& a, AirLayout* L) {
+    L->stride = a.need_rot ? 2 : 1;
+    L->prep_base = 1;
+    L->main_base = 1 + (a.preprocessed ? L->stride : 0);
+    L->part_width.clear();
+    L->part_width.push_back(3);
+    auto push = [&](const swirl_matrix& m) {
+        for (uint32_t k = 0; k < L->stride; k++) L->part_width.push_back((uint32_t)m.width);
+    };
+    if (a.preprocessed) push(*a.preprocessed);
+    for (uint64_t i = 0; i < a.n_cached; i++) push(a.cached_mains[i]);
+    push(a.common_main);
+    L->n_parts = (uint32_t)L->part_width.size();
+    L->part_col_off.assign(L->n_parts, 0);
+    for (uint32_t p = 1; p < L->n_parts; p++) L->part_col_off[p] = L->part_col_off[p - 1] + L->part_width[p - 1];
+    return 0;
+}
+
+struct Root {
+    uint32_t node, acc, weight;
+};
+
+// Compiles the sub-DAG reachable from `roots`; each root value is added into accumulator
+// root.acc with weight index root.weight right after it is computed.
+static int compile_program(const swirl_air_ctx& a, const AirLayout& L, const std::vector<Root>& roots, Program* out) {
+    const size_t n = a.n_nodes;
+    std::vector<uint8_t> needed(n, 0);
+    std::vector<std::vector<uint32_t>> root_of(n);
+    for (size_t i = 0; i < roots.size(); i++) {
+        SWIRL_REQUIRE(roots[i].node < n, "DAG root index out of range");
+        needed[roots[i].node] = 1;
+        root_of[roots[i].node].push_back((uint32_t)i);
+    }
+    for (size_t i = n; i-- > 0;) {
+        if (!needed[i]) continue;
+        const swirl_dag_node& nd = a.nodes[i];
+        if (nd.op == SWIRL_NODE_ADD || nd.op == SWIRL_NODE_SUB || nd.op == SWIRL_NODE_MUL) {
+            SWIRL_REQUIRE(nd.a < i && nd.b < i, "DAG is not in topological order");
+            needed[nd.a] = needed[nd.b] = 1;
+        } else if (nd.op == SWIRL_NODE_NEG) {
+            SWIRL_REQUIRE(nd.a < i, "DAG is not in topological order");
+            needed[nd.a] = 1;
+        }
+    }
+    std::vector<int64_t> last_use(n, -1);
+    for (size_t i = 0; i < n; i++) {
+        if (!needed[i]) continue;
+        const swirl_dag_node& nd = a.nodes[i];
+        if (nd.op == SWIRL_NODE_ADD || nd.op == SWIRL_NODE_SUB || nd.op == SWIRL_NODE_MUL) {
+            last_use[nd.a] = (int64_t)i;
+            last_use[nd.b] = (int64_t)i;
+        } else if (nd.op == SWIRL_NODE_NEG) {
+            last_use[nd.a] = (int64_t)i;
+        }
+    }
+    std::vector<int> slot(n, -1), free_slots;
+    int n_slots = 0;
+    out->code.clear();
+    auto release = [&](uint32_t node, size_t at) {
+        if (last_use[node] <= (int64_t)at && slot[node] >= 0) {
+            free_slots.push_back(slot[node]);
+            slot[node] = -1;
+        }
+    };
+    for (size_t i = 0; i < n; i++) {
+        if (!needed[i]) continue;
+        const swirl_dag_node& nd = a.nodes[i];
+        Instr ins{0, 0, 0, 0};
+        uint32_t op = 0;
+        switch (nd.op) {
+            case SWIRL_NODE_VAR_PREP:
+                SWIRL_REQUIRE(a.preprocessed && nd.a < a.preprocessed->width, "PreprocessedIndexOutOfBounds");
+                SWIRL_REQUIRE(nd.b < L.stride, "row offset needs need_rot");
+                op = I_VAR;
+                ins.a = L.prep_base + nd.b;
+                ins.b = nd.a;
+                break;
+            case SWIRL_NODE_VAR_MAIN: {
+                SWIRL_REQUIRE(nd.c <= a.n_cached, "MainPartitionIndexOutOfBounds");
+                const uint64_t w = nd.c < a.n_cached ? a.cached_mains[nd.c].width : a.common_main.width;
+                SWIRL_REQUIRE(nd.a < w, "MainPartitionIndexOutOfBounds");
+                SWIRL_REQUIRE(nd.b < L.stride, "row offset needs need_rot");
+                op = I_VAR;
+                ins.a = L.main_base + nd.c * L.stride + nd.b;
+                ins.b = nd.a;
+                break;
+            }
+            case SWIRL_NODE_VAR_PUBLIC:
+                SWIRL_REQUIRE(nd.a < a.n_public_values, "PublicValueIndexOutOfBounds");
+                op = I_CONST;
+                ins.a = a.public_values[nd.a];
+                break;
+            case SWIRL_NODE_IS_FIRST: op = I_VAR; ins.a = 0; ins.b = 0; break;
+            case SWIRL_NODE_IS_TRANSITION: op = I_VAR; ins.a = 0; ins.b = 1; break;
+            case SWIRL_NODE_IS_LAST: op = I_VAR; ins.a = 0; ins.b = 2; break;
+            case SWIRL_NODE_CONST: op = I_CONST; ins.a = nd.a; break;
+            case SWIRL_NODE_ADD: op = I_ADD; break;
+            case SWIRL_NODE_SUB: op = I_SUB; break;
+            case SWIRL_NODE_MUL: op = I_MUL; break;
+            case SWIRL_NODE_NEG: op = I_NEG; break;
+            default: SWIRL_REQUIRE(false, "unknown DAG node");
+        }
+        if (op == I_VAR) ins.c = L.part_col_off[ins.a] + ins.b;  // global column (MLE rounds)
+        if (op == I_ADD || op == I_SUB || op == I_MUL) {
+            ins.a = (uint32_t)slot[nd.a];
+            ins.b = (uint32_t)slot[nd.b];
+        } else if (op == I_NEG) {
+            ins.a = (uint32_t)slot[nd.a];
+        }
+        // operands die here: their slots may be reused for the result
+        if (nd.op == SWIRL_NODE_ADD || nd.op == SWIRL_NODE_SUB || nd.op == SWIRL_NODE_MUL) {
+            release(nd.a, i);
+            if (nd.b != nd.a) release(nd.b, i);
+        } else if (nd.op == SWIRL_NODE_NEG) {
+            release(nd.a, i);
+        }
+        int s;
+        if (!free_slots.empty()) {
+            s = free_slots.back();
+            free_slots.pop_back();
+        } else {
+            s = n_slots++;
+        }
+        slot[i] = s;
+        ins.op_dst = op | ((uint32_t)s << 8);
+        out->code.push_back(ins);
+        for (uint32_t ri : root_of[i]) out->code.push_back(Instr{I_ACC, roots[ri].acc, roots[ri].weight, (uint32_t)s});
+        if (last_use[i] < 0) release((uint32_t)i, i);  // only consumed by accumulations
+    }
+    SWIRL_REQUIRE(n_slots <= BC_MAX_SLOTS, "constraint DAG needs more live values than supported");
+    out->n_slots = n_slots;
+    return 0;
+}
+
+// ---- device: interpreter ------------------------------------------------------------------------
+struct FVal {
+    using T = uint32_t;
+    static __device__ __forceinline__ T add(T a, T b) { return bb::add(a, b); }
+    static __device__ __forceinline__ T sub(T a, T b) { return bb::sub(a, b); }
+    static __device__ __forceinline__ T mul(T a, T b) { return bb::mul(a, b); }
+    static __device__ __forceinline__ T neg(T a) { return bb::neg(a); }
+    static __device__ __forceinline__ T from_base(uint32_t m) { return m; }
+    static __device__ __forceinline__ Ext weigh(const Ext& w, T v) { return ext_mul_base(w, v); }
+};
+struct EVal {
+    using T = Ext;
+    static __device__ __forceinline__ T add(const T& a, const T& b) { return ext_add(a, b); }
+    static __device__ __forceinline__ T sub(const T& a, const T& b) { return ext_sub(a, b); }
+    static __device__ __forceinline__ T mul(const T& a, const T& b) { return ext_mul(a, b); }
+    static __device__ __forceinline__ T neg(const T& a) { return bb::ext_neg(a); }
+    static __device__ __forceinline__ T from_base(uint32_t m) { return bb::ext_from(m); }
+    static __device__ __forceinline__ Ext weigh(const Ext& w, const T& v) { return ext_mul(w, v); }
+};
+
+template <class V, int NS, class LoadVar>
+__device__ __forceinline__ void run_program(const Instr* __restrict__ code, uint32_t n_instr,
+                                            const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[3]) {
+    typename V::T slots[NS];
+    for (uint32_t pc = 0; pc < n_instr; pc++) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code) + pc);
+        const uint32_t op = raw.x & 0xff, dst = raw.x >> 8;
+        switch (op) {
+            case I_VAR: slots[dst] = load_var(raw.y, raw.z, raw.w); break;
+            case I_CONST: slots[dst] = V::from_base(raw.y); break;
+            case I_ADD: slots[dst] = V::add(slots[raw.y], slots[raw.z]); break;
+            case I_SUB: slots[dst] = V::sub(slots[raw.y], slots[raw.z]); break;
+            case I_MUL: slots[dst] = V::mul(slots[raw.y], slots[raw.z]); break;
+            case I_NEG: slots[dst] = V::neg(slots[raw.y]); break;
+            default: {  // I_ACC: acc[y] += weights[z] * slots[w]
+                const Ext wv = ldg_ext(weights + 4 * raw.z);
+                acc[raw.y] = ext_add(acc[raw.y], V::weigh(wv, slots[raw.w]));
+            }
+        }
+    }
+}
+
+struct BasePart {
+    const uint32_t* ptr;  // column-major, column stride = height
+    uint32_t height;      // power of two
+    uint32_t rot;
+};
+
+// is_first / is_transition / is_last of the lifted trace as a 3-column matrix (cpu.rs:306-322)
+__global__ void sels_kernel(uint32_t* __restrict__ out, size_t lifted, size_t height) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lifted) return;
+    const size_t r = i & (height - 1);
+    out[i] = r == 0 ? bb::R1 : 0u;
+    out[lifted + i] = r == height - 1 ? 0u : bb::R1;
+    out[2 * lifted + i] = r == height - 1 ? bb::R1 : 0u;
+}
+
+// LogUp input layer (mod.rs:103-168): one thread per (row, interaction); the interaction's own
+// sub-program leaves count in acc[1] (weight 1) and sum beta^j msg_j in acc[2].
+struct LeafArgs {
+    const Instr* code;
+    const uint32_t* prog_off;  // [n_int + 1] instruction ranges
+    const BasePart* parts;
+    const uint32_t* weights;      // [0] = 1, [1 + j] = beta^j
+    const uint32_t* denom_const;  // per interaction: beta^len * (bus + 1) + alpha
+    const uint64_t* row_idx;      // per interaction: offset in the stacked leaves
+    uint32_t* leaves;
+    uint32_t height, reps;  // reps = lifted length / height (cyclic repetition)
+    uint32_t norm;          // 1 / reps
+};
+template <int NS>
+__global__ void __launch_bounds__(BC_BLOCK) logup_leaves_kernel(LeafArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, sigma = blockIdx.y;
+    if (i >= a.height) return;
+    Ext acc[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+    const uint32_t p0 = a.prog_off[sigma], p1 = a.prog_off[sigma + 1];
+    run_program<FVal, NS>(a.code + p0, p1 - p0, a.weights,
+                          [&](uint32_t part, uint32_t col, uint32_t) {
+                              const BasePart bp = a.parts[part];
+                              return __ldg(bp.ptr + (size_t)col * bp.height + ((i + bp.rot) & (bp.height - 1)));
+                          },
+                          acc);
+    const Ext numer = ext_mul_base(acc[1], a.norm);
+    const Ext denom = ext_add(acc[2], ldg_ext(a.denom_const + 4 * sigma));
+    for (uint32_t rep = 0; rep < a.reps; rep++) {
+        uint32_t* leaf = a.leaves + (a.row_idx[sigma] + (size_t)rep * a.height + i) * 8;
+        st_ext(leaf, numer);
+        st_ext(leaf + 4, denom);
+    }
+}
+__global__ void leaves_fill_kernel(uint32_t* __restrict__ leaves, size_t n, Ext q) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_ext(leaves + 8 * i, bb::ext_zero());
+    st_ext(leaves + 8 * i + 4, q);
+}
+
+// Round 0: thread = (hypercube point x, coset point p).  partials[block][p * 12 + 4k + c] =
+// sum_x eq_xi[x] * acc_k at point p.
+struct R0Args {
+    const Instr* code;
+    uint32_t n_instr;
+    const BasePart* parts;
+    const uint32_t* weights;
+    const uint32_t* lde;    // [P][N]: Lagrange coefficients of D at the P coset points
+    const uint32_t* eq_xi;  // 2^n_lift EF
+    int l_skip, n_lift, P, x_per_block;
+    uint32_t* partials;
+};
+template <int NS>
+__global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
+    extern __shared__ uint32_t sm[];  // [blockDim][13]
+    const int P = a.P, N = 1 << a.l_skip;
+    const int p = threadIdx.x % P, g = threadIdx.x / P, G = blockDim.x / P;
+    const size_t nx = size_t(1) << a.n_lift;
+    const size_t x0 = (size_t)blockIdx.x * a.x_per_block, x1 = min(x0 + (size_t)a.x_per_block, nx);
+    const uint32_t* lde = a.lde + (size_t)p * N;
+    Ext tot[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+    for (size_t x = x0 + g; x < x1; x += G) {
+        Ext acc[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+        run_program<FVal, NS>(a.code, a.n_instr, a.weights,
+                              [&](uint32_t part, uint32_t col, uint32_t) {
+                                  const BasePart bp = a.parts[part];
+                                  const uint32_t* c = bp.ptr + (size_t)col * bp.height;
+                                  const size_t r0 = (x << a.l_skip) + bp.rot;
+                                  uint32_t v = 0;
+                                  for (int i = 0; i < N; i++)
+                                      v = bb::add(v, bb::mul(__ldg(lde + i), __ldg(c + ((r0 + i) & (bp.height - 1)))));
+                                  return v;
+                              },
+                              acc);
+        const Ext e = ldg_ext(a.eq_xi + 4 * x);
+#pragma unroll
+        for (int k = 0; k < 3; k++) tot[k] = ext_add(tot[k], ext_mul(e, acc[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) sm[threadIdx.x * 13 + 4 * k + c] = tot[k].c[c];
+    __syncthreads();
+    for (int o = threadIdx.x; o < P * 12; o += blockDim.x) {
+        const int pi = o / 12, k = o % 12;
+        uint32_t s = 0;
+        for (int gg = 0; gg < G; gg++) s = bb::add(s, sm[(gg * P + pi) * 13 + k]);
+        a.partials[(size_t)blockIdx.x * (P * 12) + o] = s;
+    }
+}
+__global__ void bc_reduce_kernel(const uint32_t* __restrict__ partials, size_t nblocks, int nv, uint32_t* __restrict__ result) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nv) return;
+    uint32_t s = 0;
+    for (size_t b = 0; b < nblocks; b++) s = bb::add(s, partials[b * nv + o]);
+    result[o] = s;
+}
+
+// MLE round: thread per hypercube point y; every X in 1..D evaluates the program on the EF values
+// t0 + (t1 - t0) X of rows (2y, 2y+1).  result[(X-1)*12 + 4k + c] = sum_y eq_xi[y] acc_k(X, y).
+// single: the tables have one row; evaluate it once (D = 1, no eq factor).
+struct MleArgs {
+    const Instr* code;
+    uint32_t n_instr;
+    const uint32_t* base;  // EF, all row parts' columns concatenated, column stride h
+    size_t h;
+    const uint32_t* weights;
+    const uint32_t* eq_xi;
+    size_t ny;
+    int single;
+    uint32_t* partials;
+    unsigned int* ticket;
+    uint32_t* result;
+};
+template <int NS, int D>
+__global__ void __launch_bounds__(128) batch_mle_kernel(MleArgs a) {
+    uint32_t v[D * 12];
+#pragma unroll
+    for (int i = 0; i < D * 12; i++) v[i] = 0;
+    for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)gridDim.x * blockDim.x) {
+        const Ext e = a.single ? bb::ext_one() : ldg_ext(a.eq_xi + 4 * y);
+#pragma unroll
+        for (int X = 1; X <= D; X++) {
+            Ext acc[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+            const uint32_t xm = bb::mont((uint64_t)X);
+            run_program<EVal, NS>(a.code, a.n_instr, a.weights,
+                                  [&](uint32_t, uint32_t, uint32_t gcol) {
+                                      const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
+                                      if (a.single) return ldg_ext(c);
+                                      const Ext t0 = ldg_ext(c + 8 * y), t1 = ldg_ext(c + 8 * y + 4);
+                                      return X == 1 ? t1 : ext_add(t0, ext_mul_base(ext_sub(t1, t0), xm));
+                                  },
+                                  acc);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const Ext t = ext_mul(e, acc[k]);
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[(X - 1) * 12 + 4 * k + c] = bb::add(v[(X - 1) * 12 + 4 * k + c], t.c[c]);
+            }
+        }
+    }
+    grid_sum<D * 12>(v, a.partials, a.ticket, a.result);
+}
+
+template <int NS>
+static void launch_mle(int D, const MleArgs& a, int grid, cudaStream_t st) {
+    switch (D) {
+        case 1: batch_mle_kernel<NS, 1><<<grid, 128, 0, st>>>(a); break;
+        case 2: batch_mle_kernel<NS, 2><<<grid, 128, 0, st>>>(a); break;
+        case 3: batch_mle_kernel<NS, 3><<<grid, 128, 0, st>>>(a); break;
+        case 4: batch_mle_kernel<NS, 4><<<grid, 128, 0, st>>>(a); break;
+        default: batch_mle_kernel<NS, 5><<<grid, 128, 0, st>>>(a); break;
+    }
+}
+// NS buckets keep the per-thread slot array (local memory) as small as the program allows
+#define BC_DISPATCH_NS(ns, CALL)          \
+    do {                                  \
+        if ((ns) <= 16) { CALL(16); }     \
+        else if ((ns) <= 32) { CALL(32); }   \
+        else if ((ns) <= 64) { CALL(64); }   \
+        else if ((ns) <= 128) { CALL(128); } \
+        else { CALL(256); }               \
+    } while (0)
+
+}  // namespace swirl
+
+using namespace swirl;
+
+namespace {
+
+struct TraceState {
+    const swirl_air_ctx* air = nullptr;
+    int log_height = 0, n = 0, n_lift = 0;
+    size_t height = 0, lifted = 0;
+    AirLayout L;
+    Program prog;
+    Instr* d_code = nullptr;
+    BasePart* d_parts = nullptr;
+    uint32_t* d_sels = nullptr;
+    uint32_t* d_weights = nullptr;
+    uint32_t* d_eq_xi = nullptr;
+    uint32_t total_cols = 0;
+    uint32_t* ef[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t h = 0;
+    std::vector<Ext> eq_3b;
+    Ext denom_const = bb::ext_zero();
+    Ext zc_tilde = bb::ext_zero(), lg_tilde[2] = {bb::ext_zero(), bb::ext_zero()};
+    uint32_t norm = bb::R1;  // 1 / 2^max(l_skip - log_height, 0)
+};
+
+int n_logup_of(int l_skip, uint64_t total) {
+    if (!total) return 0;
+    int bits = 0;
+    while (total >> bits) bits++;
+    return bits - l_skip;
+}
+
+size_t bc_words(int l_skip, int D, const swirl_air_ctx* airs, size_t n_airs, int* L_out, int* n_max_out) {
+    uint64_t total = 0;
+    int n_max = 0;
+    for (size_t t = 0; t < n_airs; t++) {
+        const int lh = ilog2(airs[t].common_main.height);
+        total += (uint64_t)airs[t].n_interactions << std::max(lh, l_skip);
+        n_max = std::max(n_max, lh - l_skip);
+    }
+    const int L = total ? l_skip + n_logup_of(l_skip, total) : 0;
+    size_t n = 1 + 4 + (size_t)L * 16 + (size_t)L * (L > 0 ? L - 1 : 0) / 2 * 12 + n_airs * 8 +
+               ((size_t)(D + 1) * ((size_t(1) << l_skip) - 1) + 1) * 4 + (size_t)n_max * (D + 1) * 4;
+    for (size_t t = 0; t < n_airs; t++) {
+        size_t w = airs[t].common_main.width;
+        for (uint64_t i = 0; i < airs[t].n_cached; i++) w += airs[t].cached_mains[i].width;
+        if (airs[t].preprocessed) w += airs[t].preprocessed->width;
+        n += w * (airs[t].need_rot ? 2 : 1) * 4;
+    }
+    if (L_out) *L_out = L;
+    if (n_max_out) *n_max_out = n_max;
+    return n;
+}
+
+// a * b (plain convolution; exact product, what the DFT-domain product of mod.rs:208-236 computes)
+std::vector<Ext> poly_mul(const std::vector<Ext>& a, const std::vector<Ext>& b, size_t out_len) {
+    std::vector<Ext> out(out_len, bb::ext_zero());
+    for (size_t i = 0; i < a.size(); i++)
+        for (size_t j = 0; j < b.size() && i + j < out_len; j++) out[i + j] = ext_add(out[i + j], ext_mul(a[i], b[j]));
+    return out;
+}
+
+}  // namespace
+
+extern "C" size_t swirl_batch_constraints_proof_words(int l_skip, int max_constraint_degree, const swirl_air_ctx* airs,
+                                                      size_t n_airs) {
+    if (!airs || !n_airs || l_skip < 0 || max_constraint_degree < 0) return 0;
+    for (size_t t = 0; t < n_airs; t++)
+        if (!is_pow2(airs[t].common_main.height)) return 0;
+    return bc_words(l_skip, max_constraint_degree, airs, n_airs, nullptr, nullptr);
+}
+
+extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* ts, int l_skip, int max_constraint_degree,
+                                             int logup_pow_bits, const swirl_air_ctx* airs, size_t n_airs, uint32_t* h_proof,
+                                             size_t proof_words, uint32_t* h_r) {
+    SWIRL_REQUIRE(ctx && ts && airs && n_airs >= 1 && h_proof && h_r, "null argument");
+    SWIRL_REQUIRE(l_skip >= 0 && l_skip <= 6, "l_skip must be in [0, 6]");
+    const int D = max_constraint_degree;
+    SWIRL_REQUIRE(D >= 1 && D <= 5, "max_constraint_degree must be in [1, 5]");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    const size_t N = size_t(1) << l_skip;
+    Transcript tr(ts);
+    RoundScratch* rs;
+    SWIRL_TRY(round_scratch_get(ctx, &rs));
+    std::vector<void*> to_free;
+    struct Cleanup {
+        swirl_ctx* ctx;
+        std::vector<void*>& v;
+        ~Cleanup() {
+            for (void* p : v) cudaFreeAsync(p, ctx->stream);
+        }
+    } cleanup{ctx, to_free};
+    auto upload = [&](const void* src, size_t bytes, void** dst) -> int {
+        SWIRL_CUDA(cudaMallocAsync(dst, bytes ? bytes : 4, ctx->stream));
+        to_free.push_back(*dst);
+        if (bytes) SWIRL_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return 0;
+    };
+
+    // ---- traces ------------------------------------------------------------------------------------
+    std::vector<TraceState> T(n_airs);
+    uint64_t total_interactions = 0;
+    for (size_t t = 0; t < n_airs; t++) {
+        TraceState& s = T[t];
+        s.air = &airs[t];
+        SWIRL_REQUIRE(is_pow2(airs[t].common_main.height), "trace height must be a power of two");
+        s.height = airs[t].common_main.height;
+        s.log_height = ilog2(s.height);
+        if (t) SWIRL_REQUIRE(s.log_height <= T[t - 1].log_height, "AIRs must be sorted by descending height");
+        s.n = s.log_height - l_skip;
+        s.n_lift = std::max(s.n, 0);
+        s.lifted = std::max(s.height, N);
+        SWIRL_REQUIRE((int)airs[t].constraint_degree <= D, "AIR constraint degree exceeds max_constraint_degree");
+        SWIRL_REQUIRE(airs[t].constraint_degree * N <= BC_BLOCK, "constraint_degree * 2^l_skip > 256 unsupported");
+        for (uint64_t i = 0; i < airs[t].n_cached; i++)
+            SWIRL_REQUIRE(airs[t].cached_mains[i].height == s.height, "cached trace height mismatch");
+        if (airs[t].preprocessed) SWIRL_REQUIRE(airs[t].preprocessed->height == s.height, "preprocessed trace height mismatch");
+        SWIRL_TRY(air_layout(airs[t], &s.L));
+        s.total_cols = s.L.part_col_off.back() + s.L.part_width.back();
+        s.norm = bb::inv(bb::to_mont((uint32_t)(s.lifted / s.height)));
+        total_interactions += (uint64_t)airs[t].n_interactions << std::max(s.log_height, l_skip);
+    }
+    int L = 0, n_max = 0;
+    SWIRL_REQUIRE(proof_words == bc_words(l_skip, D, airs, n_airs, &L, &n_max), "proof buffer size");
+    const int n_logup = n_logup_of(l_skip, total_interactions);
+    // interactions layout: StackedLayout::new(0, l_skip + n_logup, (num_interactions, log_lifted_height))
+    Layout ilayout;
+    {
+        std::vector<uint64_t> widths(n_airs);
+        std::vector<int32_t> lhs(n_airs);
+        for (size_t t = 0; t < n_airs; t++) {
+            widths[t] = airs[t].n_interactions;
+            lhs[t] = std::max(T[t].log_height, l_skip);
+        }
+        SWIRL_TRY(make_layout(0, l_skip + n_logup, n_airs, widths.data(), lhs.data(), &ilayout));
+    }
+    // proof sections
+    uint32_t* p = h_proof;
+    uint32_t* sec_pow = p; p += 1;
+    uint32_t* sec_q0 = p; p += 4;
+    uint32_t* sec_claims = p; p += (size_t)L * 16;
+    uint32_t* sec_gkr_polys = p; p += (size_t)L * (L > 0 ? L - 1 : 0) / 2 * 12;
+    uint32_t* sec_numer = p; p += n_airs * 4;
+    uint32_t* sec_denom = p; p += n_airs * 4;
+    uint32_t* sec_uni = p; p += ((size_t)(D + 1) * (N - 1) + 1) * 4;
+    uint32_t* sec_rounds = p; p += (size_t)n_max * (D + 1) * 4;
+    uint32_t* sec_open = p;
+
+    SWIRL_TRY(transcript_grind(ctx, ts, logup_pow_bits, sec_pow));
+    const Ext alpha = tr.sample_ext(), beta = tr.sample_ext();
+    size_t max_len = 0;
+    for (size_t t = 0; t < n_airs; t++)
+        for (uint64_t i = 0; i < airs[t].n_interactions; i++) max_len = std::max<size_t>(max_len, airs[t].interactions[i].msg_len);
+    std::vector<Ext> beta_pows(max_len + 1);
+    {
+        Ext b = bb::ext_one();
+        for (auto& x : beta_pows) {
+            x = b;
+            b = ext_mul(b, beta);
+        }
+    }
+
+    // ---- per trace: selector matrix, base parts, programs ---------------------------------------------
+    for (size_t t = 0; t < n_airs; t++) {
+        TraceState& s = T[t];
+        const swirl_air_ctx& a = airs[t];
+        SWIRL_CUDA(dev_alloc(ctx, &s.d_sels, 3 * s.lifted));
+        to_free.push_back(s.d_sels);
+        sels_kernel<<<(unsigned)((s.lifted + 255) / 256), 256, 0, ctx->stream>>>(s.d_sels, s.lifted, s.height);
+        SWIRL_LAUNCH_CHECK(ctx);
+        std::vector<BasePart> parts;
+        parts.push_back(BasePart{s.d_sels, (uint32_t)s.lifted, 0});
+        auto push = [&](const swirl_matrix& m) {
+            parts.push_back(BasePart{m.data, (uint32_t)m.height, 0});
+            if (a.need_rot) parts.push_back(BasePart{m.data, (uint32_t)m.height, 1});
+        };
+        if (a.preprocessed) push(*a.preprocessed);
+        for (uint64_t i = 0; i < a.n_cached; i++) push(a.cached_mains[i]);
+        push(a.common_main);
+        SWIRL_TRY(upload(parts.data(), parts.size() * sizeof(BasePart), (void**)&s.d_parts));
+        // full program: constraints (acc 0, weights 0..nc), interactions (acc 1 / acc 2)
+        std::vector<Root> roots;
+        for (uint64_t k = 0; k < a.n_constraints; k++) roots.push_back(Root{a.constraint_idx[k], 0, (uint32_t)k});
+        uint32_t w = (uint32_t)a.n_constraints;
+        for (uint64_t i = 0; i < a.n_interactions; i++) {
+            const swirl_interaction& it = a.interactions[i];
+            roots.push_back(Root{it.count_node, 1, w++});
+            for (uint32_t j = 0; j < it.msg_len; j++) roots.push_back(Root{a.msg_nodes[it.msg_offset + j], 2, w++});
+        }
+        SWIRL_TRY(compile_program(a, s.L, roots, &s.prog));
+        SWIRL_TRY(upload(s.prog.code.data(), s.prog.code.size() * sizeof(Instr), (void**)&s.d_code));
+    }
+
+    // ---- LogUp input layer + GKR -----------------------------------------------------------------------
+    std::vector<Ext> xi;
+    if (total_interactions > 0) {
+        const size_t n_leaves = size_t(1) << L;
+        uint32_t* leaves = nullptr;
+        SWIRL_CUDA(dev_alloc(ctx, &leaves, n_leaves * 8));
+        to_free.push_back(leaves);
+        leaves_fill_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, ctx->stream>>>(leaves, n_leaves, alpha);
+        SWIRL_LAUNCH_CHECK(ctx);
+        std::vector<uint32_t> lw((max_len + 2) * 4);
+        memcpy(&lw[0], bb::ext_one().c, 16);
+        for (size_t j = 0; j <= max_len; j++) memcpy(&lw[4 * (j + 1)], beta_pows[j].c, 16);
+        uint32_t* d_lw = nullptr;
+        SWIRL_TRY(upload(lw.data(), lw.size() * 4, (void**)&d_lw));
+        for (size_t t = 0; t < n_airs; t++) {
+            const swirl_air_ctx& a = airs[t];
+            if (!a.n_interactions) continue;
+            TraceState& s = T[t];
+            std::vector<Instr> code;
+            std::vector<uint32_t> off{0};
+            std::vector<uint32_t> dconst;
+            std::vector<uint64_t> row_idx(a.n_interactions, 0);
+            int ns = 0;
+            for (uint64_t i = 0; i < a.n_interactions; i++) {
+                const swirl_interaction& it = a.interactions[i];
+                std::vector<Root> roots{Root{it.count_node, 1, 0}};
+                for (uint32_t j = 0; j < it.msg_len; j++) roots.push_back(Root{a.msg_nodes[it.msg_offset + j], 2, 1 + j});
+                Program pr;
+                SWIRL_TRY(compile_program(a, s.L, roots, &pr));
+                code.insert(code.end(), pr.code.begin(), pr.code.end());
+                off.push_back((uint32_t)code.size());
+                ns = std::max(ns, pr.n_slots);
+                const Ext dc = ext_add(ext_mul_base(beta_pows[it.msg_len], bb::to_mont(it.bus_index + 1)), alpha);
+                dconst.insert(dconst.end(), dc.c, dc.c + 4);
+                bool found = false;
+                for (const LayoutCol& lc : ilayout.cols)
+                    if (lc.mat_idx == t && lc.col_in_mat == i) {
+                        row_idx[i] = lc.row_idx;
+                        found = true;
+                    }
+                SWIRL_REQUIRE(found, "InteractionsLayoutMissing");
+            }
+            LeafArgs la{};
+            SWIRL_TRY(upload(code.data(), code.size() * sizeof(Instr), (void**)&la.code));
+            SWIRL_TRY(upload(off.data(), off.size() * 4, (void**)&la.prog_off));
+            SWIRL_TRY(upload(dconst.data(), dconst.size() * 4, (void**)&la.denom_const));
+            SWIRL_TRY(upload(row_idx.data(), row_idx.size() * 8, (void**)&la.row_idx));
+            la.parts = s.d_parts;
+            la.weights = d_lw;
+            la.leaves = leaves;
+            la.height = (uint32_t)s.height;
+            la.reps = (uint32_t)(s.lifted / s.height);
+            la.norm = s.norm;
+            const dim3 grid((unsigned)((s.height + BC_BLOCK - 1) / BC_BLOCK), (unsigned)a.n_interactions);
+#define BC_LEAVES(NS) logup_leaves_kernel<NS><<<grid, BC_BLOCK, 0, ctx->stream>>>(la)
+            BC_DISPATCH_NS(ns, BC_LEAVES);
+#undef BC_LEAVES
+            SWIRL_LAUNCH_CHECK(ctx);
+        }
+        uint32_t frac_sum[8];
+        std::vector<uint32_t> xi_w((size_t)L * 4);
+        SWIRL_TRY(swirl_gkr_fractional_sumcheck(ctx, ts, leaves, L, 1, frac_sum, sec_claims, sec_gkr_polys, xi_w.data()));
+        memcpy(sec_q0, frac_sum + 4, 16);
+        for (int i = 0; i < L; i++) xi.push_back(hp::from_words(&xi_w[4 * i]));
+    } else {
+        memcpy(sec_q0, bb::ext_one().c, 16);
+    }
+    const int n_global = std::max(n_max, n_logup);
+    while ((int)xi.size() != l_skip + n_global) xi.push_back(tr.sample_ext());
+
+    // ---- batching randomness, weights, eq tables --------------------------------------------------------
+    const Ext lambda = tr.sample_ext();
+    for (size_t t = 0; t < n_airs; t++) {
+        TraceState& s = T[t];
+        const swirl_air_ctx& a = airs[t];
+        // eq(xi_3, b) per interaction (cpu.rs:247-283)
+        for (uint64_t i = 0; i < a.n_interactions; i++) {
+            uint64_t stacked_idx = 0;
+            for (const LayoutCol& lc : ilayout.cols)
+                if (lc.mat_idx == t && lc.col_in_mat == i) stacked_idx = lc.row_idx;
+            uint64_t b_int = stacked_idx >> (l_skip + s.n_lift);
+            Ext e = bb::ext_one();
+            for (int v = l_skip + s.n_lift; v < l_skip + n_logup; v++) {
+                e = ext_mul(e, hp::eq1(xi[v], (b_int & 1) != 0));
+                b_int >>= 1;
+            }
+            s.eq_3b.push_back(e);
+        }
+        std::vector<uint32_t> w;
+        Ext lp = bb::ext_one();
+        for (uint64_t k = 0; k < a.n_constraints; k++) {
+            w.insert(w.end(), lp.c, lp.c + 4);
+            lp = ext_mul(lp, lambda);
+        }
+        s.denom_const = bb::ext_zero();
+        for (uint64_t i = 0; i < a.n_interactions; i++) {
+            const swirl_interaction& it = a.interactions[i];
+            w.insert(w.end(), s.eq_3b[i].c, s.eq_3b[i].c + 4);
+            for (uint32_t j = 0; j < it.msg_len; j++) {
+                const Ext m = ext_mul(s.eq_3b[i], beta_pows[j]);
+                w.insert(w.end(), m.c, m.c + 4);
+            }
+            s.denom_const = ext_add(s.denom_const,
+                                    ext_mul(s.eq_3b[i], ext_mul_base(beta_pows[it.msg_len], bb::to_mont(it.bus_index + 1))));
+        }
+        SWIRL_TRY(upload(w.data(), w.size() * 4, (void**)&s.d_weights));
+        SWIRL_CUDA(dev_alloc(ctx, &s.d_eq_xi, (size_t(4) << s.n_lift)));
+        to_free.push_back(s.d_eq_xi);
+        TensorArgs ta;
+        for (int b = 0; b < s.n_lift; b++) {
+            memcpy(ta.w0[b], ext_sub(bb::ext_one(), xi[l_skip + b]).c, 16);
+            memcpy(ta.w1[b], xi[l_skip + b].c, 16);
+        }
+        SWIRL_TRY(mle_tensor_table(ctx, ta, s.n_lift, s.d_eq_xi));
+    }
+
+    // ---- round 0 ---------------------------------------------------------------------------------------
+    const uint32_t g = bb::to_mont(31), omega_skip = bb::two_adic_generator(l_skip);
+    std::vector<uint32_t*> d_lde(D + 1, nullptr);  // per constraint degree d: [d * N][N] Lagrange table
+    for (int d = 1; d <= D; d++) {
+        bool used = false;
+        for (size_t t = 0; t < n_airs; t++) used |= (int)airs[t].constraint_degree == d;
+        if (!used) continue;
+        std::vector<uint32_t> tab((size_t)d * N * N);
+        const uint32_t n_inv = bb::inv(bb::to_mont((uint32_t)N));
+        for (int c = 0; c < d; c++) {
+            uint32_t z = bb::pow(g, (uint64_t)c + 1);
+            for (size_t zi = 0; zi < N; zi++) {
+                const uint32_t num = bb::mul(bb::sub(bb::pow(z, N), bb::R1), n_inv);
+                uint32_t wi = bb::R1;
+                for (size_t i = 0; i < N; i++) {
+                    tab[((size_t)c * N + zi) * N + i] = bb::mul(bb::mul(num, wi), bb::inv(bb::sub(z, wi)));
+                    wi = bb::mul(wi, omega_skip);
+                }
+                z = bb::mul(z, omega_skip);
+            }
+        }
+        SWIRL_TRY(upload(tab.data(), tab.size() * 4, (void**)&d_lde[d]));
+    }
+    std::vector<size_t> r0_off(n_airs + 1, 0);
+    for (size_t t = 0; t < n_airs; t++) r0_off[t + 1] = r0_off[t] + (size_t)airs[t].constraint_degree * N * 12;
+    uint32_t* d_r0 = nullptr;
+    SWIRL_CUDA(dev_alloc(ctx, &d_r0, r0_off[n_airs] + 4));
+    to_free.push_back(d_r0);
+    for (size_t t = 0; t < n_airs; t++) {
+        TraceState& s = T[t];
+        const int cd = (int)airs[t].constraint_degree;
+        if (cd == 0) continue;
+        R0Args ra{};
+        ra.code = s.d_code;
+        ra.n_instr = (uint32_t)s.prog.code.size();
+        ra.parts = s.d_parts;
+        ra.weights = s.d_weights;
+        ra.lde = d_lde[cd];
+        ra.eq_xi = s.d_eq_xi;
+        ra.l_skip = l_skip;
+        ra.n_lift = s.n_lift;
+        ra.P = (int)(cd * N);
+        const int G = std::max(1, BC_BLOCK / ra.P);
+        const int threads = ra.P * G;
+        const size_t nx = size_t(1) << s.n_lift;
+        ra.x_per_block = G * 8;
+        const size_t blocks = (nx + ra.x_per_block - 1) / ra.x_per_block;
+        uint32_t* part = nullptr;
+        SWIRL_CUDA(dev_alloc(ctx, &part, blocks * (size_t)ra.P * 12));
+        to_free.push_back(part);
+        ra.partials = part;
+#define BC_R0(NS) batch_round0_kernel<NS><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra)
+        BC_DISPATCH_NS(s.prog.n_slots, BC_R0);
+#undef BC_R0
+        SWIRL_LAUNCH_CHECK(ctx);
+        bc_reduce_kernel<<<(ra.P * 12 + 255) / 256, 256, 0, ctx->stream>>>(part, blocks, ra.P * 12, d_r0 + r0_off[t]);
+        SWIRL_LAUNCH_CHECK(ctx);
+    }
+    std::vector<uint32_t> h_r0(r0_off[n_airs] + 4);
+    SWIRL_CUDA(cudaMemcpyAsync(h_r0.data(), d_r0, r0_off[n_airs] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    // host: per-trace s'_0 polynomials (cpu.rs:324-424)
+    const size_t sp_0_deg = (size_t)D * (N - 1), s_0_deg = (size_t)(D + 1) * (N - 1);
+    std::vector<std::vector<Ext>> sp0(3 * n_airs);  // [2t] numer, [2t+1] denom, [2n + t] zerocheck
+    for (size_t t = 0; t < n_airs; t++) {
+        const TraceState& s = T[t];
+        const int cd = (int)airs[t].constraint_degree;
+        if (cd == 0) continue;
+        const uint32_t* res = &h_r0[r0_off[t]];
+        auto at = [&](int c, size_t zi, int k) { return hp::from_words(res + ((size_t)c * N + zi) * 12 + 4 * k); };
+        // zerocheck: quotient on cd - 1 cosets, then s'_0 = (Z^N - 1) q
+        {
+            std::vector<Ext> qe(N * (cd - 1));
+            for (int c = 0; c + 1 < cd; c++) {
+                const uint32_t zinv = bb::inv(bb::sub(bb::pow(bb::pow(g, (uint64_t)c + 1), N), bb::R1));
+                for (size_t zi = 0; zi < N; zi++) qe[zi * (cd - 1) + c] = ext_mul_base(at(c, zi, 0), zinv);
+            }
+            std::vector<Ext> q = cd > 1 ? hp::interpolate_geometric_cosets(qe, l_skip, cd - 1) : std::vector<Ext>();
+            const size_t deg = (size_t)cd * (N - 1);
+            std::vector<Ext> coeffs(deg + 1);
+            for (size_t i = 0; i <= deg; i++) {
+                Ext c = i < q.size() ? bb::ext_neg(q[i]) : bb::ext_zero();
+                if (i >= N) c = ext_add(c, q[i - N]);
+                coeffs[i] = c;
+            }
+            sp0[2 * n_airs + t] = coeffs;
+        }
+        if (airs[t].n_interactions) {
+            std::vector<Ext> ne(N * cd), de(N * cd);
+            for (int c = 0; c < cd; c++)
+                for (size_t zi = 0; zi < N; zi++) {
+                    ne[zi * cd + c] = at(c, zi, 1);
+                    de[zi * cd + c] = ext_add(at(c, zi, 2), s.denom_const);
+                }
+            std::vector<Ext> np = hp::interpolate_geometric_cosets(ne, l_skip, cd);
+            for (auto& c : np) c = ext_mul_base(c, s.norm);
+            sp0[2 * t] = np;
+            sp0[2 * t + 1] = hp::interpolate_geometric_cosets(de, l_skip, cd);
+        }
+    }
+    // s_0 = eq_sharp * s'_0 (logup), eq_D(xi_0, .) * batched s'_0 (zerocheck); sum claims (mod.rs:204-301)
+    std::vector<Ext> eq_sharp_coeffs;
+    {
+        std::vector<Ext> ev(N, bb::ext_zero());
+        ev[0] = bb::ext_one();
+        for (int i = 0; i < l_skip; i++)
+            for (size_t j = 0; j < (size_t(1) << i); j++) {
+                ev[(size_t(1) << i) + j] = ext_mul(ev[j], xi[i]);
+                ev[j] = ext_mul(ev[j], ext_sub(bb::ext_one(), xi[i]));
+            }
+        eq_sharp_coeffs = hp::idft_small(ev);
+    }
+    std::vector<std::vector<Ext>> s0_logup(2 * n_airs);
+    for (size_t i = 0; i < 2 * n_airs; i++) {
+        std::vector<Ext> c = sp0[i];
+        if (c.size() > sp_0_deg + 1) c.resize(sp_0_deg + 1);
+        s0_logup[i] = poly_mul(eq_sharp_coeffs, c, s_0_deg + 1);
+    }
+    for (size_t t = 0; t < n_airs; t++) {
+        Ext sums[2];
+        for (int d = 0; d < 2; d++) {
+            Ext sm = bb::ext_zero();
+            for (size_t j = 0; j <= s_0_deg; j += N) sm = ext_add(sm, s0_logup[2 * t + d][j]);
+            sums[d] = ext_mul_base(sm, bb::to_mont((uint32_t)N));
+        }
+        tr.observe_ext(sums[0]);
+        tr.observe_ext(sums[1]);
+        memcpy(sec_numer + 4 * t, sums[0].c, 16);
+        memcpy(sec_denom + 4 * t, sums[1].c, 16);
+    }
+    const Ext mu = tr.sample_ext();
+    std::vector<Ext> mu_pows(3 * n_airs);
+    {
+        Ext m = bb::ext_one();
+        for (auto& x : mu_pows) {
+            x = m;
+            m = ext_mul(m, mu);
+        }
+    }
+    std::vector<Ext> s0_zc;
+    {
+        std::vector<Ext> sp(sp_0_deg + 1, bb::ext_zero());
+        for (size_t j = 0; j <= sp_0_deg; j++)
+            for (size_t t = 0; t < n_airs; t++) {
+                const auto& poly = sp0[2 * n_airs + t];
+                if (j < poly.size()) sp[j] = ext_add(sp[j], ext_mul(mu_pows[2 * n_airs + t], poly[j]));
+            }
+        // eq_uni_poly(l_skip, xi[0]) (poly_common.rs:85-102)
+        std::vector<Ext> eq(N);
+        const uint32_t n_inv = hp::half_pow(l_skip);
+        Ext xp = xi[0];
+        std::vector<Ext> pw(N);
+        for (size_t i = 0; i < N; i++) {
+            pw[i] = ext_mul_base(xp, n_inv);
+            xp = ext_mul(xp, xi[0]);
+        }
+        for (size_t i = 0; i < N; i++) eq[i] = pw[N - 1 - i];
+        eq[0] = hp::from_base(n_inv);
+        s0_zc = poly_mul(eq, sp, s_0_deg + 1);
+    }
+    std::vector<Ext> s_0(s_0_deg + 1);
+    for (size_t j = 0; j <= s_0_deg; j++) {
+        Ext c = s0_zc[j];
+        for (size_t i = 0; i < 2 * n_airs; i++) c = ext_add(c, ext_mul(mu_pows[i], s0_logup[i][j]));
+        tr.observe_ext(c);
+        s_0[j] = c;
+        memcpy(sec_uni + 4 * j, c.c, 16);
+    }
+    std::vector<Ext> r{tr.sample_ext()};
+    const Ext r_0 = r[0];
+    Ext prev_s_eval = hp::horner(s_0, r_0);
+
+    // ---- fold_ple: all row parts of a trace into one EF buffer -------------------------------------------
+    {
+        LagrangeArgs la;
+        const std::vector<Ext> Lc = hp::lagrange_at(l_skip, r_0);
+        for (size_t i = 0; i < N; i++) memcpy(la.L[i], Lc[i].c, 16);
+        for (size_t t = 0; t < n_airs; t++) {
+            TraceState& s = T[t];
+            const swirl_air_ctx& a = airs[t];
+            s.h = s.lifted >> l_skip;
+            SWIRL_CUDA(dev_alloc(ctx, &s.ef[0], (size_t)s.total_cols * s.h * 4));
+            SWIRL_CUDA(dev_alloc(ctx, &s.ef[1], ((size_t)s.total_cols * s.h / 2 + 1) * 4));
+            to_free.push_back(s.ef[0]);
+            to_free.push_back(s.ef[1]);
+            size_t part = 0;
+            auto fold = [&](const uint32_t* mat, size_t height, size_t width, bool rot) -> int {
+                SWIRL_TRY(fold_ple(ctx, mat, height, width, rot, l_skip, la, s.ef[0] + (size_t)s.L.part_col_off[part] * s.h * 4));
+                part++;
+                return 0;
+            };
+            SWIRL_TRY(fold(s.d_sels, s.lifted, 3, false));
+            auto both = [&](const swirl_matrix& m) -> int {
+                SWIRL_TRY(fold(m.data, m.height, m.width, false));
+                if (a.need_rot) SWIRL_TRY(fold(m.data, m.height, m.width, true));
+                return 0;
+            };
+            if (a.preprocessed) SWIRL_TRY(both(*a.preprocessed));
+            for (uint64_t i = 0; i < a.n_cached; i++) SWIRL_TRY(both(a.cached_mains[i]));
+            SWIRL_TRY(both(a.common_main));
+            s.cur = 0;
+        }
+    }
+    std::vector<Ext> eq_ns{hp::eval_eq_uni(l_skip, xi[0], r_0)};
+    std::vector<Ext> eq_sharp_ns;
+    {
+        // eval_eq_sharp_uni (poly_common.rs:134-176)
+        std::vector<Ext> ev(N, bb::ext_zero());
+        ev[0] = bb::ext_one();
+        for (int i = 0; i < l_skip; i++)
+            for (size_t j = 0; j < (size_t(1) << i); j++) {
+                ev[(size_t(1) << i) + j] = ext_mul(ev[j], xi[i]);
+                ev[j] = ext_mul(ev[j], ext_sub(bb::ext_one(), xi[i]));
+            }
+        Ext res = bb::ext_zero();
+        uint32_t wi = bb::R1;
+        for (size_t i = 0; i < N; i++) {
+            res = ext_add(res, ext_mul(hp::eval_eq_uni(l_skip, r_0, hp::from_base(wi)), ev[i]));
+            wi = bb::mul(wi, omega_skip);
+        }
+        eq_sharp_ns.push_back(res);
+    }
+
+    // ---- MLE rounds (mod.rs:314-395, cpu.rs:463-597) --------------------------------------------------------
+    const int s_deg = D + 1;
+    for (int round = 1; round <= n_max; round++) {
+        const Ext r_prev = r[round - 1];
+        const Ext eq_r_acc = eq_ns.back(), eq_sharp_r_acc = eq_sharp_ns.back();
+        std::vector<int> mode(n_airs, 0);  // 0: hypercube sum, 1: single row now, 2: tail multiply
+        for (size_t t = 0; t < n_airs; t++) {
+            TraceState& s = T[t];
+            if (airs[t].constraint_degree == 0 && !airs[t].n_interactions && !airs[t].n_constraints) {
+                mode[t] = 3;
+                continue;
+            }
+            MleArgs ma{};
+            ma.code = s.d_code;
+            ma.n_instr = (uint32_t)s.prog.code.size();
+            ma.base = s.ef[s.cur];
+            ma.h = s.h;
+            ma.weights = s.d_weights;
+            ma.partials = rs->d_partials;
+            ma.ticket = rs->d_ticket;
+            ma.result = rs->d_result + t * 64;
+            SWIRL_REQUIRE(t * 64 + 64 <= 16384, "too many AIRs for the result scratch");
+            if (round > s.n_lift) {
+                if (round != s.n_lift + 1) {
+                    mode[t] = 2;
+                    continue;
+                }
+                mode[t] = 1;
+                ma.single = 1;
+                ma.ny = 1;
+                ma.eq_xi = s.d_eq_xi;
+#define BC_MLE1(NS) launch_mle<NS>(1, ma, 1, ctx->stream)
+                BC_DISPATCH_NS(s.prog.n_slots, BC_MLE1);
+#undef BC_MLE1
+                SWIRL_LAUNCH_CHECK(ctx);
+            } else {
+                const int log_ny = s.n_lift - round;
+                TensorArgs ta;
+                for (int b = 0; b < log_ny; b++) {
+                    memcpy(ta.w0[b], ext_sub(bb::ext_one(), xi[l_skip + round + b]).c, 16);
+                    memcpy(ta.w1[b], xi[l_skip + round + b].c, 16);
+                }
+                SWIRL_TRY(mle_tensor_table(ctx, ta, log_ny, s.d_eq_xi));
+                ma.single = 0;
+                ma.ny = size_t(1) << log_ny;
+                ma.eq_xi = s.d_eq_xi;
+                int grid = (int)std::min<size_t>((ma.ny + 127) / 128, (size_t)ctx->sm_count * 8);
+#define BC_MLE(NS) launch_mle<NS>(D, ma, grid, ctx->stream)
+                BC_DISPATCH_NS(s.prog.n_slots, BC_MLE);
+#undef BC_MLE
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+        }
+        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        // sp_evals[2t] numer, [2t+1] denom, [2n+t] zerocheck: D values (head) or 1 value (tail)
+        std::vector<std::vector<Ext>> sp(3 * n_airs);
+        for (size_t t = 0; t < n_airs; t++) {
+            TraceState& s = T[t];
+            const uint32_t* res = rs->h_result + t * 64;
+            const bool has_int = airs[t].n_interactions != 0;
+            if (mode[t] == 3) {
+                sp[2 * n_airs + t].assign(D, bb::ext_zero());
+                sp[2 * t].assign(D, bb::ext_zero());
+                sp[2 * t + 1].assign(D, bb::ext_zero());
+            } else if (mode[t] == 0) {
+                for (int X = 0; X < D; X++) {
+                    sp[2 * n_airs + t].push_back(hp::from_words(res + X * 12));
+                    if (has_int) {
+                        sp[2 * t].push_back(ext_mul_base(hp::from_words(res + X * 12 + 4), s.norm));
+                        sp[2 * t + 1].push_back(ext_add(hp::from_words(res + X * 12 + 8), s.denom_const));
+                    } else {
+                        sp[2 * t].push_back(bb::ext_zero());
+                        sp[2 * t + 1].push_back(bb::ext_zero());
+                    }
+                }
+            } else {
+                if (mode[t] == 1) {
+                    s.zc_tilde = ext_mul(eq_r_acc, hp::from_words(res));
+                    if (has_int) {
+                        s.lg_tilde[0] = ext_mul_base(ext_mul(eq_sharp_r_acc, hp::from_words(res + 4)), s.norm);
+                        s.lg_tilde[1] = ext_mul(eq_sharp_r_acc, ext_add(hp::from_words(res + 8), s.denom_const));
+                    }
+                } else {
+                    s.zc_tilde = ext_mul(s.zc_tilde, r_prev);
+                    s.lg_tilde[0] = ext_mul(s.lg_tilde[0], r_prev);
+                    s.lg_tilde[1] = ext_mul(s.lg_tilde[1], r_prev);
+                }
+                sp[2 * n_airs + t] = {s.zc_tilde};
+                if (has_int) {
+                    sp[2 * t] = {s.lg_tilde[0]};
+                    sp[2 * t + 1] = {s.lg_tilde[1]};
+                } else {
+                    sp[2 * t].assign(D, bb::ext_zero());
+                    sp[2 * t + 1].assign(D, bb::ext_zero());
+                }
+            }
+        }
+        size_t tail_start = n_airs;
+        for (size_t t = 0; t < n_airs; t++)
+            if (round > T[t].n) {
+                tail_start = t;
+                break;
+            }
+        std::vector<Ext> head_zc(D, bb::ext_zero()), head_lg(D, bb::ext_zero());
+        Ext sp_tail = bb::ext_zero();
+        for (size_t t = 0; t < n_airs; t++) {
+            const size_t zc = 2 * n_airs + t, nu = 2 * t, de = nu + 1;
+            if (t < tail_start) {
+                for (int i = 0; i < D; i++) {
+                    head_zc[i] = ext_add(head_zc[i], ext_mul(mu_pows[zc], sp[zc][i]));
+                    head_lg[i] = ext_add(head_lg[i], ext_add(ext_mul(mu_pows[nu], sp[nu][i]), ext_mul(mu_pows[de], sp[de][i])));
+                }
+            } else {
+                sp_tail = ext_add(sp_tail, ext_add(ext_mul(mu_pows[zc], sp[zc][0]),
+                                                   ext_add(ext_mul(mu_pows[nu], sp[nu][0]), ext_mul(mu_pows[de], sp[de][0]))));
+            }
+        }
+        std::vector<Ext> head(s_deg, bb::ext_zero());
+        for (int i = 0; i < D; i++) head[i + 1] = ext_add(ext_mul(eq_ns[round - 1], head_zc[i]), ext_mul(eq_sharp_ns[round - 1], head_lg[i]));
+        const Ext xi_cur = xi[l_skip + round - 1];
+        head[0] = ext_mul(ext_sub(ext_sub(prev_s_eval, ext_mul(xi_cur, head[1])), sp_tail), bb::ext_inv(ext_sub(bb::ext_one(), xi_cur)));
+        std::vector<Ext> coeffs = hp::lagrange_interpolate_0n(head);
+        coeffs.push_back(bb::ext_zero());
+        {
+            const Ext b = ext_sub(bb::ext_one(), xi_cur), a = ext_sub(xi_cur, b);
+            for (int i = s_deg - 1; i >= 0; i--) coeffs[i + 1] = ext_add(ext_mul(a, coeffs[i]), ext_mul(b, coeffs[i + 1]));
+            coeffs[0] = ext_mul(coeffs[0], b);
+            coeffs[1] = ext_add(coeffs[1], sp_tail);
+        }
+        for (int i = 1; i <= s_deg; i++) {
+            const Ext e = hp::horner(coeffs, hp::from_base(bb::to_mont((uint32_t)i)));
+            tr.observe_ext(e);
+            memcpy(sec_rounds + ((size_t)(round - 1) * s_deg + (i - 1)) * 4, e.c, 16);
+        }
+        const Ext r_round = tr.sample_ext();
+        r.push_back(r_round);
+        prev_s_eval = hp::horner(coeffs, r_round);
+        for (size_t t = 0; t < n_airs; t++) {
+            TraceState& s = T[t];
+            if (s.h <= 1) continue;
+            SWIRL_TRY(ef_fold_flat(ctx, s.ef[s.cur], s.ef[s.cur ^ 1], (size_t)s.total_cols * (s.h / 2), r_round));
+            s.cur ^= 1;
+            s.h >>= 1;
+        }
+        const Ext eq_r = hp::eq1(xi_cur, r_round);
+        eq_ns.push_back(ext_mul(eq_ns[round - 1], eq_r));
+        eq_sharp_ns.push_back(ext_mul(eq_sharp_ns[round - 1], eq_r));
+    }
+
+    // ---- column openings (cpu.rs:644-694), observed common-main first (mod.rs:404-421) ------------------------
+    std::vector<std::vector<uint32_t>> rows(n_airs);
+    for (size_t t = 0; t < n_airs; t++) {
+        TraceState& s = T[t];
+        SWIRL_REQUIRE(s.h == 1, "internal: tables not fully folded");
+        rows[t].resize((size_t)s.total_cols * 4);
+        SWIRL_CUDA(cudaMemcpyAsync(rows[t].data(), s.ef[s.cur], rows[t].size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::vector<std::vector<Ext>>> openings(n_airs);
+    uint32_t* po = sec_open;
+    for (size_t t = 0; t < n_airs; t++) {
+        const TraceState& s = T[t];
+        const uint32_t stride = s.L.stride;
+        auto part_open = [&](uint32_t first_part) {
+            std::vector<Ext> v;
+            const uint32_t w = s.L.part_width[first_part];
+            for (uint32_t c = 0; c < w; c++)
+                for (uint32_t k = 0; k < stride; k++)
+                    v.push_back(hp::from_words(&rows[t][(size_t)(s.L.part_col_off[first_part + k] + c) * 4]));
+            return v;
+        };
+        openings[t].push_back(part_open(s.L.n_parts - stride));  // common main
+        for (uint32_t pt = 1; pt + stride < s.L.n_parts; pt += stride) openings[t].push_back(part_open(pt));
+        for (auto& part : openings[t])
+            for (const Ext& e : part) {
+                memcpy(po, e.c, 16);
+                po += 4;
+            }
+    }
+    auto observe_part = [&](const std::vector<Ext>& part, bool need_rot) {
+        for (const Ext& e : part) {
+            tr.observe_ext(e);
+            if (!need_rot) tr.observe_ext(bb::ext_zero());
+        }
+    };
+    for (size_t t = 0; t < n_airs; t++) observe_part(openings[t][0], airs[t].need_rot != 0);
+    for (size_t t = 0; t < n_airs; t++)
+        for (size_t pt = 1; pt < openings[t].size(); pt++) observe_part(openings[t][pt], airs[t].need_rot != 0);
+    for (size_t i = 0; i < r.size(); i++) memcpy(h_r + 4 * i, r[i].c, 16);
+    return 0;
+}

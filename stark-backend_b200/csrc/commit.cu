@@ -20,7 +20,7 @@
 namespace swirl {
 
 // sorted = (width, log_height), descending log_height
-static int make_layout(int l_skip, int log_stacked_height, size_t n, const uint64_t* widths,
+int make_layout(int l_skip, int log_stacked_height, size_t n, const uint64_t* widths,
                        const int32_t* log_heights, Layout* out) {
     out->l_skip = l_skip;
     out->height = uint64_t(1) << log_stacked_height;

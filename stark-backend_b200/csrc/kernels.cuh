@@ -1,5 +1,6 @@
 // Internal (non-ABI) entry points shared between the translation units of libswirl_b200.
 #pragma once
+#include "bb31.cuh"
 #include "common.cuh"
 
 namespace swirl {
@@ -41,6 +42,12 @@ struct TensorArgs {  // per variable b: the factor for bit b clear (w0) / set (w
 };
 int mle_tensor_table(swirl_ctx* ctx, const TensorArgs& t, int n_vars, uint32_t* d_out);
 int mle_zeta(swirl_ctx* ctx, uint32_t* d_data, size_t col_stride, int log_n, size_t cols, bool inverse);
+struct LagrangeArgs {  // Lagrange coefficients of D = <w_(2^l_skip)> at the folding point
+    uint32_t L[64][4];
+};
+int ef_fold_flat(swirl_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n_out, const bb::Ext& r);
+int fold_ple(swirl_ctx* ctx, const uint32_t* mat, size_t height, size_t width, bool is_rot, int l_skip, const LagrangeArgs& la,
+             uint32_t* out);
 int ext_aos_to_soa(swirl_ctx* ctx, const uint32_t* aos, uint32_t* soa, size_t n, size_t col_stride);
 int ext_soa_to_aos(swirl_ctx* ctx, const uint32_t* soa, uint32_t* aos, size_t n, size_t col_stride);
 

@@ -150,4 +150,49 @@ int ext_soa_to_aos(swirl_ctx* ctx, const uint32_t* soa, uint32_t* aos, size_t n,
     return 0;
 }
 
+// out[j] = in[2j] + (in[2j+1] - in[2j]) * r over a flat EF array: folds the low variable of every
+// column of a column-major EF matrix with even height (fold_mle_evals, sumcheck.rs:395-414)
+__global__ void __launch_bounds__(MLE_BLOCK)
+ef_fold_flat_kernel2(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n_out, Ext r) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    st_ext(out + 4 * j, ext_lerp(ldg_ext(in + 8 * j), ldg_ext(in + 8 * j + 4), r));
+}
+int ef_fold_flat(swirl_ctx* ctx, const uint32_t* in, uint32_t* out, size_t n_out, const Ext& r) {
+    if (!n_out) return 0;
+    ef_fold_flat_kernel2<<<(unsigned)((n_out + MLE_BLOCK - 1) / MLE_BLOCK), MLE_BLOCK, 0, ctx->stream>>>(in, out, n_out, r);
+    SWIRL_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// out[c][x] = sum_i L_i * mat[c][(x * 2^l + i + rot) mod height]: every 2^l_skip chunk's interpolant
+// over D evaluated at the point whose Lagrange coefficients are L (fold_ple_evals, sumcheck.rs:204-251).
+// out is column-major EF with height max(height, 2^l) >> l.
+__global__ void __launch_bounds__(MLE_BLOCK)
+fold_ple_kernel(const uint32_t* __restrict__ mat, size_t height, size_t new_height, size_t total, int l_skip, int rot,
+                LagrangeArgs la, uint32_t* __restrict__ out) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const size_t c = g / new_height, x = g % new_height;
+    const uint32_t* col = mat + c * height;
+    Ext acc = bb::ext_zero();
+    const int N = 1 << l_skip;
+    for (int i = 0; i < N; i++) {
+        const size_t row = ((x << l_skip) + i + rot) % height;
+        acc = bb::ext_add(acc, bb::ext_mul_base(Ext{{la.L[i][0], la.L[i][1], la.L[i][2], la.L[i][3]}}, __ldg(col + row)));
+    }
+    st_ext(out + 4 * g, acc);
+}
+int fold_ple(swirl_ctx* ctx, const uint32_t* mat, size_t height, size_t width, bool is_rot, int l_skip, const LagrangeArgs& la,
+             uint32_t* out) {
+    SWIRL_REQUIRE(l_skip <= 6, "l_skip > 6 unsupported");
+    const size_t N = size_t(1) << l_skip;
+    const size_t new_height = (height > N ? height : N) >> l_skip, total = new_height * width;
+    if (!total) return 0;
+    fold_ple_kernel<<<(unsigned)((total + MLE_BLOCK - 1) / MLE_BLOCK), MLE_BLOCK, 0, ctx->stream>>>(mat, height, new_height, total,
+                                                                                              l_skip, is_rot ? 1 : 0, la, out);
+    SWIRL_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 }  // namespace swirl

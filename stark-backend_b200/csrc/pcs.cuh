@@ -20,6 +20,10 @@ struct Layout {
     std::vector<LayoutCol> cols;
 };
 
+// StackedLayout::new (prover/stacked_pcs.rs:144-203); `sorted` = (width, log_height) by descending height
+int make_layout(int l_skip, int log_stacked_height, size_t n, const uint64_t* widths, const int32_t* log_heights,
+                Layout* out);
+
 }  // namespace swirl
 
 struct swirl_pcs {

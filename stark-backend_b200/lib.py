@@ -42,6 +42,22 @@ class MatrixC(C.Structure):
     _fields_ = [("data", C.c_void_p), ("height", C.c_uint64), ("width", C.c_uint64)]
 
 
+class DagNodeC(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("a", C.c_uint32), ("b", C.c_uint32), ("c", C.c_uint32)]
+
+
+class InteractionC(C.Structure):
+    _fields_ = [("count_node", C.c_uint32), ("bus_index", C.c_uint32), ("msg_offset", C.c_uint32), ("msg_len", C.c_uint32)]
+
+
+class AirCtxC(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_uint64), ("constraint_idx", C.c_void_p), ("n_constraints", C.c_uint64),
+                ("interactions", C.c_void_p), ("n_interactions", C.c_uint64), ("msg_nodes", C.c_void_p),
+                ("constraint_degree", C.c_uint32), ("need_rot", C.c_uint32), ("public_values", C.c_void_p),
+                ("n_public_values", C.c_uint64), ("common_main", MatrixC), ("cached_mains", C.c_void_p), ("n_cached", C.c_uint64),
+                ("preprocessed", C.c_void_p)]
+
+
 _vp, _sz, _i, _u32, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64
 
 # name -> (restype, argtypes); every prototype of include/swirl_b200.h
@@ -89,6 +105,8 @@ PROTOTYPES = {
     "swirl_whir_open": (_i, [_vp, C.POINTER(TranscriptC), C.POINTER(WhirConfigC), _vp, _sz, _vp, _vp, _sz]),
     "swirl_stacked_reduction_proof_words": (_sz, [_vp, _sz]),
     "swirl_stacked_reduction": (_i, [_vp, C.POINTER(TranscriptC), _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "swirl_batch_constraints_proof_words": (_sz, [_i, _i, _vp, _sz]),
+    "swirl_prove_batch_constraints": (_i, [_vp, C.POINTER(TranscriptC), _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
 }
 

@@ -82,3 +82,49 @@ def test_oracle_unbalanced_logup_is_an_error(oracle):
     st = np.zeros(18, np.uint32)
     with pytest.raises(ValueError):
         oracle.bc_prove(st, 2, 2, 0, A.flatten([s, r]), 2, 2)
+
+
+def to_device_airs(dev, airs):
+    out = []
+    for a in airs:
+        dm = lambda m: sb.DeviceMatrix(dev.h2d(m[0]), m[1], m[2])
+        out.append(sb.AirProvingContext(a.nodes, a.constraint_idx, a.interactions, a.constraint_degree, a.need_rot,
+                                        dm(a.common_main), a.public_values, [dm(m) for m in a.cached],
+                                        dm(a.preprocessed) if a.preprocessed is not None else None))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.__name__)
+def test_gpu_batch_constraints_match_oracle(dev, oracle, case):
+    l_skip, D, pow_bits, airs, n_max, st = setup(oracle, case, seed=5)
+    ts = sb.Transcript(st)
+    want, r = oracle.bc_prove(st, l_skip, D, pow_bits, A.flatten(airs), len(airs), n_max)
+    got, rg = dev.prove_batch_constraints(ts, l_skip, D, pow_bits, to_device_airs(dev, airs))
+    assert got.size == want.size
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, f"first mismatch at word {bad[0]} of {got.size}"
+    assert np.array_equal(rg, r) and np.array_equal(ts.words(), st)
+
+
+@pytest.mark.gpu
+def test_gpu_unbalanced_logup_is_an_error(dev, oracle):
+    rng = np.random.default_rng(4)
+    s, r = A.sender_receiver(4, 2, rng, balanced=False)
+    with pytest.raises(sb.SwirlError) as e:
+        dev.prove_batch_constraints(sb.Transcript(), 2, 2, 0, to_device_airs(dev, [s, r]))
+    assert e.value.code == 10005
+
+
+@pytest.mark.gpu
+def test_gpu_batch_constraints_large_accepted_by_oracle_verifier(dev, oracle):
+    # 2^12-row BenchmarkAir (24 columns, 24 constraints, 6 interaction pairs) + a Fibonacci trace
+    rng = np.random.default_rng(9)
+    airs = sorted_airs([A.benchmark(12, 24, 24, 6, rng), A.fibonacci(10)])
+    l_skip, D, pow_bits = 4, 2, 6
+    n_max = 12 - l_skip
+    st = np.zeros(18, np.uint32)
+    ts = sb.Transcript(st)
+    proof, r = dev.prove_batch_constraints(ts, l_skip, D, pow_bits, to_device_airs(dev, airs))
+    ok, rv = oracle.bc_verify(st, l_skip, D, pow_bits, A.flatten(airs), len(airs), n_max, proof)
+    assert ok and np.array_equal(rv, r) and np.array_equal(st, ts.words())
