@@ -296,6 +296,13 @@ int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* ts, int l_sk
                                   int logup_pow_bits, const swirl_air_ctx* airs, size_t n_airs, uint32_t* h_proof,
                                   size_t proof_words, uint32_t* h_r);
 
+/* ---- phase level: OpeningProver::prove_openings (hal.rs:118-138; cpu_backend.rs:139-220) =
+ *      swirl_stacked_reduction, u_cube = (u_0^(2^i))_{i<l_skip} ++ u[1..], swirl_whir_open.
+ *      Buffers as in those two calls. -------------------------------------------------------------- */
+int swirl_prove_openings(swirl_ctx* ctx, swirl_transcript* ts, const swirl_whir_config* cfg, const swirl_pcs* const* pcs,
+                         size_t n_commits, const uint8_t* const* need_rot, const uint32_t* h_r, size_t r_len,
+                         uint32_t* h_stacking_proof, size_t stacking_words, uint32_t* h_whir_proof, size_t whir_words);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,3 +16,4 @@ from .backend import (  # noqa: F401
     to_mont,
     from_mont,
 )
+from .prover import AirProvingKey, CommittedTraceData, Coordinator, Proof, SystemParams  # noqa: F401,E402

@@ -498,6 +498,25 @@ class B200Device:
         return dict(univariate_round_coeffs=proof[:n0].reshape(-1, 4), sumcheck_round_polys=proof[n0:n1].reshape(-1, 2, 4),
                     stacking_openings=openings, u=u, flat=proof)
 
+    # -- OpeningProver::prove_openings (cpu_backend.rs:139-220) -------------------------------------------
+    def prove_openings(self, ts, whir_cfg, pcs_list, need_rot_per_commit, r):
+        """Returns (flat StackingProof words, flat WhirProof words)."""
+        handles = (C.c_void_p * len(pcs_list))(*[d._h for d in pcs_list])
+        cc, pc = whir_cfg.c(), pcs_list[0].params.c()
+        widths = np.array([d.width for d in pcs_list], dtype=np.uint64)
+        n_st = int(self.lib.swirl_stacked_reduction_proof_words(handles, len(pcs_list)))
+        n_wh = int(self.lib.swirl_whir_proof_words(C.byref(pc), C.byref(cc), len(pcs_list), widths.ctypes.data))
+        if n_wh == 0:
+            raise _lib.SwirlError(10001, "invalid WHIR configuration")
+        st, wh = np.zeros(n_st, dtype=np.uint32), np.zeros(n_wh, dtype=np.uint32)
+        rots = [np.asarray([1 if b else 0 for b in rr], dtype=np.uint8) for rr in need_rot_per_commit]
+        rot_ptrs = (C.c_void_p * len(rots))(*[a.ctypes.data for a in rots])
+        r = np.ascontiguousarray(r, dtype=np.uint32)
+        self._sync_torch()
+        check(self.lib.swirl_prove_openings(self.ctx, C.byref(ts.c), C.byref(cc), handles, len(pcs_list), rot_ptrs, r.ctypes.data,
+                                            r.size // 4, st.ctypes.data, n_st, wh.ctypes.data, n_wh))
+        return st, wh
+
     # -- WHIR opening (prove_whir_opening, prover/whir.rs:78-341) -----------------------------------
     def whir_open(self, ts, cfg, params, pcs_list, u):
         """pcs_list: StackedPcsData (common main first).  u: (l_skip+n_stack, 4) Montgomery words.

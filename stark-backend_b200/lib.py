@@ -107,6 +107,7 @@ PROTOTYPES = {
     "swirl_stacked_reduction": (_i, [_vp, C.POINTER(TranscriptC), _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp]),
     "swirl_batch_constraints_proof_words": (_sz, [_i, _i, _vp, _sz]),
     "swirl_prove_batch_constraints": (_i, [_vp, C.POINTER(TranscriptC), _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
+    "swirl_prove_openings": (_i, [_vp, C.POINTER(TranscriptC), C.POINTER(WhirConfigC), _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _sz]),
     "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
 }
 

@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference prover driver over the C ABI.
+
+reference: Coordinator::prove (crates/stark-backend/src/prover/mod.rs:104-198) driving a
+ProverDevice = TraceCommitter + MultiRapProver + OpeningProver (prover/hal.rs:65-138); model
+implementation crates/cuda-backend/src/gpu_backend.rs:44-212.  Every compute step is a call into
+libswirl_b200.so; this file only sequences them and feeds the transcript, as the Rust Coordinator does.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .backend import PcsParams, Transcript, WhirConfig
+from .lib import check
+
+
+class SystemParams:
+    """reference: SystemParams (config.rs:36-50)."""
+
+    def __init__(self, l_skip, n_stack, log_blowup, whir, logup_pow_bits, max_constraint_degree):
+        self.l_skip, self.n_stack, self.log_blowup = l_skip, n_stack, log_blowup
+        self.whir, self.logup_pow_bits, self.max_constraint_degree = whir, logup_pow_bits, max_constraint_degree
+
+    def pcs(self):
+        return PcsParams(self.l_skip, self.n_stack, self.log_blowup, self.whir.k)
+
+
+class CommittedTraceData:
+    """reference: CommittedTraceData (prover/types.rs:61-68): commitment + trace + PcsData."""
+
+    def __init__(self, commitment, trace, data):
+        self.commitment, self.trace, self.data = commitment, trace, data
+
+
+class AirProvingKey:
+    """The parts of DeviceStarkProvingKey the driver reads (prover/types.rs:90-110)."""
+
+    def __init__(self, is_required=True, preprocessed_data=None):
+        self.is_required, self.preprocessed_data = is_required, preprocessed_data
+
+
+class Proof:
+    """reference: Proof (proof.rs:20-60), field elements as Montgomery words, sub-proofs flat in the
+    layouts documented in include/swirl_b200.h."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def words(self):
+        return np.concatenate([self.common_main_commit, self.constraints_proof, self.stacking_proof, self.whir_proof])
+
+
+class Coordinator:
+    def __init__(self, device, params, transcript=None):
+        self.device, self.params = device, params
+        self.transcript = transcript if transcript is not None else Transcript()
+
+    def prove(self, vk_pre_hash, per_air_pk, per_trace):
+        """per_air_pk: list of AirProvingKey indexed by air id.  per_trace: list of
+        (air_id, AirProvingContext, [CommittedTraceData cached mains]) — sorted here as
+        ProvingContext::into_sorted does (height descending, then air id; prover/types.rs:144-148)."""
+        dev, ts, P = self.device, self.transcript, self.params
+        ts.observe(vk_pre_hash)
+        per_trace = sorted(per_trace, key=lambda t: (-t[1].common_main.height(), t[0]))
+        root, common = dev.commit(P.pcs(), [t[1].common_main for t in per_trace])
+        ts.observe(root)
+        present = {t[0]: t for t in per_trace}
+        for air_id, pk in enumerate(per_air_pk):
+            t = present.get(air_id)
+            if not pk.is_required:
+                ts.observe(np.array([0x0FFFFFFE if t is not None else 0], dtype=np.uint32))
+            if t is not None:
+                if pk.preprocessed_data is not None:
+                    ts.observe(pk.preprocessed_data.commitment)
+                else:
+                    ts.observe(np.array([_to_mont(t[1].common_main.height().bit_length() - 1)], dtype=np.uint32))
+                for cd in t[2]:
+                    ts.observe(cd.commitment)
+                ts.observe(t[1].public_values)
+        airs = [t[1] for t in per_trace]
+        constraints_proof, r = dev.prove_batch_constraints(ts, P.l_skip, P.max_constraint_degree, P.logup_pow_bits, airs)
+        # prove_openings (cpu_backend.rs:139-220)
+        pcs_list, need_rot = [common], [[a.need_rot for a in airs]]
+        for air_id, a, cached in per_trace:
+            pk = per_air_pk[air_id]
+            for cd in ([pk.preprocessed_data] if pk.preprocessed_data is not None else []) + list(cached):
+                pcs_list.append(cd.data)
+                need_rot.append([a.need_rot])
+        stacking, whir = dev.prove_openings(ts, P.whir, pcs_list, need_rot, r)
+        return Proof(common_main_commit=root, constraints_proof=constraints_proof, stacking_proof=stacking, whir_proof=whir,
+                     r=r, public_values=[a.public_values for a in airs], common_main_pcs=common,
+                     log_heights=[a.common_main.height().bit_length() - 1 for a in airs])
+
+
+def _to_mont(x):
+    return int((int(x) % 0x78000001) * (1 << 32) % 0x78000001)
