@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — headline measurement of the SWIRL commit hot path on B200.
+"""bench.py — headline measurement of the SWIRL prover hot path on B200.
 
-One "step" = one stacked_commit (stacking + Reed–Solomon LDE + Poseidon2 Merkle tree) of
-BASELINE.json configs[1]: a single AIR of 2^20 rows x 256 columns of uniform random BabyBear
-elements, app parameters (l_skip 4, log_blowup 1, k_whir 4), stacked height 2^20 (W = 256,
-codeword 2^21 x 256).  Metric: trace cells per second.
+One "step" = one full proof (Coordinator::prove, prover/mod.rs:104-198: stacked commit, LogUp-GKR +
+batch constraint sumcheck, stacked opening reduction, WHIR opening) of BASELINE.json configs[1]:
+a single BenchmarkAir (benchmarks/synthetic/src/bin/uniform_runner.rs:78-113) of 2^20 rows x 256
+columns — 256 boolean constraints, 32 self-cancelling send/receive pairs on bus 0 — under
+app_params_with_100_bits_security(20) (stark-sdk/src/config/mod.rs:121-138: l_skip 4, n_stack 16,
+log_blowup 1, k_whir 4, WHIR queries 193/88/81, PoW bits 18/15/5/20, max constraint degree 3).
+Metric: trace cells per second (cells = rows x columns of the common main trace).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl swirl|reference]
 
-`value`   : device-timed (CUDA events on the library's stream), traces resident in HBM.
-`e2e`     : the same through swirl_commit_host with pinned HOST buffers (H2D inside the timing).
-`roofline`: the dominant kernel (fused leaf hash) timed live with CUDA events inside the region.
+`value`   : device-timed (CUDA events on the library's stream), trace resident in HBM.
+`e2e`     : the same with the trace in pinned HOST memory: H2D copy inside the timed region; the
+            proof (about 3.4 MB) is produced in host memory by every step anyway.
+`roofline`: the dominant kernel family, timed live with CUDA events inside the timed region.
 `--impl reference`: the CPU restatement of the reference algorithm (oracle/, kind "port": no Rust
-toolchain exists in this image so the reference itself cannot be built) on all host cores.
-N > 1: one process per GPU (torchrun), every rank commits its own AIR trace (independent
-commitments, weak scaling), the 32-byte roots are all-gathered over NCCL.
+            toolchain exists in this image, so the reference crates cannot be built) on a bounded
+            sample of the same workload.
+N > 1: one process per GPU (torchrun); every rank proves its own trace of the same shape
+(independent proofs, "replicas only" — SURVEY §8e fallback; the 32-byte commitments are
+all-gathered over NCCL), weak scaling.
 """
 import argparse
 import json
@@ -32,14 +38,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 LOG_ROWS, COLS = 20, 256
 L_SKIP, LOG_BLOWUP, K_WHIR = 4, 1, 4
-N_STACK = LOG_ROWS - L_SKIP
+MAX_CONSTRAINT_DEGREE, LOGUP_POW, MU_POW, FOLD_POW, QUERY_POW, LOG_FINAL_POLY = 3, 18, 15, 5, 20, 10
 CELLS = (1 << LOG_ROWS) * COLS
 WORKLOAD = (
-    "BASELINE configs[1]: 1 AIR 2^20 rows x 256 cols (uniform random BabyBear, seed 42), app params "
-    "l_skip=4 log_blowup=1 k_whir=4 n_stack=16 -> stacked 2^20 x 256, codeword 2^21 x 256: "
-    "stack + RS/LDE + Poseidon2 Merkle commit (TraceCommitter::commit)"
+    "BASELINE configs[1]: full prove of 1 BenchmarkAir 2^20 rows x 256 cols (256 assert_bool constraints, 32 "
+    "send/receive pairs on bus 0; random boolean trace, seed 42), app_params_with_100_bits_security(20): l_skip=4 "
+    "n_stack=16 log_blowup=1 k_whir=4, WHIR queries 193/88/81, pow bits logup 18 / mu 15 / fold 5 / query 20, "
+    "max_constraint_degree 3 -> commit (LDE 2^21 x 256 + Poseidon2 Merkle) + LogUp-GKR (2^27 leaves) + batch "
+    "constraint sumcheck + stacked reduction + WHIR"
 )
 P = 0x78000001
+R1 = 0x0FFFFFFE  # Montgomery 1
 
 
 def peaks():
@@ -83,10 +92,11 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
-def gen_trace(seed):
-    rng = np.random.default_rng(seed)
-    canon = rng.integers(0, P, size=CELLS, dtype=np.uint64)
-    return ((canon << np.uint64(32)) % np.uint64(P)).astype(np.uint32)  # Montgomery words
+def benchmark_air_dag(cols):
+    """BenchmarkAir as a DAG: cols assert_bool constraints, cols/8 send+receive pairs (the trace comes separately)."""
+    import airs as A
+
+    return A.benchmark(3, cols, cols, cols // 8, np.random.default_rng(0))
 
 
 def load_oracle():
@@ -98,20 +108,43 @@ def load_oracle():
     return oracle_lib.Oracle(path)
 
 
-def cpu_commit_sample(oracle, log_rows, reps=1):
-    """Times the oracle's stacked_commit on a bounded sample: 2^log_rows rows x 256 cols, same
-    parameters (n_stack shrunk with the height).  Returns (cells/s, seconds, description)."""
+def whir_queries(log_stacked_height):
+    import math
+
+    level, rate, out = 100 - QUERY_POW, LOG_BLOWUP, []
+    for _ in range(-(-(log_stacked_height - LOG_FINAL_POLY) // K_WHIR)):
+        out.append(math.ceil(level / -math.log2((1.0 + 2.0 ** (-rate)) / 2.0)))
+        rate += K_WHIR - 1
+    return out
+
+
+def cpu_prove_sample(oracle, log_rows):
+    """The oracle's full proof of the same AIR at 2^log_rows rows (same parameters except that the stacked
+    height shrinks with the trace).  Returns (cells/s, seconds, description)."""
+    import airs as A
+
     rng = np.random.default_rng(42)
+    air = benchmark_air_dag(COLS)
     h = 1 << log_rows
-    canon = rng.integers(0, P, size=h * COLS, dtype=np.uint64)
-    vals = ((canon << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
-    best = None
-    for _ in range(reps):
-        t = time.perf_counter()
-        oracle.stacked_commit(L_SKIP, log_rows - L_SKIP, LOG_BLOWUP, K_WHIR, [(vals, h, COLS)], want_codeword=False)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    return h * COLS / best, best, f"2^{log_rows} rows x {COLS} cols (1/{1 << (LOG_ROWS - log_rows)} of the workload), same params"
+    air.common_main = ((rng.integers(0, 2, size=h * COLS, dtype=np.uint64) * R1).astype(np.uint32), h, COLS)
+    n_stack = log_rows - L_SKIP
+    cfg = dict(k=K_WHIR, num_queries=whir_queries(log_rows), mu_pow_bits=MU_POW, query_phase_pow_bits=QUERY_POW,
+               folding_pow_bits=FOLD_POW)
+    t = time.perf_counter()
+    st = np.zeros(18, np.uint32)
+    root, _, _, _ = oracle.stacked_commit(L_SKIP, n_stack, LOG_BLOWUP, K_WHIR, [air.common_main], want_codeword=False)
+    oracle.sponge_observe(st, root)
+    bc, r = oracle.bc_prove(st, L_SKIP, MAX_CONSTRAINT_DEGREE, LOGUP_POW, A.flatten([air]), 1, n_stack)
+    commits = [[air.common_main + (False,)]]
+    _, u, _ = oracle.stacked_reduction_prove(st, L_SKIP, n_stack, commits, r)
+    u_cube = [u[0]]
+    for _ in range(L_SKIP - 1):
+        u_cube.append(oracle.ef_mul(u_cube[-1], u_cube[-1]))
+    u_cube = np.array(u_cube + list(u[1:]), dtype=np.uint32)
+    oracle.whir_prove(st, L_SKIP, LOG_BLOWUP, cfg, [(air.common_main[0], COLS)], h, u_cube)
+    dt = time.perf_counter() - t
+    return h * COLS / dt, dt, (f"full proof of the same AIR at 2^{log_rows} rows x {COLS} cols (1/{1 << (LOG_ROWS - log_rows)} of the "
+                               f"workload; n_stack {n_stack}, WHIR queries {cfg['num_queries']}, same PoW bits)")
 
 
 def run_reference(args):
@@ -120,37 +153,36 @@ def run_reference(args):
         return
     oracle = load_oracle()
     cores = os.cpu_count() or 1
-    log_rows = 15
+    log_rows = 12
     for _ in range(args.warmup):
-        cpu_commit_sample(oracle, 12)
+        cpu_prove_sample(oracle, 11)
     times = []
-    for _ in range(args.steps):
-        v, dt, sample = cpu_commit_sample(oracle, log_rows)
+    for _ in range(max(1, args.steps)):
+        v, dt, sample = cpu_prove_sample(oracle, log_rows)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = (1 << log_rows) * COLS / (ms / 1e3)
     print(json.dumps({
         "impl": "reference", "metric": "trace_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the reference col-major prover; only its commit phase is multi-threaded"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def int_pipe_roofline(perms, ms, clocks):
-    """Integer-multiplier roofline of a Poseidon2 kernel.  Measured on B200 (tools/int_roofline.cu,
-    profiles/r1_p2_iterate_ncu.txt): 32-bit integer multiplies issue only on the fma-heavy pipe,
-    64 lanes/clk/SM, IMAD 1 pass, IMAD.WIDE / IMAD.HI 2 passes.  A Montgomery product needs
-    IMAD.WIDE + IMAD + IMAD.HI = 5 passes; one permutation has 564 S-box products and 91 IMADs of
-    the internal diagonal => 2911 passes minimum."""
-    passes = 564 * 5 + 91
-    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-    peak = 64 * 148 * mhz * 1e6 / passes / 1e9
-    ach = perms / (ms / 1e3) / 1e9 if ms else 0.0
-    return {"perms_per_launch": perms, "gperm_per_s": ach, "peak_gperm_per_s": peak, "frac": ach / peak,
-            "model": "fma-heavy pipe, 64 lanes/clk/SM x 148 SM x sm_max_mhz / 2911 multiplier passes per permutation"}
+# kernel families of swirl_ctx_timing_read with the algorithmic bytes of one launch on this workload
+def family_bytes():
+    N, W = 1 << (LOG_ROWS + LOG_BLOWUP), COLS
+    H = 1 << LOG_ROWS
+    return {
+        # read the codeword once, write digest layer 0
+        "leaf": 4 * N * W + 32 * (N >> K_WHIR),
+        # read every column chunk once (the sweep over the H x W trace + 3 selector columns)
+        "bc_round0": 4 * H * (W + 3),
+    }
 
 
 def run_swirl(args):
@@ -158,6 +190,7 @@ def run_swirl(args):
     import torch.distributed as dist
 
     import stark_backend_b200 as sb
+    from stark_backend_b200.lib import check
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -166,10 +199,15 @@ def run_swirl(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = sb.B200Device(local)
-    params = sb.PcsParams(L_SKIP, N_STACK, LOG_BLOWUP, K_WHIR)
-    host = torch.from_numpy(gen_trace(42 + rank).view(np.int32)).pin_memory()
-    trace = sb.DeviceMatrix(host.to(dev.torch_device), 1 << LOG_ROWS, COLS)
+    whir = sb.WhirConfig(K_WHIR, whir_queries(LOG_ROWS), MU_POW, QUERY_POW, FOLD_POW)
+    params = sb.SystemParams(L_SKIP, LOG_ROWS - L_SKIP, LOG_BLOWUP, whir, LOGUP_POW, MAX_CONSTRAINT_DEGREE)
+    air = benchmark_air_dag(COLS)
+    rng = np.random.default_rng(42 + rank)
+    host = torch.from_numpy((rng.integers(0, 2, size=CELLS, dtype=np.uint64) * R1).astype(np.uint32).view(np.int32)).pin_memory()
+    trace_dev = host.to(dev.torch_device)
     stream = dev.torch_stream()
+    vk_pre_hash = np.arange(8, dtype=np.uint32)
+    pk = [sb.AirProvingKey(True, None)]
     roots_dev = torch.zeros(8, dtype=torch.int32, device=dev.torch_device)
 
     def barrier():
@@ -177,18 +215,25 @@ def run_swirl(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def prove(trace_tensor):
+        ctx = sb.AirProvingContext(air.nodes, air.constraint_idx, air.interactions, 2, False,
+                                   sb.DeviceMatrix(trace_tensor, 1 << LOG_ROWS, COLS))
+        proof = sb.Coordinator(dev, params).prove(vk_pre_hash, pk, [(0, ctx, [])])
+        proof.common_main_pcs.free()
+        return proof
+
     def step_device():
-        root, pcs = dev.commit(params, [trace])
-        pcs.free()
-        return root
+        return prove(trace_dev)
+
+    trace_e2e = torch.empty_like(trace_dev)
 
     def step_host():
-        root, pcs = dev.commit_host(params, [(host, 1 << LOG_ROWS, COLS)])
-        pcs.free()
-        return root
+        # H2D of the whole trace from pinned host memory on the library's stream, then the proof
+        check(dev.lib.swirl_memcpy_h2d(dev.ctx, trace_e2e.data_ptr(), host.data_ptr(), 4 * CELLS))
+        return prove(trace_e2e)
 
     def gather(root):
-        if world > 1:  # only the 32-byte roots cross NVLink
+        if world > 1:  # only the 32-byte commitments cross NVLink
             roots_dev.copy_(torch.from_numpy(root.view(np.int32)))
             out = [torch.empty_like(roots_dev) for _ in range(world)]
             dist.all_gather(out, roots_dev)
@@ -201,9 +246,9 @@ def run_swirl(args):
         t0 = time.time()
         a.record(stream)
         for _ in range(steps):
-            root = fn()
+            proof = fn()
         b.record(stream)
-        roots = gather(root)
+        roots = gather(proof.common_main_commit)
         barrier()
         t1 = time.time()
         ms = a.elapsed_time(b)
@@ -211,72 +256,96 @@ def run_swirl(args):
             t = torch.tensor([ms], device=dev.torch_device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, roots, t0, t1
+        return ms, roots, t0, t1, proof
 
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
-    dev.timing_enable(True)
     l0 = dev.launch_count()
-    ms, roots, t0, t1 = timed(step_device, args.steps)
+    ms, roots, t0, t1, proof = timed(step_device, args.steps)
     launches = dev.launch_count() - l0
+    # per-kernel-family durations: the same K steps again with the library's CUDA-event spans on
+    # (an event pair per launch costs ~40% on this launch-heavy step, so it is kept out of `value`)
+    dev.timing_enable(True)
+    timed(step_device, args.steps)
     spans = dev.timing_read()
     dev.timing_enable(False)
-    clocks = sampler.stop(t0, t1)
+    clocks = sampler.stop(t0, time.time())
     ms_step = ms / args.steps
     value = world * CELLS / (ms_step / 1e3)
 
     # end to end through host buffers
     step_host()
-    ms_e2e, roots_e2e, _, _ = timed(step_host, args.steps)
+    ms_e2e, roots_e2e, _, _, proof_e2e = timed(step_host, args.steps)
     e2e_value = world * CELLS / (ms_e2e / args.steps / 1e3)
     assert all(np.array_equal(a, b) for a, b in zip(roots, roots_e2e)), "device and host paths disagree"
+    assert np.array_equal(proof.words(), proof_e2e.words()), "device and host paths produce different proofs"
 
     if rank == 0:
-        pk, pk_kind = peaks()
-        N, W = 1 << (LOG_ROWS + LOG_BLOWUP), COLS
-        leaf_ms, leaf_n = spans["leaf"]
-        leaf_avg = leaf_ms / max(leaf_n, 1)
-        # algorithmic bytes of the dominant kernel: read the codeword once + write layer 0
-        leaf_bytes = 4 * N * W + 32 * (N >> K_WHIR)
-        leaf_perms = N * (W // 8) + (N - (N >> K_WHIR))
-        ach = leaf_bytes / (leaf_avg / 1e3) / 1e9 if leaf_avg else 0.0
-        lde_ms = sum(spans[k][0] for k in ("chunk", "ntt_pass", "ntt_final")) / args.steps
-        lde_bytes = 4 * (1 << LOG_ROWS) * W * (1 + (1 << LOG_BLOWUP))
+        pk_, pk_kind = peaks()
+        fam = {k: (v[0] / max(v[1], 1), v[1] // args.steps, v[0] / args.steps) for k, v in spans.items()}  # avg ms, launches/step, ms/step
+        fbytes = family_bytes()
+        dom = max(fbytes, key=lambda k: fam[k][2])
+        dom_ms = fam[dom][0]
+        ach = fbytes[dom] / (dom_ms / 1e3) / 1e9 if dom_ms else 0.0
+        leaf_perms = (1 << (LOG_ROWS + LOG_BLOWUP)) * (COLS // 8) + ((1 << (LOG_ROWS + LOG_BLOWUP)) - ((1 << (LOG_ROWS + LOG_BLOWUP)) >> K_WHIR))
+        names = {"leaf": "leaf_tree_kernel (fused Poseidon2 row sponge + 2^k_whir strided tree levels)",
+                 "bc_round0": "batch_round0_kernel (constraint DAG evaluation on the cosets of the skip domain)"}
+        lde_ms = sum(fam[k][2] for k in ("chunk", "ntt_pass", "ntt_final"))
+        lde_bytes = 4 * (1 << LOG_ROWS) * COLS * (1 + (1 << LOG_BLOWUP))
         out = {
             "metric": "trace_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "inputs (1 GiB trace, 2 GiB codeword) exceed the 126 MB L2; no flush needed",
-                       "phase": "commit only (LDE + Merkle); full prove not yet in the timed step",
-                       "parallelism": f"{world} independent per-AIR commits, roots all-gathered" if world > 1 else "single GPU"},
+            "config": {"workload": WORKLOAD,
+                       "l2": "per-step working set (1 GiB trace, 2 GiB codeword, 8 GiB GKR tree) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"{world} independent proofs (one per GPU), commitments all-gathered" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": 4 * CELLS, "d2h_bytes_per_step": 32},
+                    "h2d_bytes_per_step": 4 * CELLS, "d2h_bytes_per_step": int(proof.words().size * 4)},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "kernel": "leaf_tree_kernel (fused Poseidon2 row sponge + 2^k_whir strided tree levels)",
-                "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "peak_source": pk_kind, "traffic": None, "ms_per_launch": leaf_avg, "launches": leaf_n,
-                "note": "kernel is INT32-issue bound (Poseidon2), not HBM bound; see int_pipe",
-                "int_pipe": int_pipe_roofline(leaf_perms, leaf_avg, clocks),
+                "kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": pk_["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk_["hbm_gbs"], "peak_source": pk_kind, "traffic": None, "ms_per_launch": dom_ms,
+                "launches_per_step": fam[dom][1],
+                "timing": "CUDA events around every launch of the family, over a repeat of the K timed steps",
+                "note": "both candidate dominant kernels are INT32-multiplier bound, not HBM bound (see int_pipe and DESIGN.md)",
+                "int_pipe": int_pipe_roofline(leaf_perms, fam["leaf"][2], clocks),
             },
-            "phases_ms_per_step": {k: v[0] / args.steps for k, v in spans.items()},
+            "phases_ms_per_step": {k: v[2] for k, v in fam.items()},
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
-                    "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk["hbm_gbs"] if lde_ms else 0.0},
+                    "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk_["hbm_gbs"] if lde_ms else 0.0},
+            "proof_bytes": int(proof.words().size * 4),
         }
         if world == 1 and not args.no_cpu:
             oracle = load_oracle()
-            cpu_commit_sample(oracle, 12)
-            v, dt, sample = cpu_commit_sample(oracle, 16)
-            out["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": sample, "seconds": dt}
+            cpu_prove_sample(oracle, 11)
+            v, dt, sample = cpu_prove_sample(oracle, 12)
+            out["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
+                                   "seconds": dt,
+                                   "note": "C++ restatement of the reference col-major prover; only its commit phase is multi-threaded"}
         print(json.dumps(out))
+    del trace_dev, trace_e2e, roots_dev
+    torch.cuda.synchronize()
     dev.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def int_pipe_roofline(perms, ms, clocks):
+    """Integer-multiplier roofline of the Poseidon2 leaf kernel.  Measured on B200 (tools/int_roofline.cu,
+    profiles/r1_p2_iterate_ncu.txt): 32-bit integer multiplies issue only on the fma-heavy pipe,
+    64 lanes/clk/SM, IMAD 1 pass, IMAD.WIDE / IMAD.HI 2 passes.  A Montgomery product needs
+    IMAD.WIDE + IMAD + IMAD.HI = 5 passes; one permutation has 564 S-box products and 91 IMADs of
+    the internal diagonal => 2911 passes minimum."""
+    passes = 564 * 5 + 91
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 64 * 148 * mhz * 1e6 / passes / 1e9
+    ach = perms / (ms / 1e3) / 1e9 if ms else 0.0
+    return {"kernel": "leaf_tree_kernel", "perms_per_step": perms, "gperm_per_s": ach, "peak_gperm_per_s": peak, "frac": ach / peak,
+            "model": "fma-heavy pipe, 64 lanes/clk/SM x 148 SM x sm_max_mhz / 2911 multiplier passes per permutation"}
 
 
 def main():

@@ -59,7 +59,8 @@ const char* swirl_last_error(void);
 /* Per-kernel-family device timing with CUDA events on the ctx stream (off by default).
  * enable(on) clears the recorded spans; read() synchronises and returns the summed duration and
  * number of launches of a family: 0 leaf hash + query levels, 1 upper tree layers, 2 chunk
- * iDFT+zeta, 3 strided NTT passes, 4 final NTT pass, 5 stacking.
+ * iDFT+zeta, 3 strided NTT passes, 4 final NTT pass, 5 stacking, 6 GKR round kernels, 7 batch-constraint
+ * round 0 (coset evaluation of the constraint DAG), 8 batch-constraint MLE rounds.
  * Reference: gpu_metrics_span_on, cuda-common/src/stream.rs:278-303. */
 int swirl_ctx_timing_enable(swirl_ctx* ctx, int on);
 int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* count);

@@ -210,6 +210,22 @@ class WhirConfig:
         self.k, self.num_queries = int(k), [int(q) for q in num_queries]
         self.mu_pow_bits, self.query_phase_pow_bits, self.folding_pow_bits = mu_pow_bits, query_phase_pow_bits, folding_pow_bits
 
+    @staticmethod
+    def new(log_blowup, log_stacked_height, k, log_final_poly_len, query_phase_pow_bits, folding_pow_bits, mu_pow_bits,
+            security_bits=100):
+        """WhirConfig::new for the unique-decoding regime (config.rs:268-341): queries per round =
+        ceil((security - query_pow) / -log2((1 + 2^-rate) / 2)), rate += k - 1 per round."""
+        import math
+
+        level = max(security_bits - query_phase_pow_bits, 0)
+        rounds = -(-max(log_stacked_height - log_final_poly_len, 0) // k)
+        rate, nq = log_blowup, []
+        for _ in range(rounds):
+            per_query = -math.log2(min(max((1.0 + 2.0 ** (-rate)) / 2.0, 5e-324), 1.0))
+            nq.append(math.ceil(level / per_query))
+            rate += k - 1
+        return WhirConfig(k, nq, mu_pow_bits, query_phase_pow_bits, folding_pow_bits)
+
     def c(self):
         c = _lib.WhirConfigC()
         c.k, c.num_rounds = self.k, len(self.num_queries)
@@ -342,7 +358,8 @@ class B200Device:
     def set_ntt_plan(self, max_log_radix, scratch_bytes=0):
         check(self.lib.swirl_ctx_set_ntt_plan(self.ctx, max_log_radix, scratch_bytes))
 
-    TIMING_SLOTS = {"leaf": 0, "tree": 1, "chunk": 2, "ntt_pass": 3, "ntt_final": 4, "stack": 5}
+    TIMING_SLOTS = {"leaf": 0, "tree": 1, "chunk": 2, "ntt_pass": 3, "ntt_final": 4, "stack": 5, "gkr": 6, "bc_round0": 7,
+                    "bc_mle": 8}
 
     def timing_enable(self, on=True):
         check(self.lib.swirl_ctx_timing_enable(self.ctx, 1 if on else 0))

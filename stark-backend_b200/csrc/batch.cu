@@ -778,7 +778,10 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         to_free.push_back(part);
         ra.partials = part;
 #define BC_R0(NS) batch_round0_kernel<NS><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra)
-        BC_DISPATCH_NS(s.prog.n_slots, BC_R0);
+        {
+            SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
+            BC_DISPATCH_NS(s.prog.n_slots, BC_R0);
+        }
 #undef BC_R0
         SWIRL_LAUNCH_CHECK(ctx);
         bc_reduce_kernel<<<(ra.P * 12 + 255) / 256, 256, 0, ctx->stream>>>(part, blocks, ra.P * 12, d_r0 + r0_off[t]);
@@ -997,7 +1000,10 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 ma.eq_xi = s.d_eq_xi;
                 int grid = (int)std::min<size_t>((ma.ny + 127) / 128, (size_t)ctx->sm_count * 8);
 #define BC_MLE(NS) launch_mle<NS>(D, ma, grid, ctx->stream)
-                BC_DISPATCH_NS(s.prog.n_slots, BC_MLE);
+                {
+                    SwirlTimed timed(ctx, SWIRL_T_BC_MLE);
+                    BC_DISPATCH_NS(s.prog.n_slots, BC_MLE);
+                }
 #undef BC_MLE
                 SWIRL_LAUNCH_CHECK(ctx);
             }

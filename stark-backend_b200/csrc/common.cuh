@@ -47,7 +47,10 @@ enum {
     SWIRL_T_NTT_PASS = 3,  // strided NTT passes
     SWIRL_T_NTT_FINAL = 4, // final NTT pass (natural-order store)
     SWIRL_T_STACK = 5,     // stacking copies
-    SWIRL_T_SLOTS = 6
+    SWIRL_T_GKR = 6,       // GKR round kernels (gkr_round_kernel)
+    SWIRL_T_BC_ROUND0 = 7, // batch constraints: round-0 coset evaluation
+    SWIRL_T_BC_MLE = 8,    // batch constraints: MLE round kernels
+    SWIRL_T_SLOTS = 9
 };
 
 struct SwirlTimed {  // RAII: records an event pair around a launch when ctx->timing is on

@@ -286,6 +286,7 @@ extern "C" int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* t
         size_t h = H;  // height of the table the next kernel reads
         int cur = 0;
         for (int sr = 0; sr < round; sr++) {
+            SwirlTimed timed(ctx, SWIRL_T_GKR);
             if (sr == 0) {
                 a.height = H;
                 gkr_round_kernel<true, false><<<round_grid(ctx, H >> 1), GKR_BLOCK, 0, ctx->stream>>>(a);
