@@ -190,6 +190,7 @@ def run_swirl(args):
     import torch.distributed as dist
 
     import stark_backend_b200 as sb
+    from stark_backend_b200 import multi
     from stark_backend_b200.lib import check
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,7 +209,6 @@ def run_swirl(args):
     stream = dev.torch_stream()
     vk_pre_hash = np.arange(8, dtype=np.uint32)
     pk = [sb.AirProvingKey(True, None)]
-    roots_dev = torch.zeros(8, dtype=torch.int32, device=dev.torch_device)
 
     def barrier():
         if world > 1:
@@ -233,12 +233,7 @@ def run_swirl(args):
         return prove(trace_e2e)
 
     def gather(root):
-        if world > 1:  # only the 32-byte commitments cross NVLink
-            roots_dev.copy_(torch.from_numpy(root.view(np.int32)))
-            out = [torch.empty_like(roots_dev) for _ in range(world)]
-            dist.all_gather(out, roots_dev)
-            return [o.cpu().numpy().view(np.uint32) for o in out]
-        return [root]
+        return multi.all_gather_commitments(root, dev.torch_device)  # only the 32-byte commitments cross NVLink
 
     def timed(fn, steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,11 +246,7 @@ def run_swirl(args):
         roots = gather(proof.common_main_commit)
         barrier()
         t1 = time.time()
-        ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ms], device=dev.torch_device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = multi.max_over_ranks(a.elapsed_time(b), dev.torch_device)
         return ms, roots, t0, t1, proof
 
     for _ in range(max(args.warmup, 3)):
@@ -327,7 +318,7 @@ def run_swirl(args):
                                    "seconds": dt,
                                    "note": "C++ restatement of the reference col-major prover; only its commit phase is multi-threaded"}
         print(json.dumps(out))
-    del trace_dev, trace_e2e, roots_dev
+    del trace_dev, trace_e2e
     torch.cuda.synchronize()
     dev.close()
     if world > 1:
