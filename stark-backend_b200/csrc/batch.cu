@@ -213,23 +213,41 @@ struct EVal {
     static __device__ __forceinline__ Ext weigh(const Ext& w, const T& v) { return ext_mul(w, v); }
 };
 
-template <class V, int NS, class LoadVar>
+// Runs the program on LN independent inputs in lockstep (one decode, LN evaluations per instruction):
+// slot values and accumulators carry a lane index.  load_var(part, col, global_col, out[LN]).
+template <class V, int NS, int LN, class LoadVar>
 __device__ __forceinline__ void run_program(const Instr* __restrict__ code, uint32_t n_instr,
-                                            const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[3]) {
-    typename V::T slots[NS];
+                                            const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[LN][3]) {
+    typename V::T slots[NS][LN];
     for (uint32_t pc = 0; pc < n_instr; pc++) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code) + pc);
         const uint32_t op = raw.x & 0xff, dst = raw.x >> 8;
         switch (op) {
-            case I_VAR: slots[dst] = load_var(raw.y, raw.z, raw.w); break;
-            case I_CONST: slots[dst] = V::from_base(raw.y); break;
-            case I_ADD: slots[dst] = V::add(slots[raw.y], slots[raw.z]); break;
-            case I_SUB: slots[dst] = V::sub(slots[raw.y], slots[raw.z]); break;
-            case I_MUL: slots[dst] = V::mul(slots[raw.y], slots[raw.z]); break;
-            case I_NEG: slots[dst] = V::neg(slots[raw.y]); break;
-            default: {  // I_ACC: acc[y] += weights[z] * slots[w]
+            case I_VAR: load_var(raw.y, raw.z, raw.w, slots[dst]); break;
+            case I_CONST:
+#pragma unroll
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::from_base(raw.y);
+                break;
+            case I_ADD:
+#pragma unroll
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::add(slots[raw.y][l], slots[raw.z][l]);
+                break;
+            case I_SUB:
+#pragma unroll
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::sub(slots[raw.y][l], slots[raw.z][l]);
+                break;
+            case I_MUL:
+#pragma unroll
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::mul(slots[raw.y][l], slots[raw.z][l]);
+                break;
+            case I_NEG:
+#pragma unroll
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::neg(slots[raw.y][l]);
+                break;
+            default: {  // I_ACC: acc[.][y] += weights[z] * slots[w]
                 const Ext wv = ldg_ext(weights + 4 * raw.z);
-                acc[raw.y] = ext_add(acc[raw.y], V::weigh(wv, slots[raw.w]));
+#pragma unroll
+                for (int l = 0; l < LN; l++) acc[l][raw.y] = ext_add(acc[l][raw.y], V::weigh(wv, slots[raw.w][l]));
             }
         }
     }
@@ -268,16 +286,16 @@ template <int NS>
 __global__ void __launch_bounds__(BC_BLOCK) logup_leaves_kernel(LeafArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, sigma = blockIdx.y;
     if (i >= a.height) return;
-    Ext acc[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+    Ext acc[1][3] = {{bb::ext_zero(), bb::ext_zero(), bb::ext_zero()}};
     const uint32_t p0 = a.prog_off[sigma], p1 = a.prog_off[sigma + 1];
-    run_program<FVal, NS>(a.code + p0, p1 - p0, a.weights,
-                          [&](uint32_t part, uint32_t col, uint32_t) {
-                              const BasePart bp = a.parts[part];
-                              return __ldg(bp.ptr + (size_t)col * bp.height + ((i + bp.rot) & (bp.height - 1)));
-                          },
-                          acc);
-    const Ext numer = ext_mul_base(acc[1], a.norm);
-    const Ext denom = ext_add(acc[2], ldg_ext(a.denom_const + 4 * sigma));
+    run_program<FVal, NS, 1>(a.code + p0, p1 - p0, a.weights,
+                             [&](uint32_t part, uint32_t col, uint32_t, uint32_t(&out)[1]) {
+                                 const BasePart bp = a.parts[part];
+                                 out[0] = __ldg(bp.ptr + (size_t)col * bp.height + ((i + bp.rot) & (bp.height - 1)));
+                             },
+                             acc);
+    const Ext numer = ext_mul_base(acc[0][1], a.norm);
+    const Ext denom = ext_add(acc[0][2], ldg_ext(a.denom_const + 4 * sigma));
     for (uint32_t rep = 0; rep < a.reps; rep++) {
         uint32_t* leaf = a.leaves + (a.row_idx[sigma] + (size_t)rep * a.height + i) * 8;
         st_ext(leaf, numer);
@@ -303,31 +321,80 @@ struct R0Args {
     int l_skip, n_lift, P, x_per_block;
     uint32_t* partials;
 };
-template <int NS>
+// sum_i lde[i] * c[i] over one 16-element chunk with lazy reduction (4 products per Montgomery reduction)
+__device__ __forceinline__ uint32_t chunk_dot16(const uint32_t (&l)[16], const uint32_t (&c)[16]) {
+    const uint32_t a0 = bb::dot4(l[0], c[0], l[1], c[1], l[2], c[2], l[3], c[3]);
+    const uint32_t a1 = bb::dot4(l[4], c[4], l[5], c[5], l[6], c[6], l[7], c[7]);
+    const uint32_t a2 = bb::dot4(l[8], c[8], l[9], c[9], l[10], c[10], l[11], c[11]);
+    const uint32_t a3 = bb::dot4(l[12], c[12], l[13], c[13], l[14], c[14], l[15], c[15]);
+    return bb::add(bb::add(a0, a1), bb::add(a2, a3));
+}
+
+// LOGN = 4: the thread's 16 Lagrange coefficients live in registers and chunks are fetched as four
+// 16-byte loads; LOGN = 0: generic l_skip.  Two hypercube points per thread run in lockstep.
+template <int NS, int LOGN>
 __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
     extern __shared__ uint32_t sm[];  // [blockDim][13]
+    constexpr int LN = 2;
     const int P = a.P, N = 1 << a.l_skip;
     const int p = threadIdx.x % P, g = threadIdx.x / P, G = blockDim.x / P;
     const size_t nx = size_t(1) << a.n_lift;
     const size_t x0 = (size_t)blockIdx.x * a.x_per_block, x1 = min(x0 + (size_t)a.x_per_block, nx);
     const uint32_t* lde = a.lde + (size_t)p * N;
-    Ext tot[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
-    for (size_t x = x0 + g; x < x1; x += G) {
-        Ext acc[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
-        run_program<FVal, NS>(a.code, a.n_instr, a.weights,
-                              [&](uint32_t part, uint32_t col, uint32_t) {
-                                  const BasePart bp = a.parts[part];
-                                  const uint32_t* c = bp.ptr + (size_t)col * bp.height;
-                                  const size_t r0 = (x << a.l_skip) + bp.rot;
-                                  uint32_t v = 0;
-                                  for (int i = 0; i < N; i++)
-                                      v = bb::add(v, bb::mul(__ldg(lde + i), __ldg(c + ((r0 + i) & (bp.height - 1)))));
-                                  return v;
-                              },
-                              acc);
-        const Ext e = ldg_ext(a.eq_xi + 4 * x);
+    uint32_t lreg[16];
+    if (LOGN == 4) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) tot[k] = ext_add(tot[k], ext_mul(e, acc[k]));
+        for (int i = 0; i < 16; i++) lreg[i] = __ldg(lde + i);
+    }
+    Ext tot[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+    for (size_t xb = x0 + g; xb < x1; xb += (size_t)LN * G) {
+        size_t xs[LN];
+        bool live[LN];
+#pragma unroll
+        for (int l = 0; l < LN; l++) {
+            live[l] = xb + (size_t)l * G < x1;
+            xs[l] = live[l] ? xb + (size_t)l * G : xb;
+        }
+        Ext acc[LN][3];
+#pragma unroll
+        for (int l = 0; l < LN; l++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[l][k] = bb::ext_zero();
+        run_program<FVal, NS, LN>(a.code, a.n_instr, a.weights,
+                                  [&](uint32_t part, uint32_t col, uint32_t, uint32_t(&out)[LN]) {
+                                      const BasePart bp = a.parts[part];
+                                      const uint32_t* c = bp.ptr + (size_t)col * bp.height;
+#pragma unroll
+                                      for (int l = 0; l < LN; l++) {
+                                          const size_t r0 = xs[l] << a.l_skip;
+                                          if (LOGN == 4 && bp.height >= 16) {
+                                              const uint4* q = reinterpret_cast<const uint4*>(c + r0);
+                                              const uint4 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3);
+                                              uint32_t ch[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w,
+                                                                 v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+                                              if (bp.rot) {  // rows r0+1 .. r0+16 (cyclic)
+                                                  const uint32_t nxt = __ldg(c + ((r0 + 16) & (bp.height - 1)));
+#pragma unroll
+                                                  for (int i = 0; i < 15; i++) ch[i] = ch[i + 1];
+                                                  ch[15] = nxt;
+                                              }
+                                              out[l] = chunk_dot16(lreg, ch);
+                                          } else {
+                                              uint32_t v = 0;
+                                              for (int i = 0; i < N; i++)
+                                                  v = bb::add(v, bb::mul(__ldg(lde + i), __ldg(c + ((r0 + bp.rot + i) & (bp.height - 1)))));
+                                              out[l] = v;
+                                          }
+                                      }
+                                  },
+                                  acc);
+#pragma unroll
+        for (int l = 0; l < LN; l++) {
+            if (!live[l]) continue;
+            const Ext e = ldg_ext(a.eq_xi + 4 * xs[l]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) tot[k] = ext_add(tot[k], ext_mul(e, acc[l][k]));
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; k++)
@@ -372,25 +439,34 @@ __global__ void __launch_bounds__(128) batch_mle_kernel(MleArgs a) {
     for (int i = 0; i < D * 12; i++) v[i] = 0;
     for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)gridDim.x * blockDim.x) {
         const Ext e = a.single ? bb::ext_one() : ldg_ext(a.eq_xi + 4 * y);
+        Ext acc[D][3];
 #pragma unroll
-        for (int X = 1; X <= D; X++) {
-            Ext acc[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
-            const uint32_t xm = bb::mont((uint64_t)X);
-            run_program<EVal, NS>(a.code, a.n_instr, a.weights,
-                                  [&](uint32_t, uint32_t, uint32_t gcol) {
-                                      const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
-                                      if (a.single) return ldg_ext(c);
-                                      const Ext t0 = ldg_ext(c + 8 * y), t1 = ldg_ext(c + 8 * y + 4);
-                                      return X == 1 ? t1 : ext_add(t0, ext_mul_base(ext_sub(t1, t0), xm));
-                                  },
-                                  acc);
+        for (int X = 0; X < D; X++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) acc[X][k] = bb::ext_zero();
+        // all X = 1..D in lockstep: one pair of loads per variable, values t1, t1 + d, t1 + 2d, ...
+        run_program<EVal, NS, D>(a.code, a.n_instr, a.weights,
+                                 [&](uint32_t, uint32_t, uint32_t gcol, Ext(&out)[D]) {
+                                     const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
+                                     if (a.single) {
+                                         out[0] = ldg_ext(c);
+                                         return;
+                                     }
+                                     const Ext t0 = ldg_ext(c + 8 * y), t1 = ldg_ext(c + 8 * y + 4);
+                                     const Ext d = ext_sub(t1, t0);
+                                     out[0] = t1;
+#pragma unroll
+                                     for (int X = 1; X < D; X++) out[X] = ext_add(out[X - 1], d);
+                                 },
+                                 acc);
+#pragma unroll
+        for (int X = 0; X < D; X++)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const Ext t = ext_mul(e, acc[k]);
+                const Ext t = ext_mul(e, acc[X][k]);
 #pragma unroll
-                for (int c = 0; c < 4; c++) v[(X - 1) * 12 + 4 * k + c] = bb::add(v[(X - 1) * 12 + 4 * k + c], t.c[c]);
+                for (int c = 0; c < 4; c++) v[X * 12 + 4 * k + c] = bb::add(v[X * 12 + 4 * k + c], t.c[c]);
             }
-        }
     }
     grid_sum<D * 12>(v, a.partials, a.ticket, a.result);
 }
@@ -771,13 +847,19 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         const int G = std::max(1, BC_BLOCK / ra.P);
         const int threads = ra.P * G;
         const size_t nx = size_t(1) << s.n_lift;
-        ra.x_per_block = G * 8;
+        ra.x_per_block = G * 16;
         const size_t blocks = (nx + ra.x_per_block - 1) / ra.x_per_block;
         uint32_t* part = nullptr;
         SWIRL_CUDA(dev_alloc(ctx, &part, blocks * (size_t)ra.P * 12));
         to_free.push_back(part);
         ra.partials = part;
-#define BC_R0(NS) batch_round0_kernel<NS><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra)
+#define BC_R0(NS)                                                                                                  \
+    do {                                                                                                           \
+        if (l_skip == 4)                                                                                           \
+            batch_round0_kernel<NS, 4><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra);  \
+        else                                                                                                       \
+            batch_round0_kernel<NS, 0><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra);  \
+    } while (0)
         {
             SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
             BC_DISPATCH_NS(s.prog.n_slots, BC_R0);
