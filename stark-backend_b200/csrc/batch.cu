@@ -215,10 +215,22 @@ struct EVal {
 
 // Runs the program on LN independent inputs in lockstep (one decode, LN evaluations per instruction):
 // slot values and accumulators carry a lane index.  load_var(part, col, global_col, out[LN]).
-template <class V, int NS, int LN, class LoadVar>
-__device__ __forceinline__ void run_program(const Instr* __restrict__ code, uint32_t n_instr,
-                                            const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[LN][3]) {
-    typename V::T slots[NS][LN];
+// Slot storage in shared memory, one column per thread: slot s lane l of thread t at [(s * LN + l) * blockDim + t]
+template <class T, int LN>
+struct SharedSlots {
+    T* base;  // + threadIdx.x
+    int stride;
+    struct Row {
+        T* p;
+        int stride;
+        __device__ __forceinline__ T& operator[](int l) const { return p[l * stride]; }
+    };
+    __device__ __forceinline__ Row operator[](uint32_t s) const { return Row{base + (size_t)s * LN * stride, stride}; }
+};
+
+template <class V, int LN, class Slots, class LoadVar>
+__device__ __forceinline__ void run_program_on(Slots&& slots, const Instr* __restrict__ code, uint32_t n_instr,
+                                               const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[LN][3]) {
     for (uint32_t pc = 0; pc < n_instr; pc++) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code) + pc);
         const uint32_t op = raw.x & 0xff, dst = raw.x >> 8;
@@ -251,6 +263,13 @@ __device__ __forceinline__ void run_program(const Instr* __restrict__ code, uint
             }
         }
     }
+}
+
+template <class V, int NS, int LN, class LoadVar>
+__device__ __forceinline__ void run_program(const Instr* __restrict__ code, uint32_t n_instr,
+                                            const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[LN][3]) {
+    typename V::T slots[NS][LN];
+    run_program_on<V, LN>(slots, code, n_instr, weights, load_var, acc);
 }
 
 struct BasePart {
@@ -289,7 +308,7 @@ __global__ void __launch_bounds__(BC_BLOCK) logup_leaves_kernel(LeafArgs a) {
     Ext acc[1][3] = {{bb::ext_zero(), bb::ext_zero(), bb::ext_zero()}};
     const uint32_t p0 = a.prog_off[sigma], p1 = a.prog_off[sigma + 1];
     run_program<FVal, NS, 1>(a.code + p0, p1 - p0, a.weights,
-                             [&](uint32_t part, uint32_t col, uint32_t, uint32_t(&out)[1]) {
+                             [&](uint32_t part, uint32_t col, uint32_t, auto&& out) {
                                  const BasePart bp = a.parts[part];
                                  out[0] = __ldg(bp.ptr + (size_t)col * bp.height + ((i + bp.rot) & (bp.height - 1)));
                              },
@@ -334,7 +353,7 @@ __device__ __forceinline__ uint32_t chunk_dot16(const uint32_t (&l)[16], const u
 // 16-byte loads; LOGN = 0: generic l_skip.  Two hypercube points per thread run in lockstep.
 template <int NS, int LOGN>
 __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
-    extern __shared__ uint32_t sm[];  // [blockDim][13]
+    extern __shared__ uint32_t sm[];  // [blockDim][13] reduction scratch, then [NS][LN][blockDim] value slots
     constexpr int LN = 2;
     const int P = a.P, N = 1 << a.l_skip;
     const int p = threadIdx.x % P, g = threadIdx.x / P, G = blockDim.x / P;
@@ -360,8 +379,7 @@ __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
         for (int l = 0; l < LN; l++)
 #pragma unroll
             for (int k = 0; k < 3; k++) acc[l][k] = bb::ext_zero();
-        run_program<FVal, NS, LN>(a.code, a.n_instr, a.weights,
-                                  [&](uint32_t part, uint32_t col, uint32_t, uint32_t(&out)[LN]) {
+        auto load_var = [&](uint32_t part, uint32_t col, uint32_t, auto&& out) {
                                       const BasePart bp = a.parts[part];
                                       const uint32_t* c = bp.ptr + (size_t)col * bp.height;
 #pragma unroll
@@ -386,8 +404,13 @@ __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
                                               out[l] = v;
                                           }
                                       }
-                                  },
-                                  acc);
+                                  };
+        if (NS <= 64) {  // value slots in shared memory (short-scoreboard latency instead of local-memory round trips)
+            run_program_on<FVal, LN>(SharedSlots<uint32_t, LN>{sm + blockDim.x * 13 + threadIdx.x, (int)blockDim.x}, a.code,
+                                     a.n_instr, a.weights, load_var, acc);
+        } else {
+            run_program<FVal, NS, LN>(a.code, a.n_instr, a.weights, load_var, acc);
+        }
 #pragma unroll
         for (int l = 0; l < LN; l++) {
             if (!live[l]) continue;
@@ -433,7 +456,7 @@ struct MleArgs {
     uint32_t* result;
 };
 template <int NS, int D>
-__global__ void __launch_bounds__(128) batch_mle_kernel(MleArgs a) {
+__global__ void __launch_bounds__(128, 4) batch_mle_kernel(MleArgs a) {
     uint32_t v[D * 12];
 #pragma unroll
     for (int i = 0; i < D * 12; i++) v[i] = 0;
@@ -446,7 +469,7 @@ __global__ void __launch_bounds__(128) batch_mle_kernel(MleArgs a) {
             for (int k = 0; k < 3; k++) acc[X][k] = bb::ext_zero();
         // all X = 1..D in lockstep: one pair of loads per variable, values t1, t1 + d, t1 + 2d, ...
         run_program<EVal, NS, D>(a.code, a.n_instr, a.weights,
-                                 [&](uint32_t, uint32_t, uint32_t gcol, Ext(&out)[D]) {
+                                 [&](uint32_t, uint32_t, uint32_t gcol, auto&& out) {
                                      const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
                                      if (a.single) {
                                          out[0] = ldg_ext(c);
@@ -847,18 +870,22 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         const int G = std::max(1, BC_BLOCK / ra.P);
         const int threads = ra.P * G;
         const size_t nx = size_t(1) << s.n_lift;
-        ra.x_per_block = G * 16;
+        ra.x_per_block = G * 4;
         const size_t blocks = (nx + ra.x_per_block - 1) / ra.x_per_block;
         uint32_t* part = nullptr;
         SWIRL_CUDA(dev_alloc(ctx, &part, blocks * (size_t)ra.P * 12));
         to_free.push_back(part);
         ra.partials = part;
-#define BC_R0(NS)                                                                                                  \
-    do {                                                                                                           \
-        if (l_skip == 4)                                                                                           \
-            batch_round0_kernel<NS, 4><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra);  \
-        else                                                                                                       \
-            batch_round0_kernel<NS, 0><<<(unsigned)blocks, threads, (size_t)threads * 13 * 4, ctx->stream>>>(ra);  \
+#define BC_R0(NS)                                                                                            \
+    do {                                                                                                     \
+        const size_t smem = (size_t)threads * (13 + ((NS) <= 64 ? (NS) * 2 : 0)) * 4;                        \
+        if (l_skip == 4) {                                                                                   \
+            cudaFuncSetAttribute(batch_round0_kernel<NS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            batch_round0_kernel<NS, 4><<<(unsigned)blocks, threads, smem, ctx->stream>>>(ra);               \
+        } else {                                                                                             \
+            cudaFuncSetAttribute(batch_round0_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            batch_round0_kernel<NS, 0><<<(unsigned)blocks, threads, smem, ctx->stream>>>(ra);               \
+        }                                                                                                    \
     } while (0)
         {
             SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
