@@ -191,7 +191,6 @@ def run_swirl(args):
 
     import stark_backend_b200 as sb
     from stark_backend_b200 import multi
-    from stark_backend_b200.lib import check
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,34 +224,70 @@ def run_swirl(args):
     def step_device():
         return prove(trace_dev)
 
-    trace_e2e = torch.empty_like(trace_dev)
+    air_h = sb.AirProvingContext(air.nodes, air.constraint_idx, air.interactions, 2, False, None)
 
     def step_host():
-        # H2D of the whole trace from pinned host memory on the library's stream, then the proof
-        check(dev.lib.swirl_memcpy_h2d(dev.ctx, trace_e2e.data_ptr(), host.data_ptr(), 4 * CELLS))
-        return prove(trace_e2e)
+        # the trace starts in pinned host memory: transport (H2D, pipelined by column groups with the RS
+        # encoding and leaf hashing inside swirl_commit_host) + the rest of the proof
+        proof = sb.Coordinator(dev, params).prove_host(vk_pre_hash, pk, air_h, host, 1 << LOG_ROWS, COLS)
+        proof.common_main_pcs.free()
+        return proof
 
     def gather(root):
         return multi.all_gather_commitments(root, dev.torch_device)  # only the 32-byte commitments cross NVLink
 
-    def timed(fn, steps):
+    stalls = {}
+
+    def timed_once(fn, steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.time()
         a.record(stream)
+        walls = []
         for _ in range(steps):
+            ts_ = time.perf_counter()
             proof = fn()
+            walls.append(1e3 * (time.perf_counter() - ts_))
+            if os.environ.get("BENCH_DEBUG"):
+                print(f"step {fn.__name__} {walls[-1]:.1f} ms", file=sys.stderr)
         b.record(stream)
         roots = gather(proof.common_main_commit)
         barrier()
         t1 = time.time()
         ms = multi.max_over_ranks(a.elapsed_time(b), dev.torch_device)
-        return ms, roots, t0, t1, proof
+        return ms, roots, t0, t1, proof, walls
+
+    def timed(fn, steps):
+        """K steps; every step performs identical work (same trace, deterministic transcript), so a step
+        that takes > 2.5x the median is a host/box stall (seen sporadically on shared boxes: 0.2-1.2 s):
+        like a throttled run it is re-measured once, and both measurements are reported."""
+        r = timed_once(fn, steps)
+        med = sorted(r[5])[len(r[5]) // 2]
+        worst = multi.max_over_ranks(max(r[5]) / med, dev.torch_device)
+        if worst > 2.5:
+            stalls[fn.__name__] = {"first_ms_per_step": r[0] / steps, "first_step_ms": [round(x, 1) for x in r[5]]}
+            r = timed_once(fn, steps)
+        stalls.setdefault("step_ms", {})[fn.__name__] = [round(x, 1) for x in r[5]]
+        return r[:5]
 
     # the sampler starts before the warm-up: the first nvidia-smi start-up on a fresh box contends for the
     # driver lock for about a second, which would otherwise land in the timed region of this sync-heavy step
     sampler = ClockSampler(local)
     sampler.start()
+    if os.environ.get("BENCH_DEBUG"):
+        def wrap(name):
+            f = getattr(dev, name)
+            def g(*a, **k):
+                t_ = time.perf_counter()
+                r_ = f(*a, **k)
+                dev.synchronize()
+                d_ = 1e3 * (time.perf_counter() - t_)
+                if d_ > 60:
+                    print(f"   slow {name}: {d_:.1f} ms", file=sys.stderr)
+                return r_
+            setattr(dev, name, g)
+        for nm in ("commit", "commit_host", "prove_batch_constraints", "prove_openings"):
+            wrap(nm)
     for _ in range(max(args.warmup, 3)):
         step_device()
     l0 = dev.launch_count()
@@ -311,6 +346,8 @@ def run_swirl(args):
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
                     "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk_["hbm_gbs"] if lde_ms else 0.0},
             "proof_bytes": int(proof.words().size * 4),
+            "host_step_ms": stalls.pop("step_ms"),
+            "remeasured_after_host_stall": stalls or None,
         }
         if world == 1 and not args.no_cpu:
             oracle = load_oracle()
@@ -320,7 +357,7 @@ def run_swirl(args):
                                    "seconds": dt,
                                    "note": "C++ restatement of the reference col-major prover; only its commit phase is multi-threaded"}
         print(json.dumps(out))
-    del trace_dev, trace_e2e
+    del trace_dev
     torch.cuda.synchronize()
     dev.close()
     if world > 1:

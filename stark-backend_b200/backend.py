@@ -203,6 +203,23 @@ class StackedPcsData:
             pass
 
 
+class PcsTraceView:
+    """A trace that lives inside a StackedPcsData produced by commit_host (the device copy made by the
+    transport): same accessors as DeviceMatrix, kept alive by the PCS handle."""
+
+    def __init__(self, pcs, ptr, height, width):
+        self._pcs, self._ptr, self._h, self._w = pcs, int(ptr), int(height), int(width)
+
+    def height(self):
+        return self._h
+
+    def width(self):
+        return self._w
+
+    def ptr(self):
+        return self._ptr
+
+
 class WhirConfig:
     """reference: WhirConfig / WhirRoundConfig (config.rs:172-197)."""
 

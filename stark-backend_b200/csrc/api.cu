@@ -85,6 +85,7 @@ int swirl_ctx_destroy(swirl_ctx* ctx) {
     for (uint32_t* t : ctx->tw_lo_scaled)
         if (t) cudaFree(t);
     round_scratch_free(ctx);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -716,8 +716,13 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         uint32_t* leaves = nullptr;
         SWIRL_CUDA(dev_alloc(ctx, &leaves, n_leaves * 8));
         to_free.push_back(leaves);
-        leaves_fill_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, ctx->stream>>>(leaves, n_leaves, alpha);
-        SWIRL_LAUNCH_CHECK(ctx);
+        // only the padding behind the last interaction block needs the (0, alpha) fill
+        size_t used = 0;
+        for (const LayoutCol& lc : ilayout.cols) used = std::max<size_t>(used, lc.row_idx + (size_t(1) << lc.log_height));
+        if (used < n_leaves) {
+            leaves_fill_kernel<<<(unsigned)((n_leaves - used + 255) / 256), 256, 0, ctx->stream>>>(leaves + used * 8, n_leaves - used, alpha);
+            SWIRL_LAUNCH_CHECK(ctx);
+        }
         std::vector<uint32_t> lw((max_len + 2) * 4);
         memcpy(&lw[0], bb::ext_one().c, 16);
         for (size_t j = 0; j <= max_len; j++) memcpy(&lw[4 * (j + 1)], beta_pows[j].c, 16);

@@ -11,6 +11,7 @@
 // stacking never leaves a gap, so the flat column-major stacked matrix is just the concatenation
 // of the flat trace buffers (traces shorter than 2^l_skip are first expanded by striding).  A
 // single trace that exactly fills its stacked columns is therefore used in place, with no copy.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -162,11 +163,81 @@ int swirl_commit(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_mat
     return 0;
 }
 
+// Pipelined transport + commit of a single host trace that is its own stacked matrix: the H2D copy
+// of column group g+1 (copy stream) overlaps the RS encoding and sponge absorption of group g
+// (compute stream); per-row sponge states wait in HBM between groups.  Returns 1 when the shape
+// does not qualify (caller falls back), 0 on success.
+static int commit_host_pipelined(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* t, uint32_t h_root[8],
+                                 swirl_pcs* pcs) {
+    const int l_skip = params->l_skip, n_stack = params->n_stack;
+    if (!is_pow2(t->height) || t->height != (uint64_t(1) << (l_skip + n_stack))) return 1;
+    const uint64_t H = t->height, W = t->width, N = H << params->log_blowup;
+    constexpr uint64_t GROUP = 32;
+    if (W <= GROUP || H * W * 4 < (uint64_t(32) << 20) || (uint64_t(1) << params->k_whir) > 256 || N < (uint64_t(1) << params->k_whir))
+        return 1;
+    SWIRL_REQUIRE(params->log_blowup >= 0 && params->k_whir >= 0 && l_skip + n_stack <= 27, "parameters");
+    uint64_t widths[1] = {W};
+    int32_t lhs[1] = {ilog2(H)};
+    pcs->params = *params;
+    SWIRL_TRY(make_layout(l_skip, l_skip + n_stack, 1, widths, lhs, &pcs->layout));
+    if (!ctx->copy_stream) SWIRL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    uint32_t *d_trace = nullptr, *state = nullptr;
+    SWIRL_CUDA(dev_alloc(ctx, &d_trace, H * W));
+    pcs->owned_traces.push_back(d_trace);
+    pcs->stacked = d_trace;
+    pcs->owns_stacked = false;
+    pcs->codeword_height = N;
+    pcs->query_stride = N >> params->k_whir;
+    SWIRL_CUDA(dev_alloc(ctx, &pcs->codeword, N * W));
+    SWIRL_CUDA(dev_alloc(ctx, &pcs->layers, (2 * pcs->query_stride - 1) * 8 + 8));
+    SWIRL_CUDA(dev_alloc(ctx, &state, N * 16));
+    // the copy stream must not run ahead of the allocation (stream-ordered pool) on the compute stream
+    cudaEvent_t ready;
+    SWIRL_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    SWIRL_CUDA(cudaEventRecord(ready, ctx->stream));
+    SWIRL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+    const uint64_t ngroups = (W + GROUP - 1) / GROUP;
+    std::vector<cudaEvent_t> ev(ngroups);
+    int rc = 0;
+    for (uint64_t g = 0; g < ngroups && rc == 0; g++) {
+        const uint64_t c0 = g * GROUP, nc = std::min(GROUP, W - c0);
+        SWIRL_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+        SWIRL_CUDA(cudaMemcpyAsync(d_trace + c0 * H, t->data + c0 * H, nc * H * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        SWIRL_CUDA(cudaEventRecord(ev[g], ctx->copy_stream));
+        SWIRL_CUDA(cudaStreamWaitEvent(ctx->stream, ev[g], 0));
+        rc = rs_encode(ctx, d_trace + c0 * H, H, H, nc, l_skip, params->log_blowup, pcs->codeword + c0 * N);
+        if (rc == 0)
+            rc = merkle_commit_columns(ctx, pcs->codeword + c0 * N, N, nc, params->k_whir, pcs->layers, state, g == 0,
+                                       g == ngroups - 1);
+    }
+    if (rc == 0) {
+        SWIRL_CUDA(cudaMemcpyAsync(h_root, pcs->layers + (2 * pcs->query_stride - 2) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    dev_free(ctx, state);
+    cudaEventDestroy(ready);
+    for (auto e : ev)
+        if (e) cudaEventDestroy(e);
+    return rc;
+}
+
 int swirl_commit_host(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* h_traces, size_t n_traces,
                       uint32_t h_root[8], swirl_pcs** out) {
     SWIRL_REQUIRE(ctx && params && h_traces && h_root && out, "null argument");
     SWIRL_CUDA(cudaSetDevice(ctx->device));
     swirl_pcs* pcs = new swirl_pcs();
+    if (n_traces == 1 && h_traces[0].width) {
+        const int prc = commit_host_pipelined(ctx, params, &h_traces[0], h_root, pcs);
+        if (prc == 0) {
+            *out = pcs;
+            return 0;
+        }
+        if (prc != 1) {
+            pcs_release(ctx, pcs);
+            *out = nullptr;
+            return prc;
+        }
+    }
     std::vector<swirl_matrix> dev(n_traces);
     int rc = 0;
     for (size_t i = 0; i < n_traces && rc == 0; i++) {

@@ -19,6 +19,7 @@ struct swirl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D transport overlapping the compute stream (swirl_commit_host)
     int sm_count = 148;
     // twiddle tables: W = two_adic_generator(27) in Montgomery form
     //   tw_lo[i] = W^i            (i < 2^14)

@@ -11,6 +11,8 @@ namespace swirl {
 // (query_stride = num_leaves >> log_rpq digests) first, the root last; 2*query_stride-1 digests.
 int merkle_commit(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, int log_rpq,
                   uint32_t* d_layers);
+int merkle_commit_columns(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, int log_rpq,
+                          uint32_t* d_layers, uint32_t* d_state, bool first, bool last);
 int poseidon2_permute_batch(swirl_ctx* ctx, uint32_t* d_states, size_t n);
 int poseidon2_compress_batch(swirl_ctx* ctx, const uint32_t* d_pairs, uint32_t* d_out, size_t n);
 int merkle_query_proofs(swirl_ctx* ctx, const uint32_t* d_layers, size_t query_stride,

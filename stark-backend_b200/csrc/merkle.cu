@@ -34,10 +34,17 @@ __device__ __forceinline__ void load_digest(uint32_t* s, const uint32_t* src) {
 }
 
 // Sponge over one row of a column-major matrix; leaves the digest in s[0..8).
+__device__ __forceinline__ void hash_row_into(uint32_t s[16], const uint32_t* __restrict__ matrix, size_t height,
+                                              uint32_t width, size_t row);
 __device__ __forceinline__ void hash_row(uint32_t s[16], const uint32_t* __restrict__ matrix, size_t height,
                                          uint32_t width, size_t row) {
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = 0;
+    hash_row_into(s, matrix, height, width, row);
+}
+// Continues the sponge of one row over `width` more columns (the state so far is in s).
+__device__ __forceinline__ void hash_row_into(uint32_t s[16], const uint32_t* __restrict__ matrix, size_t height,
+                                              uint32_t width, size_t row) {
     const bool live = row < height;  // rows past the matrix hash as zeros
     const uint32_t* p = matrix + (live ? row : 0);
     const uint32_t nfull = width >> 3, tail = width & 7;
@@ -68,15 +75,28 @@ __device__ __forceinline__ void hash_row(uint32_t s[16], const uint32_t* __restr
 // blockDim.x = yb << log_rpq (<= MK_BLOCK); grid.x = S / yb.
 __global__ void __launch_bounds__(MK_BLOCK)
 leaf_tree_kernel(const uint32_t* __restrict__ matrix, size_t height, uint32_t width, size_t S, int log_rpq,
-                 int log_yb, uint32_t* __restrict__ layer0) {
+                 int log_yb, uint32_t* __restrict__ layer0, const uint32_t* __restrict__ state_in,
+                 uint32_t* __restrict__ state_out) {
     __shared__ uint32_t sm[8][MK_BLOCK];
     const int tid = threadIdx.x;
     const int yb = 1 << log_yb;
     const int yl = tid & (yb - 1);
     const int t = tid >> log_yb;
     const size_t y = (size_t)blockIdx.x * yb + yl;
+    const size_t row = (size_t)t * S + y, n_rows = S << log_rpq;
     uint32_t s[16];
-    hash_row(s, matrix, height, width, (size_t)t * S + y);
+    if (state_in) {  // sponge states of a previous column group, word-major [16][n_rows]
+#pragma unroll
+        for (int i = 0; i < 16; i++) s[i] = state_in[(size_t)i * n_rows + row];
+        hash_row_into(s, matrix, height, width, row);
+    } else {
+        hash_row(s, matrix, height, width, row);
+    }
+    if (state_out) {  // more columns follow: park the sponge state
+#pragma unroll
+        for (int i = 0; i < 16; i++) state_out[(size_t)i * n_rows + row] = s[i];
+        return;
+    }
 
     int active = blockDim.x;
     for (int lvl = 0; lvl < log_rpq; lvl++) {
@@ -240,6 +260,14 @@ static int compress_upper_layers(swirl_ctx* ctx, uint32_t* d_layers, size_t S) {
 
 int merkle_commit(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, int log_rpq,
                   uint32_t* d_layers) {
+    return merkle_commit_columns(ctx, d_matrix, height, width, log_rpq, d_layers, nullptr, true, true);
+}
+
+// Streaming form: absorbs `width` more columns (a multiple of 8 unless `last`) into the per-row
+// sponge states `d_state` ([16][num_leaves] words; ignored when first && last) and, on the last
+// group, finishes the tree.
+int merkle_commit_columns(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, int log_rpq,
+                          uint32_t* d_layers, uint32_t* d_state, bool first, bool last) {
     SWIRL_REQUIRE(height > 0, "MerkleTreeEmptyMatrix");
     SWIRL_REQUIRE(log_rpq >= 0 && log_rpq < 32, "rows_per_query");
     SWIRL_REQUIRE(width < (size_t(1) << 31), "width");
@@ -248,6 +276,8 @@ int merkle_commit(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_
     while (num_leaves < height) num_leaves <<= 1;
     SWIRL_REQUIRE((size_t(1) << log_rpq) <= num_leaves, "MerkleTreeRowsPerQueryExceeded");
     const size_t S = num_leaves >> log_rpq;
+    SWIRL_REQUIRE((first && last) || (d_state && (1 << log_rpq) <= MK_BLOCK), "streaming commit needs a state buffer");
+    SWIRL_REQUIRE(last || (width & 7) == 0, "column groups must be multiples of the sponge rate");
     if ((1 << log_rpq) <= MK_BLOCK) {
         int log_yb = ilog2(MK_BLOCK) - log_rpq;
         if ((size_t(1) << log_yb) > S) log_yb = ilog2(S);
@@ -256,9 +286,11 @@ int merkle_commit(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_
         {
             SwirlTimed timed(ctx, SWIRL_T_LEAF);
             leaf_tree_kernel<<<(unsigned)grid, 1 << (log_yb + log_rpq), 0, ctx->stream>>>(
-                d_matrix, height, (uint32_t)width, S, log_rpq, log_yb, d_layers);
+                d_matrix, height, (uint32_t)width, S, log_rpq, log_yb, d_layers, first ? nullptr : d_state,
+                last ? nullptr : d_state);
         }
         SWIRL_LAUNCH_CHECK(ctx);
+        if (!last) return 0;
     } else {
         // rows_per_query larger than a CTA: plain row hashes, then one launch per strided level
         uint32_t *a = nullptr, *b = nullptr;

@@ -59,7 +59,9 @@ extern "C" int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], in
     const uint32_t mask = (1u << bits) - 1;
     uint32_t* d_res = nullptr;
     SWIRL_CUDA(dev_alloc(ctx, &d_res, 1));
-    uint64_t window = uint64_t(4) << bits;
+    // ascending windows of 2^bits candidates: each holds a witness with probability 1 - 1/e, so the
+    // expected work is ~1.6 * 2^bits permutations (the smallest witness is in the first non-empty window)
+    uint64_t window = uint64_t(1) << bits;
     if (window < (1u << 16)) window = 1u << 16;
     if (window > (1u << 24)) window = 1u << 24;
     int rc = 0;

@@ -55,14 +55,30 @@ class Coordinator:
         self.device, self.params = device, params
         self.transcript = transcript if transcript is not None else Transcript()
 
-    def prove(self, vk_pre_hash, per_air_pk, per_trace):
+    def prove_host(self, vk_pre_hash, per_air_pk, air, host_trace, height, width):
+        """Single-AIR proof with the common main trace in HOST memory: the H2D transport runs inside
+        swirl_commit_host, pipelined with the RS encoding and leaf hashing by column groups; the later
+        phases read the device copy the commitment keeps (DeviceDataTransporter + Coordinator::prove)."""
+        from .backend import AirProvingContext, PcsTraceView
+
+        dev, P = self.device, self.params
+        root, common = dev.commit_host(P.pcs(), [(host_trace, height, width)])
+        view = PcsTraceView(common, dev.lib.swirl_pcs_stacked_matrix(common._h), height, width)
+        ctx = AirProvingContext(air.nodes, air.constraint_idx, air.interactions, air.constraint_degree, air.need_rot, view,
+                                air.public_values)
+        return self.prove(vk_pre_hash, per_air_pk, [(0, ctx, [])], precommitted=(root, common))
+
+    def prove(self, vk_pre_hash, per_air_pk, per_trace, precommitted=None):
         """per_air_pk: list of AirProvingKey indexed by air id.  per_trace: list of
         (air_id, AirProvingContext, [CommittedTraceData cached mains]) — sorted here as
         ProvingContext::into_sorted does (height descending, then air id; prover/types.rs:144-148)."""
         dev, ts, P = self.device, self.transcript, self.params
         ts.observe(vk_pre_hash)
         per_trace = sorted(per_trace, key=lambda t: (-t[1].common_main.height(), t[0]))
-        root, common = dev.commit(P.pcs(), [t[1].common_main for t in per_trace])
+        if precommitted is None:
+            root, common = dev.commit(P.pcs(), [t[1].common_main for t in per_trace])
+        else:
+            root, common = precommitted
         ts.observe(root)
         present = {t[0]: t for t in per_trace}
         for air_id, pk in enumerate(per_air_pk):

@@ -336,3 +336,19 @@ def test_sponge_grind_matches_oracle(dev, oracle, bits, absorbed):
         w2 = dev.sponge_grind(st, bits, min_w=w + 1)
         assert w2 > w and oracle.sponge_check_witness(st.copy(), bits, int(oracle.to_mont([w2])[0]))
         assert dev.sponge_grind(st, bits, min_w=w + 1, max_w=w2) is None
+
+
+def test_commit_host_pipelined_matches_device_commit(dev, oracle):
+    # wide enough (>= 32 MiB, > 32 columns) to take the pipelined transport path of swirl_commit_host
+    rng = np.random.default_rng(77)
+    h, w = 1 << 17, 72
+    vals = oracle.random_field(rng, h * w)
+    params = sb.PcsParams(4, 13, 1, 4)
+    root_d, pcs_d = dev.commit(params, [_dm(dev, vals, h, w)])
+    host = torch.from_numpy(vals.view(np.int32)).pin_memory()
+    root_h, pcs_h = dev.commit_host(params, [(host, h, w)])
+    assert np.array_equal(root_d, root_h)
+    assert np.array_equal(pcs_d.tree.backing_matrix(), pcs_h.tree.backing_matrix())
+    assert np.array_equal(pcs_h.matrix(), vals)
+    pcs_d.free()
+    pcs_h.free()
