@@ -32,6 +32,7 @@ import time
 
 import numpy as np
 
+os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -273,7 +274,8 @@ def run_swirl(args):
     # the sampler starts before the warm-up: the first nvidia-smi start-up on a fresh box contends for the
     # driver lock for about a second, which would otherwise land in the timed region of this sync-heavy step
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # one poller per job: every nvidia-smi query briefly takes the driver lock of the whole node
+        sampler.start()
     if os.environ.get("BENCH_DEBUG"):
         def wrap(name):
             f = getattr(dev, name)
