@@ -292,7 +292,7 @@ class Oracle:
         off, hs, ws, rot, arrs = [0], [], [], [], []
         for traces in commits:
             for v, h, w, nr in traces:
-                arrs.append(np.ascontiguousarray(v, np.uint32))
+                arrs.append(np.ascontiguousarray(v, np.uint32))  # may be empty when only shapes are needed (verifier)
                 hs.append(h)
                 ws.append(w)
                 rot.append(1 if nr else 0)
@@ -340,7 +340,7 @@ class Oracle:
             return _p(a) if a.size else None
         hs = np.array([m[1] for m in flat["mats"]], np.uint64)
         ws = np.array([m[2] for m in flat["mats"]], np.uint64)
-        arrs = [np.ascontiguousarray(m[0], np.uint32) for m in flat["mats"]]
+        arrs = [np.ascontiguousarray(m[0], np.uint32) for m in flat["mats"]]  # unused (may be empty) for the verifier
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         return (pp(flat["meta"]), pp(flat["nodes"]), pp(flat["cidx"]), pp(flat["inter"]), pp(flat["msg"]), pp(flat["pubs"])), ptrs, hs, ws, arrs
 

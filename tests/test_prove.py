@@ -63,50 +63,25 @@ def oracle_prove(oracle, airs, order, is_required, vk_pre_hash):
 
 
 def test_oracle_whole_proof_verifies(oracle):
+    import verify_chain
+
     airs, order = fixture_airs(2)
     is_required = [True, True, True, True, False]
     vk = oracle.to_mont(np.arange(100, 108))
     pr = oracle_prove(oracle, airs, order, is_required, vk)
-    sa = pr["sorted_airs"]
-    # ---- verifier: same transcript prefix, then the three sub-verifiers
-    st = np.zeros(18, np.uint32)
-    oracle.sponge_observe(st, vk)
-    oracle.sponge_observe(st, pr["root"])
     commit1 = lambda m: oracle.stacked_commit(L_SKIP, N_STACK, LOG_BLOWUP, WHIR["k"], [m], want_codeword=False)[0]
-    for air_id, a in enumerate(airs):
-        if not is_required[air_id]:
-            oracle.sponge_observe(st, mont1(1))
-        oracle.sponge_observe(st, commit1(a.preprocessed) if a.preprocessed is not None else mont1(a.height.bit_length() - 1))
-        for c in a.cached:
-            oracle.sponge_observe(st, commit1(c))
-        oracle.sponge_observe(st, a.public_values)
-    ok, r = oracle.bc_verify(st, L_SKIP, D, LOGUP_POW, A.flatten(sa), len(sa), pr["n_max"], pr["bc"])
-    assert ok
-    # column openings (tail of the batch-constraint proof) -> (claim, rot claim) per commit, per column
-    n_open = sum((a.common_main[2] + sum(m[2] for m in a.cached) + (a.preprocessed[2] if a.preprocessed is not None else 0))
-                 * (2 if a.need_rot else 1) for a in sa)
-    op = pr["bc"][-4 * n_open:].reshape(-1, 4)
-    pos, per_air = 0, []
-    for a in sa:
-        parts = []
-        for m in [a.common_main] + ([a.preprocessed] if a.preprocessed is not None else []) + a.cached:
-            n = m[2] * (2 if a.need_rot else 1)
-            parts.append(op[pos:pos + n])
-            pos += n
-        per_air.append(parts)
-    zero = np.zeros(4, np.uint32)
-    pairs = lambda part, rot: [np.concatenate([part[2 * i], part[2 * i + 1]]) for i in range(len(part) // 2)] if rot else \
-        [np.concatenate([c, zero]) for c in part]
-    t_claims = [p_ for a, parts in zip(sa, per_air) for p_ in pairs(parts[0], a.need_rot)]
-    for a, parts in zip(sa, per_air):
-        for part in parts[1:]:
-            t_claims += pairs(part, a.need_rot)
-    ok, u = oracle.stacked_reduction_verify(st, L_SKIP, N_STACK, pr["commits"], np.array(t_claims), r, pr["stacking"])
-    assert ok and np.array_equal(u, pr["u"])
-    n0 = (2 * ((1 << L_SKIP) - 1) + 1) * 4 + N_STACK * 8
-    openings = pr["stacking"][n0:].reshape(-1, 4)
-    assert oracle.whir_verify(st, L_SKIP, N_STACK, LOG_BLOWUP, WHIR, pr["whir"], pr["widths"], openings, pr["roots"], pr["u_cube"])
+    pre_cached = [(commit1(a.preprocessed) if a.preprocessed is not None else None, [commit1(c) for c in a.cached]) for a in airs]
+    ok, st = verify_chain.verify(oracle, L_SKIP, N_STACK, LOG_BLOWUP, D, LOGUP_POW, WHIR, vk, airs, is_required, pr["root"],
+                                 pre_cached, pr["bc"], pr["stacking"], pr["whir"])
+    assert ok is True, st
     assert np.array_equal(st, pr["st"])
+    # a proof with one flipped word in any part is rejected at that stage
+    for key, stage in (("bc", "batch_constraints"), ("stacking", "stacked_reduction"), ("whir", "whir")):
+        bad = {k: pr[k].copy() for k in ("bc", "stacking", "whir")}
+        bad[key][5] ^= 1
+        ok, where = verify_chain.verify(oracle, L_SKIP, N_STACK, LOG_BLOWUP, D, LOGUP_POW, WHIR, vk, airs, is_required,
+                                        pr["root"], pre_cached, bad["bc"], bad["stacking"], bad["whir"])
+        assert ok is False and where == stage, (key, where)
 
 
 @pytest.mark.gpu
