@@ -20,6 +20,7 @@
 // normalisation factors and all polynomial bookkeeping stay on the host with the transcript.
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "ext.cuh"
@@ -329,7 +330,8 @@ __global__ void leaves_fill_kernel(uint32_t* __restrict__ leaves, size_t n, Ext 
 }
 
 // Round 0: thread = (hypercube point x, coset point p).  partials[block][p * 12 + 4k + c] =
-// sum_x eq_xi[x] * acc_k at point p.
+// sum_x eq_xi[x] * acc_k at point p.  All present AIRs share one launch: block -> (AIR, chunk) through
+// block_air / first_block.
 struct R0Args {
     const Instr* code;
     uint32_t n_instr;
@@ -338,7 +340,9 @@ struct R0Args {
     const uint32_t* lde;    // [P][N]: Lagrange coefficients of D at the P coset points
     const uint32_t* eq_xi;  // 2^n_lift EF
     int l_skip, n_lift, P, x_per_block;
-    uint32_t* partials;
+    uint32_t first_block, n_blocks;
+    uint32_t* partials;  // this AIR's [n_blocks][P * 12]
+    uint32_t* result;    // this AIR's [P * 12]
 };
 // sum_i lde[i] * c[i] over one 16-element chunk with lazy reduction (4 products per Montgomery reduction)
 __device__ __forceinline__ uint32_t chunk_dot16(const uint32_t (&l)[16], const uint32_t (&c)[16]) {
@@ -352,13 +356,18 @@ __device__ __forceinline__ uint32_t chunk_dot16(const uint32_t (&l)[16], const u
 // LOGN = 4: the thread's 16 Lagrange coefficients live in registers and chunks are fetched as four
 // 16-byte loads; LOGN = 0: generic l_skip.  Two hypercube points per thread run in lockstep.
 template <int NS, int LOGN>
-__global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
+__global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(const R0Args* __restrict__ descs,
+                                                                const uint16_t* __restrict__ block_air) {
     extern __shared__ uint32_t sm[];  // [blockDim][13] reduction scratch, then [NS][LN][blockDim] value slots
     constexpr int LN = 2;
+    const R0Args a = descs[block_air[blockIdx.x]];
+    const uint32_t bidx = blockIdx.x - a.first_block;
     const int P = a.P, N = 1 << a.l_skip;
-    const int p = threadIdx.x % P, g = threadIdx.x / P, G = blockDim.x / P;
+    const int G = blockDim.x / P;
+    const bool idle = (int)threadIdx.x >= P * G;  // blockDim is fixed; P need not divide it
+    const int p = idle ? 0 : threadIdx.x % P, g = idle ? 0 : threadIdx.x / P;
     const size_t nx = size_t(1) << a.n_lift;
-    const size_t x0 = (size_t)blockIdx.x * a.x_per_block, x1 = min(x0 + (size_t)a.x_per_block, nx);
+    const size_t x0 = (size_t)bidx * a.x_per_block, x1 = idle ? 0 : min(x0 + (size_t)a.x_per_block, nx);
     const uint32_t* lde = a.lde + (size_t)p * N;
     uint32_t lreg[16];
     if (LOGN == 4) {
@@ -428,8 +437,18 @@ __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(R0Args a) {
         const int pi = o / 12, k = o % 12;
         uint32_t s = 0;
         for (int gg = 0; gg < G; gg++) s = bb::add(s, sm[(gg * P + pi) * 13 + k]);
-        a.partials[(size_t)blockIdx.x * (P * 12) + o] = s;
+        a.partials[(size_t)bidx * (P * 12) + o] = s;
     }
+}
+// per AIR (blockIdx.y): result[o] = sum_b partials[b * nv + o]
+__global__ void bc_reduce_multi_kernel(const R0Args* __restrict__ descs) {
+    const R0Args a = descs[blockIdx.y];
+    const int nv = a.P * 12;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nv) return;
+    uint32_t s = 0;
+    for (uint32_t b = 0; b < a.n_blocks; b++) s = bb::add(s, a.partials[(size_t)b * nv + o]);
+    a.result[o] = s;
 }
 __global__ void bc_reduce_kernel(const uint32_t* __restrict__ partials, size_t nblocks, int nv, uint32_t* __restrict__ result) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,16 +470,34 @@ struct MleArgs {
     const uint32_t* eq_xi;
     size_t ny;
     int single;
+    uint32_t first_block, n_blocks;  // this AIR's blocks inside the shared launch
     uint32_t* partials;
     unsigned int* ticket;
     uint32_t* result;
 };
+// every AIR with live tables folds in one launch: out[j] = lerp(in[2j], in[2j+1], r)
+struct FoldArgs {
+    const uint32_t* in;
+    uint32_t* out;
+    size_t n_out;
+    uint32_t first_block;
+};
+__global__ void __launch_bounds__(BC_BLOCK)
+ef_fold_multi_kernel(const FoldArgs* __restrict__ descs, const uint16_t* __restrict__ block_air, Ext r) {
+    const FoldArgs a = descs[block_air[blockIdx.x]];
+    const size_t j = (size_t)(blockIdx.x - a.first_block) * blockDim.x + threadIdx.x;
+    if (j >= a.n_out) return;
+    st_ext(a.out + 4 * j, ext_lerp(ldg_ext(a.in + 8 * j), ldg_ext(a.in + 8 * j + 4), r));
+}
 template <int NS, int D>
-__global__ void __launch_bounds__(128, 4) batch_mle_kernel(MleArgs a) {
+__global__ void __launch_bounds__(128, 4) batch_mle_kernel(const MleArgs* __restrict__ descs,
+                                                           const uint16_t* __restrict__ block_air) {
+    const MleArgs a = descs[block_air[blockIdx.x]];
+    const uint32_t bidx = blockIdx.x - a.first_block;
     uint32_t v[D * 12];
 #pragma unroll
     for (int i = 0; i < D * 12; i++) v[i] = 0;
-    for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)gridDim.x * blockDim.x) {
+    for (size_t y = (size_t)bidx * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)a.n_blocks * blockDim.x) {
         const Ext e = a.single ? bb::ext_one() : ldg_ext(a.eq_xi + 4 * y);
         Ext acc[D][3];
 #pragma unroll
@@ -491,17 +528,17 @@ __global__ void __launch_bounds__(128, 4) batch_mle_kernel(MleArgs a) {
                 for (int c = 0; c < 4; c++) v[X * 12 + 4 * k + c] = bb::add(v[X * 12 + 4 * k + c], t.c[c]);
             }
     }
-    grid_sum<D * 12>(v, a.partials, a.ticket, a.result);
+    group_sum<D * 12>(v, a.partials, a.ticket, a.result, a.n_blocks, bidx);
 }
 
 template <int NS>
-static void launch_mle(int D, const MleArgs& a, int grid, cudaStream_t st) {
+static void launch_mle(int D, const MleArgs* descs, const uint16_t* block_air, int grid, cudaStream_t st) {
     switch (D) {
-        case 1: batch_mle_kernel<NS, 1><<<grid, 128, 0, st>>>(a); break;
-        case 2: batch_mle_kernel<NS, 2><<<grid, 128, 0, st>>>(a); break;
-        case 3: batch_mle_kernel<NS, 3><<<grid, 128, 0, st>>>(a); break;
-        case 4: batch_mle_kernel<NS, 4><<<grid, 128, 0, st>>>(a); break;
-        default: batch_mle_kernel<NS, 5><<<grid, 128, 0, st>>>(a); break;
+        case 1: batch_mle_kernel<NS, 1><<<grid, 128, 0, st>>>(descs, block_air); break;
+        case 2: batch_mle_kernel<NS, 2><<<grid, 128, 0, st>>>(descs, block_air); break;
+        case 3: batch_mle_kernel<NS, 3><<<grid, 128, 0, st>>>(descs, block_air); break;
+        case 4: batch_mle_kernel<NS, 4><<<grid, 128, 0, st>>>(descs, block_air); break;
+        default: batch_mle_kernel<NS, 5><<<grid, 128, 0, st>>>(descs, block_air); break;
     }
 }
 // NS buckets keep the per-thread slot array (local memory) as small as the program allows
@@ -820,14 +857,28 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                                     ext_mul(s.eq_3b[i], ext_mul_base(beta_pows[it.msg_len], bb::to_mont(it.bus_index + 1))));
         }
         SWIRL_TRY(upload(w.data(), w.size() * 4, (void**)&s.d_weights));
-        SWIRL_CUDA(dev_alloc(ctx, &s.d_eq_xi, (size_t(4) << s.n_lift)));
-        to_free.push_back(s.d_eq_xi);
+    }
+    // eq(xi[l_skip..], .) tables are shared by all AIRs of one height class
+    std::map<int, uint32_t*> eq_tab;
+    auto build_eq = [&](int first_var, int n_lift) -> int {  // table over xi[first_var .. l_skip + n_lift)
         TensorArgs ta;
-        for (int b = 0; b < s.n_lift; b++) {
-            memcpy(ta.w0[b], ext_sub(bb::ext_one(), xi[l_skip + b]).c, 16);
-            memcpy(ta.w1[b], xi[l_skip + b].c, 16);
+        const int nv = l_skip + n_lift - first_var;
+        for (int b = 0; b < nv; b++) {
+            memcpy(ta.w0[b], ext_sub(bb::ext_one(), xi[first_var + b]).c, 16);
+            memcpy(ta.w1[b], xi[first_var + b].c, 16);
         }
-        SWIRL_TRY(mle_tensor_table(ctx, ta, s.n_lift, s.d_eq_xi));
+        return mle_tensor_table(ctx, ta, nv, eq_tab[n_lift]);
+    };
+    for (size_t t = 0; t < n_airs; t++) {
+        TraceState& s = T[t];
+        if (!eq_tab.count(s.n_lift)) {
+            uint32_t* e = nullptr;
+            SWIRL_CUDA(dev_alloc(ctx, &e, (size_t(4) << s.n_lift)));
+            to_free.push_back(e);
+            eq_tab[s.n_lift] = e;
+            SWIRL_TRY(build_eq(l_skip, s.n_lift));
+        }
+        s.d_eq_xi = eq_tab[s.n_lift];
     }
 
     // ---- round 0 ---------------------------------------------------------------------------------------
@@ -858,48 +909,69 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     uint32_t* d_r0 = nullptr;
     SWIRL_CUDA(dev_alloc(ctx, &d_r0, r0_off[n_airs] + 4));
     to_free.push_back(d_r0);
-    for (size_t t = 0; t < n_airs; t++) {
-        TraceState& s = T[t];
-        const int cd = (int)airs[t].constraint_degree;
-        if (cd == 0) continue;
-        R0Args ra{};
-        ra.code = s.d_code;
-        ra.n_instr = (uint32_t)s.prog.code.size();
-        ra.parts = s.d_parts;
-        ra.weights = s.d_weights;
-        ra.lde = d_lde[cd];
-        ra.eq_xi = s.d_eq_xi;
-        ra.l_skip = l_skip;
-        ra.n_lift = s.n_lift;
-        ra.P = (int)(cd * N);
-        const int G = std::max(1, BC_BLOCK / ra.P);
-        const int threads = ra.P * G;
-        const size_t nx = size_t(1) << s.n_lift;
-        ra.x_per_block = G * 4;
-        const size_t blocks = (nx + ra.x_per_block - 1) / ra.x_per_block;
-        uint32_t* part = nullptr;
-        SWIRL_CUDA(dev_alloc(ctx, &part, blocks * (size_t)ra.P * 12));
-        to_free.push_back(part);
-        ra.partials = part;
-#define BC_R0(NS)                                                                                            \
-    do {                                                                                                     \
-        const size_t smem = (size_t)threads * (13 + ((NS) <= 64 ? (NS) * 2 : 0)) * 4;                        \
-        if (l_skip == 4) {                                                                                   \
-            cudaFuncSetAttribute(batch_round0_kernel<NS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            batch_round0_kernel<NS, 4><<<(unsigned)blocks, threads, smem, ctx->stream>>>(ra);               \
-        } else {                                                                                             \
-            cudaFuncSetAttribute(batch_round0_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            batch_round0_kernel<NS, 0><<<(unsigned)blocks, threads, smem, ctx->stream>>>(ra);               \
-        }                                                                                                    \
-    } while (0)
-        {
-            SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
-            BC_DISPATCH_NS(s.prog.n_slots, BC_R0);
+    int max_slots = 1;
+    for (size_t t = 0; t < n_airs; t++) max_slots = std::max(max_slots, T[t].prog.n_slots);
+    {
+        std::vector<R0Args> descs;
+        std::vector<uint16_t> block_air;
+        size_t part_words = 0;
+        for (size_t t = 0; t < n_airs; t++) {
+            TraceState& s = T[t];
+            const int cd = (int)airs[t].constraint_degree;
+            if (cd == 0) continue;
+            R0Args ra{};
+            ra.code = s.d_code;
+            ra.n_instr = (uint32_t)s.prog.code.size();
+            ra.parts = s.d_parts;
+            ra.weights = s.d_weights;
+            ra.lde = d_lde[cd];
+            ra.eq_xi = s.d_eq_xi;
+            ra.l_skip = l_skip;
+            ra.n_lift = s.n_lift;
+            ra.P = (int)(cd * N);
+            const int G = std::max(1, BC_BLOCK / ra.P);
+            const size_t nx = size_t(1) << s.n_lift;
+            ra.x_per_block = G * 4;
+            ra.n_blocks = (uint32_t)((nx + ra.x_per_block - 1) / ra.x_per_block);
+            ra.first_block = (uint32_t)block_air.size();
+            ra.partials = (uint32_t*)(uintptr_t)part_words;  // offset for now, rebased below
+            ra.result = d_r0 + r0_off[t];
+            part_words += (size_t)ra.n_blocks * ra.P * 12;
+            SWIRL_REQUIRE(descs.size() < 65535, "too many AIRs");
+            block_air.insert(block_air.end(), ra.n_blocks, (uint16_t)descs.size());
+            descs.push_back(ra);
         }
+        if (!descs.empty()) {
+            uint32_t* part = nullptr;
+            SWIRL_CUDA(dev_alloc(ctx, &part, part_words + 4));
+            to_free.push_back(part);
+            for (auto& d : descs) d.partials = part + (size_t)(uintptr_t)d.partials;
+            R0Args* d_descs = nullptr;
+            uint16_t* d_ba = nullptr;
+            SWIRL_TRY(upload(descs.data(), descs.size() * sizeof(R0Args), (void**)&d_descs));
+            SWIRL_TRY(upload(block_air.data(), block_air.size() * sizeof(uint16_t), (void**)&d_ba));
+            const unsigned blocks = (unsigned)block_air.size();
+#define BC_R0(NS)                                                                                                     \
+    do {                                                                                                              \
+        const size_t smem = (size_t)BC_BLOCK * (13 + ((NS) <= 64 ? (NS) * 2 : 0)) * 4;                               \
+        if (l_skip == 4) {                                                                                            \
+            cudaFuncSetAttribute(batch_round0_kernel<NS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            batch_round0_kernel<NS, 4><<<blocks, BC_BLOCK, smem, ctx->stream>>>(d_descs, d_ba);                      \
+        } else {                                                                                                      \
+            cudaFuncSetAttribute(batch_round0_kernel<NS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            batch_round0_kernel<NS, 0><<<blocks, BC_BLOCK, smem, ctx->stream>>>(d_descs, d_ba);                      \
+        }                                                                                                             \
+    } while (0)
+            {
+                SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
+                BC_DISPATCH_NS(max_slots, BC_R0);
+            }
 #undef BC_R0
-        SWIRL_LAUNCH_CHECK(ctx);
-        bc_reduce_kernel<<<(ra.P * 12 + 255) / 256, 256, 0, ctx->stream>>>(part, blocks, ra.P * 12, d_r0 + r0_off[t]);
-        SWIRL_LAUNCH_CHECK(ctx);
+            SWIRL_LAUNCH_CHECK(ctx);
+            const int max_nv = D * (int)N * 12;
+            bc_reduce_multi_kernel<<<dim3((max_nv + 255) / 256, (unsigned)descs.size()), 256, 0, ctx->stream>>>(d_descs);
+            SWIRL_LAUNCH_CHECK(ctx);
+        }
     }
     std::vector<uint32_t> h_r0(r0_off[n_airs] + 4);
     SWIRL_CUDA(cudaMemcpyAsync(h_r0.data(), d_r0, r0_off[n_airs] * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1068,14 +1140,36 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
 
     // ---- MLE rounds (mod.rs:314-395, cpu.rs:463-597) --------------------------------------------------------
     const int s_deg = D + 1;
+    MleArgs* d_mle_descs = nullptr;
+    FoldArgs* d_fold_descs = nullptr;
+    uint16_t *d_mle_ba = nullptr, *d_fold_ba = nullptr;
+    size_t max_fold_blocks = 0;
+    for (size_t t = 0; t < n_airs; t++) max_fold_blocks += ((size_t)T[t].total_cols * (T[t].h / 2) + BC_BLOCK - 1) / BC_BLOCK + 1;
+    SWIRL_CUDA(dev_alloc(ctx, &d_mle_descs, n_airs));
+    SWIRL_CUDA(dev_alloc(ctx, &d_fold_descs, n_airs));
+    SWIRL_CUDA(dev_alloc(ctx, &d_mle_ba, (size_t)rs->max_blocks));
+    SWIRL_CUDA(dev_alloc(ctx, &d_fold_ba, max_fold_blocks));
+    to_free.push_back(d_mle_descs);
+    to_free.push_back(d_fold_descs);
+    to_free.push_back(d_mle_ba);
+    to_free.push_back(d_fold_ba);
     for (int round = 1; round <= n_max; round++) {
         const Ext r_prev = r[round - 1];
         const Ext eq_r_acc = eq_ns.back(), eq_sharp_r_acc = eq_sharp_ns.back();
-        std::vector<int> mode(n_airs, 0);  // 0: hypercube sum, 1: single row now, 2: tail multiply
+        std::vector<int> mode(n_airs, 0);  // 0: hypercube sum, 1: single row now, 2: tail multiply, 3: nothing to evaluate
+        // eq tables of this round, one per height class still summing over a hypercube
+        for (auto& kv : eq_tab)
+            if (round <= kv.first) SWIRL_TRY(build_eq(l_skip + round, kv.first));
+        std::vector<MleArgs> descs;
+        std::vector<uint16_t> block_air;
         for (size_t t = 0; t < n_airs; t++) {
             TraceState& s = T[t];
             if (airs[t].constraint_degree == 0 && !airs[t].n_interactions && !airs[t].n_constraints) {
                 mode[t] = 3;
+                continue;
+            }
+            if (round > s.n_lift + 1) {
+                mode[t] = 2;
                 continue;
             }
             MleArgs ma{};
@@ -1084,43 +1178,39 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             ma.base = s.ef[s.cur];
             ma.h = s.h;
             ma.weights = s.d_weights;
-            ma.partials = rs->d_partials;
-            ma.ticket = rs->d_ticket;
+            ma.eq_xi = s.d_eq_xi;
+            ma.ticket = rs->d_ticket + (t & 1023);
+            SWIRL_REQUIRE(n_airs <= 256, "too many AIRs for the result scratch");
             ma.result = rs->d_result + t * 64;
-            SWIRL_REQUIRE(t * 64 + 64 <= 16384, "too many AIRs for the result scratch");
-            if (round > s.n_lift) {
-                if (round != s.n_lift + 1) {
-                    mode[t] = 2;
-                    continue;
-                }
+            if (round == s.n_lift + 1) {
                 mode[t] = 1;
                 ma.single = 1;
                 ma.ny = 1;
-                ma.eq_xi = s.d_eq_xi;
-#define BC_MLE1(NS) launch_mle<NS>(1, ma, 1, ctx->stream)
-                BC_DISPATCH_NS(s.prog.n_slots, BC_MLE1);
-#undef BC_MLE1
-                SWIRL_LAUNCH_CHECK(ctx);
+                ma.n_blocks = 1;
             } else {
                 const int log_ny = s.n_lift - round;
-                TensorArgs ta;
-                for (int b = 0; b < log_ny; b++) {
-                    memcpy(ta.w0[b], ext_sub(bb::ext_one(), xi[l_skip + round + b]).c, 16);
-                    memcpy(ta.w1[b], xi[l_skip + round + b].c, 16);
-                }
-                SWIRL_TRY(mle_tensor_table(ctx, ta, log_ny, s.d_eq_xi));
                 ma.single = 0;
                 ma.ny = size_t(1) << log_ny;
-                ma.eq_xi = s.d_eq_xi;
-                int grid = (int)std::min<size_t>((ma.ny + 127) / 128, (size_t)ctx->sm_count * 8);
-#define BC_MLE(NS) launch_mle<NS>(D, ma, grid, ctx->stream)
-                {
-                    SwirlTimed timed(ctx, SWIRL_T_BC_MLE);
-                    BC_DISPATCH_NS(s.prog.n_slots, BC_MLE);
-                }
-#undef BC_MLE
-                SWIRL_LAUNCH_CHECK(ctx);
+                ma.n_blocks = (uint32_t)std::min<size_t>((ma.ny + 127) / 128, (size_t)ctx->sm_count * 8);
             }
+            ma.first_block = (uint32_t)block_air.size();
+            ma.partials = rs->d_partials + (size_t)ma.first_block * 64;
+            block_air.insert(block_air.end(), ma.n_blocks, (uint16_t)descs.size());
+            descs.push_back(ma);
+        }
+        if (!descs.empty()) {
+            SWIRL_REQUIRE(block_air.size() <= (size_t)rs->max_blocks, "too many blocks for the reduction scratch");
+            SWIRL_CUDA(cudaMemcpyAsync(d_mle_descs, descs.data(), descs.size() * sizeof(MleArgs), cudaMemcpyHostToDevice, ctx->stream));
+            SWIRL_CUDA(cudaMemcpyAsync(d_mle_ba, block_air.data(), block_air.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+            const int grid = (int)block_air.size();
+            // single-row AIRs evaluate lane 0 only; D lanes are still the kernel's width
+#define BC_MLE(NS) launch_mle<NS>(D, d_mle_descs, d_mle_ba, grid, ctx->stream)
+            {
+                SwirlTimed timed(ctx, SWIRL_T_BC_MLE);
+                BC_DISPATCH_NS(max_slots, BC_MLE);
+            }
+#undef BC_MLE
+            SWIRL_LAUNCH_CHECK(ctx);
         }
         SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
         // sp_evals[2t] numer, [2t+1] denom, [2n+t] zerocheck: D values (head) or 1 value (tail)
@@ -1206,12 +1296,24 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         const Ext r_round = tr.sample_ext();
         r.push_back(r_round);
         prev_s_eval = hp::horner(coeffs, r_round);
-        for (size_t t = 0; t < n_airs; t++) {
-            TraceState& s = T[t];
-            if (s.h <= 1) continue;
-            SWIRL_TRY(ef_fold_flat(ctx, s.ef[s.cur], s.ef[s.cur ^ 1], (size_t)s.total_cols * (s.h / 2), r_round));
-            s.cur ^= 1;
-            s.h >>= 1;
+        {
+            std::vector<FoldArgs> fd;
+            std::vector<uint16_t> fba;
+            for (size_t t = 0; t < n_airs; t++) {
+                TraceState& s = T[t];
+                if (s.h <= 1) continue;
+                FoldArgs f{s.ef[s.cur], s.ef[s.cur ^ 1], (size_t)s.total_cols * (s.h / 2), (uint32_t)fba.size()};
+                fba.insert(fba.end(), (f.n_out + BC_BLOCK - 1) / BC_BLOCK, (uint16_t)fd.size());
+                fd.push_back(f);
+                s.cur ^= 1;
+                s.h >>= 1;
+            }
+            if (!fd.empty()) {
+                SWIRL_CUDA(cudaMemcpyAsync(d_fold_descs, fd.data(), fd.size() * sizeof(FoldArgs), cudaMemcpyHostToDevice, ctx->stream));
+                SWIRL_CUDA(cudaMemcpyAsync(d_fold_ba, fba.data(), fba.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+                ef_fold_multi_kernel<<<(unsigned)fba.size(), BC_BLOCK, 0, ctx->stream>>>(d_fold_descs, d_fold_ba, r_round);
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
         }
         const Ext eq_r = hp::eq1(xi_cur, r_round);
         eq_ns.push_back(ext_mul(eq_ns[round - 1], eq_r));

@@ -55,26 +55,29 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t (&v)[NV]) {
 // writes the NV totals to `result` (mapped pinned host memory or device).  Field addition is
 // exact, so the summation order does not affect the value.  `ticket` must be zero on entry and is
 // reset for the next launch.  blockDim.x must be a multiple of 32, <= 1024, >= NV.
+// Group form: the blocks [0, nblocks) of one logical group (bidx = this block's index in the group)
+// reduce into `result`; several groups may share a launch, each with its own ticket and partials.
 template <int NV>
-__device__ __forceinline__ void grid_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
-                                         unsigned int* __restrict__ ticket, uint32_t* __restrict__ result) {
+__device__ __forceinline__ void group_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
+                                          unsigned int* __restrict__ ticket, uint32_t* __restrict__ result,
+                                          unsigned nblocks, unsigned bidx) {
     __shared__ bool sm_last;
     const uint32_t tot = block_sum<NV>(v);
-    if (gridDim.x == 1) {
+    if (nblocks == 1) {
         if (threadIdx.x < NV) result[threadIdx.x] = tot;
         return;
     }
-    if (threadIdx.x < NV) partials[(size_t)blockIdx.x * NV + threadIdx.x] = tot;
+    if (threadIdx.x < NV) partials[(size_t)bidx * NV + threadIdx.x] = tot;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) sm_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) sm_last = (atomicAdd(ticket, 1u) == nblocks - 1);
     __syncthreads();
     if (sm_last) {
         __threadfence();
         uint32_t acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; i++) acc[i] = 0;
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x) {
 #pragma unroll
             for (int i = 0; i < NV; i++) acc[i] = bb::add(acc[i], __ldcg(partials + (size_t)b * NV + i));
         }
@@ -83,12 +86,17 @@ __device__ __forceinline__ void grid_sum(uint32_t (&v)[NV], uint32_t* __restrict
         if (threadIdx.x == 0) *ticket = 0;
     }
 }
+template <int NV>
+__device__ __forceinline__ void grid_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
+                                         unsigned int* __restrict__ ticket, uint32_t* __restrict__ result) {
+    group_sum<NV>(v, partials, ticket, result, gridDim.x, blockIdx.x);
+}
 
 // Scratch every sumcheck-type phase needs: block partials, the ticket, and a mapped pinned result
 // area the host reads after synchronising the stream.
 struct RoundScratch {
     uint32_t* d_partials = nullptr;  // max_blocks * max_nv words
-    unsigned int* d_ticket = nullptr;
+    unsigned int* d_ticket = nullptr;  // 1024 zero-initialised tickets (one per group of a launch)
     uint32_t* h_result = nullptr;  // pinned, mapped
     uint32_t* d_result = nullptr;  // device alias of h_result
     int max_blocks = 0;

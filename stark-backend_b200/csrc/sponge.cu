@@ -102,8 +102,8 @@ int round_scratch_get(swirl_ctx* ctx, RoundScratch** out) {
         RoundScratch* rs = new RoundScratch();
         rs->max_blocks = 8192;
         SWIRL_CUDA(cudaMalloc((void**)&rs->d_partials, (size_t)rs->max_blocks * 64 * sizeof(uint32_t)));
-        SWIRL_CUDA(cudaMalloc((void**)&rs->d_ticket, sizeof(unsigned int)));
-        SWIRL_CUDA(cudaMemset(rs->d_ticket, 0, sizeof(unsigned int)));
+        SWIRL_CUDA(cudaMalloc((void**)&rs->d_ticket, 1024 * sizeof(unsigned int)));
+        SWIRL_CUDA(cudaMemset(rs->d_ticket, 0, 1024 * sizeof(unsigned int)));
         SWIRL_CUDA(cudaHostAlloc((void**)&rs->h_result, 65536, cudaHostAllocMapped));
         SWIRL_CUDA(cudaHostGetDevicePointer((void**)&rs->d_result, rs->h_result, 0));
         ctx->round_scratch = rs;

@@ -122,10 +122,32 @@ whir_ood_kernel(const uint32_t* __restrict__ g_soa, size_t n, size_t col_stride,
     grid_sum<4>(v, partials, ticket, result);
 }
 
-// w[x] += gamma * eq(x, pow(z0)) + sum_q gamma^(q+2) * eq(x, pow(z_q)),  z_q in F (whir.rs:310-325)
+// w[x] += gamma * eq(x, pow(z0)) + sum_q gamma^(q+2) * eq(x, pow(z_q)),  z_q in F (whir.rs:310-325).
+// eq(x, pow(z)) = A_z[x_lo] * B_z[x_hi] (product over the low / high index bits), so the per-query
+// half tables are built first (whir_eq_halves_kernel) and an entry costs one base multiply and one
+// EF x F multiply per query instead of 2 * dim multiplies.
+// tabs: per query [A (2^lo_bits) | B (2^hi_bits)] base-field words.
 __global__ void __launch_bounds__(WH_BLOCK)
-whir_w_accumulate_kernel(uint32_t* __restrict__ w, size_t n, int dim, PowArgs z0p, const uint32_t* __restrict__ zs,
-                         const uint32_t* __restrict__ gamma_pows /* [0] = gamma, [1+q] = gamma^(q+2) */, int nq) {
+whir_eq_halves_kernel(const uint32_t* __restrict__ zs, int nq, int lo_bits, int hi_bits, uint32_t* __restrict__ tabs) {
+    const size_t per_q = (size_t(1) << lo_bits) + (size_t(1) << hi_bits);
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= per_q * (size_t)nq) return;
+    const size_t q = g / per_q, i = g % per_q;
+    const bool hi = i >= (size_t(1) << lo_bits);
+    const size_t idx = hi ? i - (size_t(1) << lo_bits) : i;
+    const int bits = hi ? hi_bits : lo_bits;
+    uint32_t zp = __ldg(zs + q), e = bb::R1;
+    if (hi)
+        for (int b = 0; b < lo_bits; b++) zp = bb::sqr(zp);  // z^(2^lo_bits)
+    for (int b = 0; b < bits; b++) {
+        e = bb::mul(e, ((idx >> b) & 1) ? zp : bb::sub(bb::R1, zp));
+        zp = bb::sqr(zp);
+    }
+    tabs[g] = e;
+}
+__global__ void __launch_bounds__(WH_BLOCK)
+whir_w_accumulate_kernel(uint32_t* __restrict__ w, size_t n, int dim, PowArgs z0p, const uint32_t* __restrict__ tabs,
+                         int lo_bits, const uint32_t* __restrict__ gamma_pows /* [0] = gamma, [1+q] = gamma^(q+2) */, int nq) {
     const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
     Ext e0 = bb::ext_one();
@@ -134,12 +156,11 @@ whir_w_accumulate_kernel(uint32_t* __restrict__ w, size_t n, int dim, PowArgs z0
         e0 = ext_mul(e0, ((x >> b) & 1) ? zb : ext_one_minus(zb));
     }
     Ext acc = ext_add(ld_ext(w + 4 * x), ext_mul(ldg_ext(gamma_pows), e0));
+    const size_t lo = x & ((size_t(1) << lo_bits) - 1), hi = x >> lo_bits;
+    const size_t per_q = (size_t(1) << lo_bits) + (size_t(1) << (dim - lo_bits));
     for (int q = 0; q < nq; q++) {
-        uint32_t zp = __ldg(zs + q), e = bb::R1;
-        for (int b = 0; b < dim; b++) {
-            e = bb::mul(e, ((x >> b) & 1) ? zp : bb::sub(bb::R1, zp));
-            zp = bb::sqr(zp);
-        }
+        const uint32_t* t = tabs + (size_t)q * per_q;
+        const uint32_t e = bb::mul(__ldg(t + lo), __ldg(t + (size_t(1) << lo_bits) + hi));
         acc = ext_add(acc, bb::ext_mul_base(ldg_ext(gamma_pows + 4 * (q + 1)), e));
     }
     st_ext(w + 4 * x, acc);
@@ -424,9 +445,21 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             }
             SWIRL_CUDA(cudaMemcpyAsync(d_gam, h_gam.data(), ((size_t)nq + 1) * 16, cudaMemcpyHostToDevice, ctx->stream));
             if (nq) SWIRL_CUDA(cudaMemcpyAsync(d_zs, h_zs.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
-            whir_w_accumulate_kernel<<<(unsigned)((n + WH_BLOCK - 1) / WH_BLOCK), WH_BLOCK, 0, ctx->stream>>>(w[cur], n, m - k, z0p,
-                                                                                                            d_zs, d_gam, nq);
-            SWIRL_LAUNCH_CHECK(ctx);
+            {
+                const int dim = m - k, lo_bits = dim / 2, hi_bits = dim - lo_bits;
+                const size_t per_q = (size_t(1) << lo_bits) + (size_t(1) << hi_bits);
+                uint32_t* tabs = nullptr;
+                SWIRL_CUDA(dev_alloc(ctx, &tabs, per_q * (size_t)(nq ? nq : 1)));
+                if (nq) {
+                    whir_eq_halves_kernel<<<(unsigned)((per_q * nq + WH_BLOCK - 1) / WH_BLOCK), WH_BLOCK, 0, ctx->stream>>>(
+                        d_zs, nq, lo_bits, hi_bits, tabs);
+                    SWIRL_LAUNCH_CHECK(ctx);
+                }
+                whir_w_accumulate_kernel<<<(unsigned)((n + WH_BLOCK - 1) / WH_BLOCK), WH_BLOCK, 0, ctx->stream>>>(
+                    w[cur], n, dim, z0p, tabs, lo_bits, d_gam, nq);
+                SWIRL_LAUNCH_CHECK(ctx);
+                dev_free(ctx, tabs);
+            }
             // h_gam / h_zs are reused next round: make sure the copies have been consumed
             SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
         }

@@ -72,7 +72,18 @@ class Coordinator:
         """per_air_pk: list of AirProvingKey indexed by air id.  per_trace: list of
         (air_id, AirProvingContext, [CommittedTraceData cached mains]) — sorted here as
         ProvingContext::into_sorted does (height descending, then air id; prover/types.rs:144-148)."""
+        import os
+        import time
+
         dev, ts, P = self.device, self.transcript, self.params
+        trace_on = bool(os.environ.get("SWIRL_PHASE_TIMING"))
+        marks = [("start", time.perf_counter())]
+
+        def mark(name):
+            if trace_on:
+                dev.synchronize()
+                marks.append((name, time.perf_counter()))
+
         ts.observe(vk_pre_hash)
         per_trace = sorted(per_trace, key=lambda t: (-t[1].common_main.height(), t[0]))
         if precommitted is None:
@@ -94,6 +105,7 @@ class Coordinator:
                     ts.observe(cd.commitment)
                 ts.observe(t[1].public_values)
         airs = [t[1] for t in per_trace]
+        mark("commit")
         constraints_proof, r = dev.prove_batch_constraints(ts, P.l_skip, P.max_constraint_degree, P.logup_pow_bits, airs)
         # prove_openings (cpu_backend.rs:139-220)
         pcs_list, need_rot = [common], [[a.need_rot for a in airs]]
@@ -102,7 +114,10 @@ class Coordinator:
             for cd in ([pk.preprocessed_data] if pk.preprocessed_data is not None else []) + list(cached):
                 pcs_list.append(cd.data)
                 need_rot.append([a.need_rot])
+        mark("batch_constraints")
         stacking, whir = dev.prove_openings(ts, P.whir, pcs_list, need_rot, r)
+        mark("openings")
+        self.phase_ms = {marks[i][0]: 1e3 * (marks[i][1] - marks[i - 1][1]) for i in range(1, len(marks))}
         return Proof(common_main_commit=root, constraints_proof=constraints_proof, stacking_proof=stacking, whir_proof=whir,
                      r=r, public_values=[a.public_values for a in airs], common_main_pcs=common,
                      log_heights=[a.common_main.height().bit_length() - 1 for a in airs])

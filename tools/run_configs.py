@@ -42,7 +42,8 @@ def prove_and_verify(name, airs, traces, l_skip, n_stack, log_blowup, D, logup_p
     for _ in range(reps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        proof = sb.Coordinator(dev, params).prove(vk, pk, per_trace)
+        coord = sb.Coordinator(dev, params)
+        proof = coord.prove(vk, pk, per_trace)
         dev.synchronize()
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
@@ -55,7 +56,7 @@ def prove_and_verify(name, airs, traces, l_skip, n_stack, log_blowup, D, logup_p
     tv = time.perf_counter() - t0
     proof.common_main_pcs.free()
     emit(config=name, prove_ms=best * 1e3, trace_cells=cells, cells_per_s=cells / best, proof_bytes=int(proof.words().size * 4),
-         oracle_verifier_accepts=bool(ok is True), failed_stage=None if ok is True else where, verify_s=tv, whir=whir,
+         phase_ms=coord.phase_ms, oracle_verifier_accepts=bool(ok is True), failed_stage=None if ok is True else where, verify_s=tv, whir=whir,
          params=dict(l_skip=l_skip, n_stack=n_stack, log_blowup=log_blowup, max_constraint_degree=D, logup_pow_bits=logup_pow))
 
 def shape_only(a, h, w):
