@@ -60,37 +60,76 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled during the timed region.  In-process NVML (nvidia_ml_py) on a
+    thread: a looping `nvidia-smi --query-gpu` child holds the driver lock for its whole multi-field query and
+    was seen to stall this sync-heavy step (~350 stream synchronisations per proof) by 0.1-0.6 s at random;
+    BENCH_SAMPLER=smi selects that recipe form anyway, BENCH_SAMPLER=none disables sampling."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.kind = index, [], None, os.environ.get("BENCH_SAMPLER", "nvml")
+        self._stop = threading.Event()
+        self.period = float(os.environ.get("BENCH_SMI_MS", "100")) / 1e3
 
     def start(self):
+        if self.kind == "none":
+            return
+        if self.kind == "nvml":
+            try:
+                import pynvml
+
+                pynvml.nvmlInit()
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                threading.Thread(target=self._poll_nvml, args=(pynvml,), daemon=True).start()
+                return
+            except Exception:
+                self.kind = "smi"
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "100")],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", "-i", str(self._physical_index()), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 str(int(self.period * 1e3))], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll_nvml(self, nv):
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.time(), [str(mhz), str(self.max_mhz), ""] + ["Active" if mask & b else "Not Active" for b in bits]))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0, t1):
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
         rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "sampler": self.kind}
         sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                "samples": len(rows)}
+                "samples": len(rows), "sampler": self.kind}
 
 
 def benchmark_air_dag(cols):
@@ -258,7 +297,7 @@ def run_swirl(args):
         ms = multi.max_over_ranks(a.elapsed_time(b), dev.torch_device)
         return ms, roots, t0, t1, proof, walls
 
-    def timed(fn, steps):
+    def timed(fn, steps, on_retry=None, label=None):
         """K steps; every step performs identical work (same trace, deterministic transcript), so a step
         that takes > 2.5x the median is a host/box stall (seen sporadically on shared boxes: 0.2-1.2 s):
         like a throttled run it is re-measured once, and both measurements are reported."""
@@ -266,9 +305,11 @@ def run_swirl(args):
         med = sorted(r[5])[len(r[5]) // 2]
         worst = multi.max_over_ranks(max(r[5]) / med, dev.torch_device)
         if worst > 2.5:
-            stalls[fn.__name__] = {"first_ms_per_step": r[0] / steps, "first_step_ms": [round(x, 1) for x in r[5]]}
+            stalls[label or fn.__name__] = {"first_ms_per_step": r[0] / steps, "first_step_ms": [round(x, 1) for x in r[5]]}
+            if on_retry:
+                on_retry()
             r = timed_once(fn, steps)
-        stalls.setdefault("step_ms", {})[fn.__name__] = [round(x, 1) for x in r[5]]
+        stalls.setdefault("step_ms", {})[label or fn.__name__] = [round(x, 1) for x in r[5]]
         return r[:5]
 
     # the sampler starts before the warm-up: the first nvidia-smi start-up on a fresh box contends for the
@@ -298,7 +339,7 @@ def run_swirl(args):
     # per-kernel-family durations: the same K steps again with the library's CUDA-event spans on
     # (an event pair per launch costs ~40% on this launch-heavy step, so it is kept out of `value`)
     dev.timing_enable(True)
-    timed(step_device, args.steps)
+    timed(step_device, args.steps, on_retry=lambda: dev.timing_enable(True), label="step_device_with_spans")  # enabling clears the spans
     spans = dev.timing_read()
     dev.timing_enable(False)
     clocks = sampler.stop(t0, time.time())
@@ -347,7 +388,7 @@ def run_swirl(args):
             "phases_ms_per_step": {k: v[2] for k, v in fam.items()},
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
                     "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk_["hbm_gbs"] if lde_ms else 0.0},
-            "proof_bytes": int(proof.words().size * 4),
+            "proof_bytes": len(proof.encode()),  # Proof::encode_to_vec() wire format (stark-backend_b200/codec.py)
             "host_step_ms": stalls.pop("step_ms"),
             "remeasured_after_host_stall": stalls or None,
         }

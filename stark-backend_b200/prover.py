@@ -49,6 +49,14 @@ class Proof:
     def words(self):
         return np.concatenate([self.common_main_commit, self.constraints_proof, self.stacking_proof, self.whir_proof])
 
+    def encode(self):
+        """Bytes of `Proof::encode_to_vec()` (proof.rs:226-257, codec.rs): canonical LE u32 words with the
+        reference's length prefixes."""
+        from . import codec
+
+        return codec.encode_proof(self.shape, self.common_main_commit, self.constraints_proof, self.stacking_proof,
+                                  self.whir_proof)
+
 
 class Coordinator:
     def __init__(self, device, params, transcript=None):
@@ -117,8 +125,24 @@ class Coordinator:
         mark("batch_constraints")
         stacking, whir = dev.prove_openings(ts, P.whir, pcs_list, need_rot, r)
         mark("openings")
+        from .codec import AirShape, ProofShape
+
+        lifted = lambda a: max(a.common_main.height(), 1 << P.l_skip)
+        total_interactions = sum(len(a.interactions) * lifted(a) for a in airs)
+        log_h = lambda a: a.common_main.height().bit_length() - 1
+        shape = ProofShape(
+            l_skip=P.l_skip, n_stack=P.n_stack, log_blowup=P.log_blowup, max_constraint_degree=P.max_constraint_degree,
+            k_whir=P.whir.k, num_queries=list(P.whir.num_queries),
+            airs=[AirShape([a.common_main.width()] + ([a.preprocessed.width()] if a.preprocessed is not None else [])
+                           + [m.width() for m in a.cached_mains], a.need_rot) for a in airs],
+            gkr_layers=total_interactions.bit_length() if total_interactions else 0,  # calculate_n_logup, lib.rs:82-93
+            n_max=max(max(log_h(a) for a in airs) - P.l_skip, 0), commit_widths=[d.width for d in pcs_list],
+            trace_vdata=[(log_h(present[i][1]), [cd.commitment for cd in present[i][2]]) if i in present else None
+                         for i in range(len(per_air_pk))],
+            public_values=[present[i][1].public_values if i in present else np.zeros(0, np.uint32)
+                           for i in range(len(per_air_pk))])
         self.phase_ms = {marks[i][0]: 1e3 * (marks[i][1] - marks[i - 1][1]) for i in range(1, len(marks))}
-        return Proof(common_main_commit=root, constraints_proof=constraints_proof, stacking_proof=stacking, whir_proof=whir,
+        return Proof(common_main_commit=root, constraints_proof=constraints_proof, stacking_proof=stacking, whir_proof=whir, shape=shape,
                      r=r, public_values=[a.public_values for a in airs], common_main_pcs=common,
                      log_heights=[a.common_main.height().bit_length() - 1 for a in airs])
 
