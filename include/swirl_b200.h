@@ -67,8 +67,11 @@ int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* 
 
 /* ---- device memory + transport (reference: DeviceDataTransporter, hal.rs:141-207;
  *      DeviceBuffer / cuda_memcpy, cuda-common/src/{d_buffer.rs,copy.rs}) ---------------------- */
-int swirl_malloc(swirl_ctx* ctx, size_t bytes, void** d_out); /* stream-ordered pool */
+int swirl_malloc(swirl_ctx* ctx, size_t bytes, void** d_out); /* stream-ordered; blocks >= 1 MiB come from the ctx arena */
 int swirl_free(swirl_ctx* ctx, void* d_ptr);
+/* The context keeps large scratch blocks for reuse by the next proof (the role of the reference's VPMM pool,
+ * docs/vpmm_spec.md); trim returns the idle ones to the driver. */
+int swirl_ctx_trim(swirl_ctx* ctx);
 int swirl_memcpy_h2d(swirl_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on the ctx stream */
 int swirl_memcpy_d2h(swirl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* synchronises */
 
@@ -148,6 +151,12 @@ int swirl_transcript_grind(swirl_ctx* ctx, swirl_transcript* ts, int bits, uint3
 int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves, int log_n,
                                   int assert_zero, uint32_t h_frac_sum[8], uint32_t* h_claims,
                                   uint32_t* h_polys, uint32_t* h_xi);
+/* Same, for a leaf layer whose tail is the constant fraction (0, pad_q): only the first n_stored leaves
+ * (2^log_n, or a multiple of 4) are read; the interaction layout of prove_zerocheck_and_logup pads with
+ * (0, alpha) (prover/logup_zerocheck/mod.rs:103-168).  The proof is the one the full 2^log_n leaves give. */
+int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves, uint64_t n_stored,
+                                         const uint32_t pad_q[4], int log_n, int assert_zero, uint32_t h_frac_sum[8],
+                                         uint32_t* h_claims, uint32_t* h_polys, uint32_t* h_xi);
 
 /* ---- phase level: TraceCommitter::commit (hal.rs:84-87) ------------------------------------- */
 

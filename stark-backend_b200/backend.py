@@ -390,6 +390,10 @@ class B200Device:
             out[name] = (ms.value, int(n.value))
         return out
 
+    def trim(self):
+        """Return the idle scratch blocks the context keeps for the next proof to the driver."""
+        check(self.lib.swirl_ctx_trim(self.ctx))
+
     def alloc(self, n_words):
         return torch.empty(int(n_words), dtype=torch.int32, device=self.torch_device)
 
@@ -479,8 +483,9 @@ class B200Device:
         return int(w.value)
 
     # -- LogUp-GKR (fractional_sumcheck, fractional_sumcheck_gkr.rs:60-213) ---------------------------
-    def gkr_fractional_sumcheck(self, ts, leaves, log_n, assert_zero=True):
-        """leaves: CUDA int32 tensor of 2^log_n Frac<EF> (8 words each).  Returns dict(frac_sum,
+    def gkr_fractional_sumcheck(self, ts, leaves, log_n, assert_zero=True, n_stored=None, pad_q=None):
+        """leaves: CUDA int32 tensor of 2^log_n Frac<EF> (8 words each) — or only the first n_stored of
+        them when the rest is the constant fraction (0, pad_q).  Returns dict(frac_sum,
         claims[log_n,16], polys[log_n(log_n-1)/2,12], xi[log_n,4]) of Montgomery words."""
         n_polys = log_n * (log_n - 1) // 2
         frac_sum = np.zeros(8, np.uint32)
@@ -488,8 +493,14 @@ class B200Device:
         polys = np.zeros((max(n_polys, 1), 12), np.uint32)
         xi = np.zeros((log_n, 4), np.uint32)
         self._sync_torch()
-        check(self.lib.swirl_gkr_fractional_sumcheck(self.ctx, C.byref(ts.c), leaves.data_ptr(), log_n, 1 if assert_zero else 0,
-                                                     frac_sum.ctypes.data, claims.ctypes.data, polys.ctypes.data, xi.ctypes.data))
+        if n_stored is None:
+            check(self.lib.swirl_gkr_fractional_sumcheck(self.ctx, C.byref(ts.c), leaves.data_ptr(), log_n, 1 if assert_zero else 0,
+                                                         frac_sum.ctypes.data, claims.ctypes.data, polys.ctypes.data, xi.ctypes.data))
+        else:
+            pq = np.ascontiguousarray(pad_q, dtype=np.uint32)
+            check(self.lib.swirl_gkr_fractional_sumcheck_padded(self.ctx, C.byref(ts.c), leaves.data_ptr(), int(n_stored), pq.ctypes.data,
+                                                                log_n, 1 if assert_zero else 0, frac_sum.ctypes.data, claims.ctypes.data,
+                                                                polys.ctypes.data, xi.ctypes.data))
         return dict(frac_sum=frac_sum, claims=claims, polys=polys[:n_polys], xi=xi)
 
     # -- MultiRapProver::prove_rap_constraints (prove_zerocheck_and_logup, logup_zerocheck/mod.rs:40-438) --

@@ -1,6 +1,7 @@
 // C-ABI glue: context lifetime, error text, and the thin extern "C" wrappers over the kernel-level
 // primitives (include/swirl_b200.h).  Phase-level entry points live next to their orchestration
 // (commit.cu, sponge.cu).
+#include <cstdlib>
 #include <string>
 
 #include "kernels.cuh"
@@ -15,6 +16,69 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     g_last_error = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") in " + what +
                    " at " + file + ":" + std::to_string(line);
     return (int)e;
+}
+
+double stall_debug_ms() {
+    static const double lim = [] {
+        const char* e = getenv("SWIRL_STALL_DEBUG");
+        return e ? atof(e) : 0.0;
+    }();
+    return lim;
+}
+static cudaError_t timed_malloc_async(swirl_ctx* ctx, void** p, size_t bytes) {
+    const double lim = stall_debug_ms();
+    if (lim <= 0) return cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream);
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 4, ctx->stream);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > lim) stall_report("cudaMallocAsync", __FILE__, __LINE__, ms, bytes);
+    return e;
+}
+
+cudaError_t arena_alloc(swirl_ctx* ctx, void** p, size_t bytes) {
+    if (bytes < ARENA_MIN) return timed_malloc_async(ctx, p, bytes);
+    bytes = (bytes + 511) & ~size_t(511);
+    auto it = ctx->arena_free.lower_bound(bytes);
+    if (it != ctx->arena_free.end() && it->first <= bytes + bytes / 4) {
+        *p = it->second;
+        ctx->arena_live[*p] = it->first;
+        ctx->arena_free.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = timed_malloc_async(ctx, p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the idle blocks back and try once more
+        cudaGetLastError();
+        arena_trim(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        e = timed_malloc_async(ctx, p, bytes);
+    }
+    if (e == cudaSuccess) {
+        ctx->arena_live[*p] = bytes;
+        ctx->arena_bytes += bytes;
+    }
+    return e;
+}
+
+void arena_free_block(swirl_ctx* ctx, void* p) {
+    auto it = ctx->arena_live.find(p);
+    if (it == ctx->arena_live.end()) {
+        cudaFreeAsync(p, ctx->stream);
+        return;
+    }
+    ctx->arena_free.emplace(it->second, p);
+    ctx->arena_live.erase(it);
+}
+
+void arena_trim(swirl_ctx* ctx) {
+    for (auto& kv : ctx->arena_free) {
+        cudaFreeAsync(kv.second, ctx->stream);
+        ctx->arena_bytes -= kv.first;
+    }
+    ctx->arena_free.clear();
+}
+
+void stall_report(const char* what, const char* file, int line, double ms, size_t bytes) {
+    fprintf(stderr, "[swirl stall] %s %.1f ms (%zu bytes) at %s:%d\n", what, ms, bytes, file, line);
 }
 
 }  // namespace swirl
@@ -80,6 +144,10 @@ int swirl_ctx_destroy(swirl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream || !ctx->owns_stream) cudaStreamSynchronize(ctx->stream);
     timing_clear(ctx);
+    arena_trim(ctx);
+    for (auto& kv : ctx->arena_live) cudaFreeAsync(kv.first, ctx->stream);  // blocks the caller never released
+    ctx->arena_live.clear();
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->tw_lo) cudaFree(ctx->tw_lo);
     if (ctx->tw_hi) cudaFree(ctx->tw_hi);
     for (uint32_t* t : ctx->tw_lo_scaled)
@@ -93,7 +161,7 @@ int swirl_ctx_destroy(swirl_ctx* ctx) {
 
 int swirl_ctx_synchronize(swirl_ctx* ctx) {
     SWIRL_REQUIRE(ctx, "null ctx");
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     return 0;
 }
 
@@ -120,7 +188,7 @@ static void timing_clear(swirl_ctx* ctx) {
 
 int swirl_ctx_timing_enable(swirl_ctx* ctx, int on) {
     SWIRL_REQUIRE(ctx, "null ctx");
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     timing_clear(ctx);
     ctx->timing = on != 0;
     return 0;
@@ -129,7 +197,7 @@ int swirl_ctx_timing_enable(swirl_ctx* ctx, int on) {
 int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* count) {
     SWIRL_REQUIRE(ctx && total_ms && count, "null argument");
     SWIRL_REQUIRE(slot >= 0 && slot < SWIRL_T_SLOTS, "slot");
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     double tot = 0;
     uint64_t n = 0;
     for (auto& s : ctx->spans)
@@ -147,13 +215,20 @@ int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* 
 int swirl_malloc(swirl_ctx* ctx, size_t bytes, void** d_out) {
     SWIRL_REQUIRE(ctx && d_out, "null argument");
     SWIRL_CUDA(cudaSetDevice(ctx->device));
-    SWIRL_CUDA(cudaMallocAsync(d_out, bytes ? bytes : 1, ctx->stream));
+    SWIRL_CUDA(arena_alloc(ctx, d_out, bytes ? bytes : 1));
     return 0;
 }
 
 int swirl_free(swirl_ctx* ctx, void* d_ptr) {
     SWIRL_REQUIRE(ctx, "null ctx");
-    if (d_ptr) SWIRL_CUDA(cudaFreeAsync(d_ptr, ctx->stream));
+    if (d_ptr) arena_free_block(ctx, d_ptr);
+    return 0;
+}
+
+int swirl_ctx_trim(swirl_ctx* ctx) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    arena_trim(ctx);
     return 0;
 }
 
@@ -166,7 +241,7 @@ int swirl_memcpy_h2d(swirl_ctx* ctx, void* d_dst, const void* h_src, size_t byte
 int swirl_memcpy_d2h(swirl_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
     SWIRL_REQUIRE(ctx && ((h_dst && d_src) || bytes == 0), "null argument");
     if (bytes) SWIRL_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     return 0;
 }
 

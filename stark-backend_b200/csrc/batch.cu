@@ -642,11 +642,11 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         swirl_ctx* ctx;
         std::vector<void*>& v;
         ~Cleanup() {
-            for (void* p : v) cudaFreeAsync(p, ctx->stream);
+            for (void* p : v) arena_free_block(ctx, p);
         }
     } cleanup{ctx, to_free};
     auto upload = [&](const void* src, size_t bytes, void** dst) -> int {
-        SWIRL_CUDA(cudaMallocAsync(dst, bytes ? bytes : 4, ctx->stream));
+        SWIRL_CUDA(arena_alloc(ctx, dst, bytes ? bytes : 4));
         to_free.push_back(*dst);
         if (bytes) SWIRL_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return 0;
@@ -749,13 +749,14 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     // ---- LogUp input layer + GKR -----------------------------------------------------------------------
     std::vector<Ext> xi;
     if (total_interactions > 0) {
-        const size_t n_leaves = size_t(1) << L;
+        // the padding (0, alpha) behind the last interaction block is never materialised: the GKR prover
+        // takes the stored prefix and the tail constant (gkr.cu)
+        size_t used = 0;
+        for (const LayoutCol& lc : ilayout.cols) used = std::max<size_t>(used, lc.row_idx + (size_t(1) << lc.log_height));
+        const size_t n_leaves = std::min(size_t(1) << L, (used + 3) & ~size_t(3));
         uint32_t* leaves = nullptr;
         SWIRL_CUDA(dev_alloc(ctx, &leaves, n_leaves * 8));
         to_free.push_back(leaves);
-        // only the padding behind the last interaction block needs the (0, alpha) fill
-        size_t used = 0;
-        for (const LayoutCol& lc : ilayout.cols) used = std::max<size_t>(used, lc.row_idx + (size_t(1) << lc.log_height));
         if (used < n_leaves) {
             leaves_fill_kernel<<<(unsigned)((n_leaves - used + 255) / 256), 256, 0, ctx->stream>>>(leaves + used * 8, n_leaves - used, alpha);
             SWIRL_LAUNCH_CHECK(ctx);
@@ -812,7 +813,8 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         }
         uint32_t frac_sum[8];
         std::vector<uint32_t> xi_w((size_t)L * 4);
-        SWIRL_TRY(swirl_gkr_fractional_sumcheck(ctx, ts, leaves, L, 1, frac_sum, sec_claims, sec_gkr_polys, xi_w.data()));
+        SWIRL_TRY(swirl_gkr_fractional_sumcheck_padded(ctx, ts, leaves, n_leaves, alpha.c, L, 1, frac_sum, sec_claims, sec_gkr_polys,
+                                                       xi_w.data()));
         memcpy(sec_q0, frac_sum + 4, 16);
         for (int i = 0; i < L; i++) xi.push_back(hp::from_words(&xi_w[4 * i]));
     } else {
@@ -975,7 +977,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     }
     std::vector<uint32_t> h_r0(r0_off[n_airs] + 4);
     SWIRL_CUDA(cudaMemcpyAsync(h_r0.data(), d_r0, r0_off[n_airs] * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     // host: per-trace s'_0 polynomials (cpu.rs:324-424)
     const size_t sp_0_deg = (size_t)D * (N - 1), s_0_deg = (size_t)(D + 1) * (N - 1);
     std::vector<std::vector<Ext>> sp0(3 * n_airs);  // [2t] numer, [2t+1] denom, [2n + t] zerocheck
@@ -1212,7 +1214,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
 #undef BC_MLE
             SWIRL_LAUNCH_CHECK(ctx);
         }
-        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         // sp_evals[2t] numer, [2t+1] denom, [2n+t] zerocheck: D values (head) or 1 value (tail)
         std::vector<std::vector<Ext>> sp(3 * n_airs);
         for (size_t t = 0; t < n_airs; t++) {
@@ -1328,7 +1330,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         rows[t].resize((size_t)s.total_cols * 4);
         SWIRL_CUDA(cudaMemcpyAsync(rows[t].data(), s.ef[s.cur], rows[t].size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     std::vector<std::vector<std::vector<Ext>>> openings(n_airs);
     uint32_t* po = sec_open;
     for (size_t t = 0; t < n_airs; t++) {

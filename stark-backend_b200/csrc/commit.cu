@@ -133,7 +133,7 @@ static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swi
     SWIRL_TRY(merkle_commit(ctx, pcs->codeword, N, W, params->k_whir, pcs->layers));
     SWIRL_CUDA(cudaMemcpyAsync(h_root, pcs->layers + (2 * pcs->query_stride - 2) * 8, 32, cudaMemcpyDeviceToHost,
                                ctx->stream));
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     return 0;
 }
 
@@ -212,7 +212,7 @@ static int commit_host_pipelined(swirl_ctx* ctx, const swirl_pcs_params* params,
     }
     if (rc == 0) {
         SWIRL_CUDA(cudaMemcpyAsync(h_root, pcs->layers + (2 * pcs->query_stride - 2) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     }
     dev_free(ctx, state);
     cudaEventDestroy(ready);

@@ -6,11 +6,14 @@
 // cuda-common/include/launcher.cuh:43-55 (CHECK_KERNEL).  We use the driver's stream-ordered pool
 // (cudaMallocAsync with an unbounded release threshold) instead of the reference's VPMM pool.
 #pragma once
+#include <chrono>
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/swirl_b200.h"
@@ -38,6 +41,10 @@ struct swirl_ctx {
         cudaEvent_t a, b;
     };
     std::vector<TimedSpan> spans;
+    // Arena of large device blocks (>= ARENA_MIN bytes), see dev_alloc below.
+    std::multimap<size_t, void*> arena_free;        // size -> idle block
+    std::unordered_map<void*, size_t> arena_live;   // block handed out -> size
+    size_t arena_bytes = 0;                         // idle + live
 };
 
 // kernel families for swirl_ctx_timing_read
@@ -78,14 +85,39 @@ constexpr int TW_HI_BITS = 13;
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
-// stream-ordered allocation helpers
+// SWIRL_STALL_DEBUG=<ms>: host calls (stream-ordered allocations, stream synchronisations) that take longer
+// than <ms> of wall time are reported on stderr with their call site (box / allocator stall hunting).
+double stall_debug_ms();
+void stall_report(const char* what, const char* file, int line, double ms, size_t bytes);
+inline cudaError_t stream_sync(swirl_ctx* ctx, const char* file, int line) {
+    const double lim = stall_debug_ms();
+    if (lim <= 0) return cudaStreamSynchronize(ctx->stream);
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > lim) stall_report("cudaStreamSynchronize", file, line, ms, 0);
+    return e;
+}
+
+// Scratch allocation.  Small blocks come from the driver's stream-ordered pool.  Blocks of ARENA_MIN bytes
+// and more are kept by the context and handed out again by size (exact size first, then the smallest idle
+// block within +25 %): a proof allocates the same multi-GiB tables in the same order every time, and carving
+// them out of the driver pool again and again was measured to stall for 0.1-0.9 s at random when the pool
+// has to re-map physical memory behind a new virtual range (tools: SWIRL_STALL_DEBUG).  Reuse is ordered by
+// ctx->stream like cudaFreeAsync was.  swirl_ctx_trim / an out-of-memory allocation return idle blocks to
+// the driver.
+constexpr size_t ARENA_MIN = size_t(1) << 20;
+cudaError_t arena_alloc(swirl_ctx* ctx, void** p, size_t bytes);
+void arena_free_block(swirl_ctx* ctx, void* p);
+void arena_trim(swirl_ctx* ctx);
+
 template <class T>
 inline cudaError_t dev_alloc(swirl_ctx* ctx, T** p, size_t count) {
-    return cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
+    return arena_alloc(ctx, (void**)p, count * sizeof(T));
 }
 template <class T>
 inline void dev_free(swirl_ctx* ctx, T* p) {
-    if (p) cudaFreeAsync((void*)p, ctx->stream);
+    if (p) arena_free_block(ctx, (void*)p);
 }
 
 inline int ilog2(size_t n) {

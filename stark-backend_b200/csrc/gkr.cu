@@ -5,19 +5,30 @@
 //   crates/cuda-backend/src/logup_zerocheck/fractional.rs:649-       fractional_sumcheck_gpu
 // Semantics = crates/stark-backend/src/prover/logup_zerocheck/fractional_sumcheck_gkr.rs:60-213.
 //
-// Design: the tree is stored as in the reference CPU prover (node i has children 2i, 2i+1, layer k
-// at [2^k, 2^(k+1)), Frac = {p, q} 32 bytes), leaves stay in the caller's buffer.  Layer j's
-// sumcheck runs on 5 columns (eq, p0, q0, p1, q1).  Round 0 and round 1 read the tree layer
-// directly (4 consecutive Fracs per hypercube point y = one 128-byte line) together with the eq
-// table; from round 1 on every kernel FOLDS its input with the previous challenge on the fly,
-// writes the folded table (half the size, structure-of-arrays) and accumulates the next round
-// polynomial in the same pass, so each table is read once and written once per round.
-// s(1), s(2), s(3) leave the device through one grid-wide reduction per round (ext.cuh) into mapped
-// pinned memory; the host transcript (transcript.hpp) turns them into the next challenge.
+// Design: the tree is stored as in the reference CPU prover (node i has children 2i, 2i+1, Frac =
+// {p, q} 32 bytes), leaves stay in the caller's buffer.  Three things keep the work proportional to
+// the REAL interactions and the traffic close to one read per table per round:
+//  * constant tail: the interaction layout pads the leaf layer with (0, alpha) up to the next power
+//    of two (between 0 and 50 % of it).  Every node above a constant run is again a constant
+//    (0, c_k), c_k = c_{k+1}^2, so each layer stores only its first S_k nodes and the sumchecks run
+//    over the stored rows; the tail's contribution lambda * c^2 * sum_{y >= y_tail} eq(xi, y) has a
+//    closed form in the O(log) prefix sums of eq and is added on the host (field arithmetic is
+//    exact, so the round polynomials are the same elements the full-table sum would give).
+//  * eq is never materialised: eq(xi,(x_0..x_{s-1} = r, X, y)) = e_bound * eq1(xi_s, X) * E_s[y],
+//    the first two factors leave the sum (host), E_s[y] = A_s[y_lo] * B_s[y_hi] comes from suffix
+//    tables of <= 2^14 entries that stay in L2 (eq_suffix_kernel).
+//  * layer j's sumcheck runs on 4 columns (p0, q0, p1, q1).  Round 0 and round 1 read the tree layer
+//    directly (4 consecutive Fracs per pair = one 128-byte line); from round 1 on every kernel FOLDS
+//    its input with the previous challenge on the fly, writes the folded table (half the size,
+//    structure-of-arrays) and accumulates the next round polynomial in the same pass.
+// t(1), t(2), t(3) (the eq-free inner sums) leave the device through one grid-wide reduction per
+// round (ext.cuh) into mapped pinned memory; the host transcript (transcript.hpp) turns them into
+// s(1), s(2), s(3) and the next challenge.
 #include <cstring>
 #include <vector>
 
 #include "ext.cuh"
+#include "hostpoly.hpp"
 #include "kernels.cuh"
 #include "transcript.hpp"
 
@@ -29,15 +40,18 @@ using bb::ext_sub;
 
 constexpr int GKR_BLOCK = 256;
 
-struct Frac4 {  // the four fractions tree[4y .. 4y+3] of one y, as rows x = 2y (lo) and 2y+1 (hi)
-    Ext p0_lo, q0_lo, p1_lo, q1_lo, p0_hi, q0_hi, p1_hi, q1_hi;
-};
-
-// parent[i] = child[2i] + child[2i+1]  (projective fraction addition)
+// parent[i] = child[2i] + child[2i+1] (projective fraction addition) for the stored prefix of a layer;
+// parents whose children lie in the constant tail are the constant (0, c_parent).
 __global__ void __launch_bounds__(GKR_BLOCK)
-frac_tree_layer_kernel(const uint32_t* __restrict__ child, uint32_t* __restrict__ parent, size_t n_parent) {
+frac_tree_layer_kernel(const uint32_t* __restrict__ child, uint32_t* __restrict__ parent, size_t n_parent,
+                       size_t n_child, Ext c_parent) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_parent) return;
+    if (2 * i >= n_child) {
+        st_ext(parent + i * 8, bb::ext_zero());
+        st_ext(parent + i * 8 + 4, c_parent);
+        return;
+    }
     const uint32_t* c = child + i * 16;
     const Ext pl = ldg_ext(c), ql = ldg_ext(c + 4), pr = ldg_ext(c + 8), qr = ldg_ext(c + 12);
     st_ext(parent + i * 8, ext_add(ext_mul(pl, qr), ext_mul(ql, pr)));
@@ -48,77 +62,77 @@ struct XiArgs {
     uint32_t x[28][4];
 };
 
-// out[i] = prod_b (bit b of i ? x_b : 1 - x_b), i < 2^n  (poly.rs:133-149 evals_eq_hypercube).
-// Two-level: `lo_bits` low variables come from a table built by the same kernel in a first launch.
-__global__ void __launch_bounds__(GKR_BLOCK)
-eq_table_kernel(XiArgs xi, int first_var, int n_vars, const uint32_t* __restrict__ lo_table, int lo_bits,
-                uint32_t* __restrict__ out, size_t n_out) {
+// Suffix eq tables of the variables [first_var, first_var + n_vars): table t (blockIdx.y) covers the
+// variables [first_var + t, first_var + n_vars), has 2^(n_vars - t) entries
+// out_t[i] = prod_b (bit b of i ? x_{first_var+t+b} : 1 - x_{first_var+t+b})   (poly.rs:133-149)
+// and starts at entry 2^(n_vars+1) - 2^(n_vars-t+1); table n_vars is the single entry 1.
+__global__ void __launch_bounds__(GKR_BLOCK) eq_suffix_kernel(XiArgs xi, int first_var, int n_vars, uint32_t* __restrict__ out) {
+    const int t = blockIdx.y;
+    const size_t size = size_t(1) << (n_vars - t);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
-    Ext acc = lo_table ? ldg_ext(lo_table + (i & ((size_t(1) << lo_bits) - 1)) * 4) : bb::ext_one();
-    const size_t hi = lo_table ? i >> lo_bits : i;
-    for (int b = 0; b < n_vars; b++) {
-        const Ext x = Ext{{xi.x[first_var + b][0], xi.x[first_var + b][1], xi.x[first_var + b][2], xi.x[first_var + b][3]}};
-        acc = ext_mul(acc, ((hi >> b) & 1) ? x : ext_one_minus(x));
+    if (i >= size) return;
+    Ext acc = bb::ext_one();
+    for (int b = 0; b < n_vars - t; b++) {
+        const uint32_t* xw = xi.x[first_var + t + b];
+        const Ext x = Ext{{xw[0], xw[1], xw[2], xw[3]}};
+        acc = ext_mul(acc, ((i >> b) & 1) ? x : ext_one_minus(x));
     }
-    st_ext(out + i * 4, acc);
-}
-
-// out[i] = A[i mod 2^lo_bits] * B[i >> lo_bits]: eq table of (x_lo, x_hi) from the two half tables
-__global__ void __launch_bounds__(GKR_BLOCK)
-eq_combine_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ B, int lo_bits,
-                  uint32_t* __restrict__ out, size_t n_out) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
-    st_ext(out + i * 4, ext_mul(ldg_ext(A + (i & ((size_t(1) << lo_bits) - 1)) * 4), ldg_ext(B + (i >> lo_bits) * 4)));
+    st_ext(out + ((size_t(2) << n_vars) - 2 * size + i) * 4, acc);
 }
 
 struct RoundArgs {
-    const uint32_t* tree;  // FROM_TREE: layer segment, 2 * height Fracs
-    const uint32_t* eq;    // FROM_TREE: eq table, `height` EF
-    const uint32_t* in;    // !FROM_TREE: 5 columns (eq, p0, q0, p1, q1) of `height` EF, column stride in_stride
+    const uint32_t* tree;  // FROM_TREE: layer segment; row x = Fracs 2x, 2x+1
+    const uint32_t* in;    // !FROM_TREE: 4 columns (p0, q0, p1, q1) of EF, column stride in_stride
     size_t in_stride;
-    uint32_t* out;  // FOLD: 5 columns of height/2 EF, column stride out_stride
+    size_t rows_in;  // stored rows of the input table; rows beyond are the constant (0, c, 0, c)
+    uint32_t* out;   // FOLD: 4 columns, column stride out_stride
     size_t out_stride;
-    size_t height;  // rows of the input table
+    size_t ny;          // pairs (FOLD: quads) to process
+    const uint32_t* A;  // eq suffix table of the low variables (a_bits of them), or unused when a_bits == 0
+    const uint32_t* B;  // eq suffix table of the high variables
+    int a_bits;
+    uint32_t c[4];  // the constant q of the tail rows
     uint32_t r[4];  // FOLD: previous challenge
     uint32_t lambda[4];
     uint32_t* partials;
     unsigned int* ticket;
-    uint32_t* result;  // 12 words: s(1), s(2), s(3)
+    uint32_t* result;  // 12 words: t(1), t(2), t(3)
 };
 
 template <bool FROM_TREE>
-__device__ __forceinline__ void load_row(const RoundArgs& a, size_t x, Ext (&row)[5]) {
+__device__ __forceinline__ void load_row(const RoundArgs& a, size_t x, const Ext& c, Ext (&row)[4]) {
+    if (x >= a.rows_in) {
+        row[0] = bb::ext_zero();
+        row[1] = c;
+        row[2] = bb::ext_zero();
+        row[3] = c;
+        return;
+    }
     if (FROM_TREE) {
-        row[0] = ldg_ext(a.eq + x * 4);
         const uint32_t* t = a.tree + x * 16;
-        row[1] = ldg_ext(t);
-        row[2] = ldg_ext(t + 4);
-        row[3] = ldg_ext(t + 8);
-        row[4] = ldg_ext(t + 12);
+#pragma unroll
+        for (int k = 0; k < 4; k++) row[k] = ldg_ext(t + 4 * k);
     } else {
 #pragma unroll
-        for (int c = 0; c < 5; c++) row[c] = ldg_ext(a.in + (c * a.in_stride + x) * 4);
+        for (int k = 0; k < 4; k++) row[k] = ldg_ext(a.in + (k * a.in_stride + x) * 4);
     }
 }
 
-// contribution of the pair (lo, hi) = rows (2y, 2y+1) to s(1), s(2), s(3)
-__device__ __forceinline__ void accumulate(const Ext (&lo)[5], const Ext (&hi)[5], const Ext& lambda, Ext (&s)[3]) {
-    Ext d[5], cur[5];
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-        d[c] = ext_sub(hi[c], lo[c]);
-        cur[c] = hi[c];  // X = 1
-    }
+// contribution of the pair (lo, hi) = rows (2y, 2y+1) to t(1), t(2), t(3):
+// E * (p0 q1 + p1 q0 + lambda q0 q1) = E * (p0 q1 + q0 (p1 + lambda q1)), every factor linear in X
+__device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ext (&hi)[4], const Ext& lambda, const Ext& E, Ext (&s)[3]) {
+    const Ext w_lo = ext_add(lo[2], ext_mul(lambda, lo[3])), w_hi = ext_add(hi[2], ext_mul(lambda, hi[3]));
+    const Ext d0 = ext_sub(hi[0], lo[0]), d1 = ext_sub(hi[1], lo[1]), d3 = ext_sub(hi[3], lo[3]), dw = ext_sub(w_hi, w_lo);
+    Ext p0 = hi[0], q0 = hi[1], q1 = hi[3], w = w_hi;  // X = 1
 #pragma unroll
     for (int X = 0; X < 3; X++) {
-        // eq * (p0 q1 + p1 q0 + lambda q0 q1) = eq * (p0 q1 + q0 (p1 + lambda q1))
-        const Ext inner = ext_add(ext_mul(cur[1], cur[4]), ext_mul(cur[2], ext_add(cur[3], ext_mul(lambda, cur[4]))));
-        s[X] = ext_add(s[X], ext_mul(cur[0], inner));
+        const Ext inner = ext_add(ext_mul(p0, q1), ext_mul(q0, w));
+        s[X] = ext_add(s[X], ext_mul(E, inner));
         if (X < 2) {
-#pragma unroll
-            for (int c = 0; c < 5; c++) cur[c] = ext_add(cur[c], d[c]);
+            p0 = ext_add(p0, d0);
+            q0 = ext_add(q0, d1);
+            q1 = ext_add(q1, d3);
+            w = ext_add(w, dw);
         }
     }
 }
@@ -130,30 +144,33 @@ template <bool FROM_TREE, bool FOLD>
 __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
     const Ext lambda = Ext{{a.lambda[0], a.lambda[1], a.lambda[2], a.lambda[3]}};
     const Ext r = Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
+    const Ext c = Ext{{a.c[0], a.c[1], a.c[2], a.c[3]}};
     Ext s[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
-    const size_t ny = FOLD ? a.height >> 2 : a.height >> 1;
-    for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < ny; y += (size_t)gridDim.x * blockDim.x) {
-        Ext lo[5], hi[5];
+    const size_t a_mask = (size_t(1) << a.a_bits) - 1;
+    for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)gridDim.x * blockDim.x) {
+        Ext lo[4], hi[4];
         if (FOLD) {
-            Ext a0[5], a1[5];
-            load_row<FROM_TREE>(a, 4 * y, a0);
-            load_row<FROM_TREE>(a, 4 * y + 1, a1);
+            Ext a0[4], a1[4];
+            load_row<FROM_TREE>(a, 4 * y, c, a0);
+            load_row<FROM_TREE>(a, 4 * y + 1, c, a1);
 #pragma unroll
-            for (int c = 0; c < 5; c++) lo[c] = ext_lerp(a0[c], a1[c], r);
-            load_row<FROM_TREE>(a, 4 * y + 2, a0);
-            load_row<FROM_TREE>(a, 4 * y + 3, a1);
+            for (int k = 0; k < 4; k++) lo[k] = ext_lerp(a0[k], a1[k], r);
+            load_row<FROM_TREE>(a, 4 * y + 2, c, a0);
+            load_row<FROM_TREE>(a, 4 * y + 3, c, a1);
 #pragma unroll
-            for (int c = 0; c < 5; c++) hi[c] = ext_lerp(a0[c], a1[c], r);
+            for (int k = 0; k < 4; k++) hi[k] = ext_lerp(a0[k], a1[k], r);
 #pragma unroll
-            for (int c = 0; c < 5; c++) {
-                st_ext(a.out + (c * a.out_stride + 2 * y) * 4, lo[c]);
-                st_ext(a.out + (c * a.out_stride + 2 * y + 1) * 4, hi[c]);
+            for (int k = 0; k < 4; k++) {
+                st_ext(a.out + (k * a.out_stride + 2 * y) * 4, lo[k]);
+                st_ext(a.out + (k * a.out_stride + 2 * y + 1) * 4, hi[k]);
             }
         } else {
-            load_row<FROM_TREE>(a, 2 * y, lo);
-            load_row<FROM_TREE>(a, 2 * y + 1, hi);
+            load_row<FROM_TREE>(a, 2 * y, c, lo);
+            load_row<FROM_TREE>(a, 2 * y + 1, c, hi);
         }
-        accumulate(lo, hi, lambda, s);
+        Ext E = ldg_ext(a.B + (y >> a.a_bits) * 4);
+        if (a.a_bits) E = ext_mul(E, ldg_ext(a.A + (y & a_mask) * 4));
+        accumulate(lo, hi, lambda, E, s);
     }
     uint32_t v[12];
 #pragma unroll
@@ -168,15 +185,16 @@ template <bool FROM_TREE>
 __global__ void gkr_claims_kernel(RoundArgs a) {
     if (threadIdx.x >= 4) return;
     const Ext r = Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
-    Ext lo[5], hi[5];
-    load_row<FROM_TREE>(a, 0, lo);
-    load_row<FROM_TREE>(a, 1, hi);
-    Ext sel_lo = lo[1], sel_hi = hi[1];
+    const Ext c = Ext{{a.c[0], a.c[1], a.c[2], a.c[3]}};
+    Ext lo[4], hi[4];
+    load_row<FROM_TREE>(a, 0, c, lo);
+    load_row<FROM_TREE>(a, 1, c, hi);
+    Ext sel_lo = lo[0], sel_hi = hi[0];
 #pragma unroll
-    for (int c = 2; c < 5; c++)
-        if ((int)threadIdx.x == c - 1) {
-            sel_lo = lo[c];
-            sel_hi = hi[c];
+    for (int k = 1; k < 4; k++)
+        if ((int)threadIdx.x == k) {
+            sel_lo = lo[k];
+            sel_hi = hi[k];
         }
     const Ext v = ext_lerp(sel_lo, sel_hi, r);
 #pragma unroll
@@ -190,40 +208,71 @@ static int round_grid(const swirl_ctx* ctx, size_t work_items) {
     return blocks ? (int)blocks : 1;
 }
 
+// sum_{y < t} prod_{i < count} eq1(xi[first + i], bit i of y), t <= 2^count
+static Ext eq_prefix_sum(const std::vector<Ext>& xi, int first, int count, size_t t) {
+    if (t >= (size_t(1) << count)) return bb::ext_one();
+    Ext acc = bb::ext_zero(), pre = bb::ext_one();
+    for (int i = count - 1; i >= 0; i--) {
+        const Ext& x = xi[first + i];
+        if ((t >> i) & 1) {
+            acc = ext_add(acc, ext_mul(pre, ext_one_minus(x)));
+            pre = ext_mul(pre, x);
+        } else {
+            pre = ext_mul(pre, ext_one_minus(x));
+        }
+    }
+    return acc;
+}
+
 static Ext ext_from_words(const uint32_t* w) { return Ext{{w[0], w[1], w[2], w[3]}}; }
 
 }  // namespace swirl
 
 using namespace swirl;
 
-extern "C" int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves, int log_n,
-                                             int assert_zero, uint32_t h_frac_sum[8], uint32_t* h_claims,
-                                             uint32_t* h_polys, uint32_t* h_xi) {
+static size_t round_up4(size_t x) { return (x + 3) & ~size_t(3); }
+
+extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves,
+                                                    uint64_t n_stored, const uint32_t pad_q[4], int log_n, int assert_zero,
+                                                    uint32_t h_frac_sum[8], uint32_t* h_claims, uint32_t* h_polys,
+                                                    uint32_t* h_xi) {
     SWIRL_REQUIRE(ctx && ts && d_leaves && h_frac_sum && h_claims && h_xi, "null argument");
     SWIRL_REQUIRE(log_n >= 1 && log_n <= 27, "log_n must be in [1, 27]");
     SWIRL_REQUIRE(((uintptr_t)d_leaves & 15) == 0, "leaves must be 16-byte aligned");
+    const int n = log_n;
+    const size_t N = size_t(1) << n;
+    SWIRL_REQUIRE(n_stored >= 1 && n_stored <= N && (n_stored == N || (n_stored % 4 == 0 && pad_q)),
+                  "n_stored must be 2^log_n or a multiple of 4 with a padding denominator");
     SWIRL_CUDA(cudaSetDevice(ctx->device));
     Transcript tr(ts);
     RoundScratch* rs;
     SWIRL_TRY(round_scratch_get(ctx, &rs));
-    const int n = log_n;
-    const size_t N = size_t(1) << n;
 
-    // ---- tree: layers 0..n-1 in `tree` (node i at tree + i*8 words), layer n = the leaves ------
-    uint32_t* tree = nullptr;
-    SWIRL_CUDA(dev_alloc(ctx, &tree, N * 8));
-    auto layer_ptr = [&](int k) -> const uint32_t* { return k == n ? d_leaves : tree + (size_t(1) << k) * 8; };
+    // ---- stored prefix S[k] and tail constant c[k] of every layer (layer n = the leaves) ----------
+    std::vector<size_t> S(n + 1), off(n + 1, 0);
+    std::vector<Ext> cst(n + 1, bb::ext_one());
+    S[n] = n_stored;
+    if (pad_q) cst[n] = ext_from_words(pad_q);
+    size_t tree_nodes = 0;
     for (int k = n - 1; k >= 0; k--) {
-        const size_t np = size_t(1) << k;
-        frac_tree_layer_kernel<<<(unsigned)((np + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(
-            layer_ptr(k + 1), tree + np * 8, np);
+        S[k] = std::min(size_t(1) << k, round_up4((S[k + 1] + 1) / 2));
+        cst[k] = ext_mul(cst[k + 1], cst[k + 1]);
+        off[k] = tree_nodes;
+        tree_nodes += round_up4(S[k]);  // keeps every layer segment 128-byte aligned
+    }
+    uint32_t* tree = nullptr;
+    SWIRL_CUDA(dev_alloc(ctx, &tree, tree_nodes * 8));
+    auto layer_ptr = [&](int k) -> const uint32_t* { return k == n ? d_leaves : tree + off[k] * 8; };
+    for (int k = n - 1; k >= 0; k--) {
+        frac_tree_layer_kernel<<<(unsigned)((S[k] + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(
+            layer_ptr(k + 1), tree + off[k] * 8, S[k], S[k + 1], cst[k]);
         SWIRL_LAUNCH_CHECK(ctx);
     }
-    // root + layer 1 (nodes 1, 2, 3) -> host
+    // root (layer 0) + layer 1 -> host
     uint32_t top[24];
-    SWIRL_CUDA(cudaMemcpyAsync(top, tree + 8, n >= 2 ? 96 : 32, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n == 1) SWIRL_CUDA(cudaMemcpyAsync(top + 8, d_leaves, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+    SWIRL_CUDA(cudaMemcpyAsync(top, layer_ptr(0), 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SWIRL_CUDA(cudaMemcpyAsync(top + 8, layer_ptr(1), 64, cudaMemcpyDeviceToHost, ctx->stream));
+    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     memcpy(h_frac_sum, top, 32);
     int rc = 0;
     const Ext root_p = ext_from_words(top), root_q = ext_from_words(top + 4);
@@ -237,97 +286,125 @@ extern "C" int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* t
         tr.observe_ext(root_p);
     }
     tr.observe_ext(root_q);
-    // layer 1 claims: tree[2].p, tree[2].q, tree[3].p, tree[3].q
+    // layer 1 claims: node 0 and node 1 of layer 1
     memcpy(h_claims, top + 8, 64);
     for (int i = 0; i < 4; i++) tr.observe_ext(ext_from_words(top + 8 + 4 * i));
     std::vector<Ext> xi_prev{tr.sample_ext()};
 
-    // ---- working buffers: eq table (<= N/2 EF), two ping-pong SoA tables (5 cols x <= N/4 EF) ---
-    uint32_t *eq = nullptr, *eq_lo = nullptr, *tab[2] = {nullptr, nullptr};
-    const size_t max_h = N >> 1;  // largest layer table height (layer n-1)
-    const size_t tab_stride = max_h >= 2 ? max_h >> 1 : 1;
+    // ---- working buffers: eq suffix tables, two ping-pong SoA tables (4 columns) -----------------
+    uint32_t *eqA = nullptr, *eqB = nullptr, *tab[2] = {nullptr, nullptr};
+    size_t tab_stride[2] = {1, 1};
     if (n >= 2) {
-        SWIRL_CUDA(dev_alloc(ctx, &eq, max_h * 4));
-        SWIRL_CUDA(dev_alloc(ctx, &eq_lo, (size_t(8) << 14)));  // two half tables of <= 2^14 EF
-        SWIRL_CUDA(dev_alloc(ctx, &tab[0], 5 * tab_stride * 4));
-        SWIRL_CUDA(dev_alloc(ctx, &tab[1], 5 * (tab_stride >> 1 ? tab_stride >> 1 : 1) * 4));
+        SWIRL_CUDA(dev_alloc(ctx, &eqA, (size_t(8) << 14)));  // suffix tables of <= 13 variables: < 2^14 EF
+        SWIRL_CUDA(dev_alloc(ctx, &eqB, (size_t(8) << 14)));
+        const size_t rows_max = (S[n] + 1) / 2;                // stored rows of the largest layer table
+        tab_stride[0] = 2 * ((rows_max + 3) / 4);              // rows written by the first fold
+        tab_stride[1] = 2 * ((tab_stride[0] + 3) / 4);
+        SWIRL_CUDA(dev_alloc(ctx, &tab[0], 4 * tab_stride[0] * 4));
+        SWIRL_CUDA(dev_alloc(ctx, &tab[1], 4 * tab_stride[1] * 4));
     }
+    const Ext one = bb::ext_one();
+    const Ext X123[3] = {bb::ext_from(bb::mont(1)), bb::ext_from(bb::mont(2)), bb::ext_from(bb::mont(3))};
     size_t poly_off = 0;
     for (int round = 1; round < n && rc == 0; round++) {
-        const size_t H = size_t(1) << round;
         const Ext lambda = tr.sample_ext();
-        // eq table of xi_prev (round variables)
+        // eq(xi_prev, x) = e_bound * eq1(xi_s, X) * A_s[y_lo] * B_s[y_hi]: variable 0 never enters a table;
+        // low group = variables [1, v_split), high group = [v_split, round)
+        const int v_split = round <= 13 ? round : (round + 1) / 2 + 1;
+        const int nA = v_split - 1, nB = round - v_split;  // both <= 13
         XiArgs xa;
         for (int b = 0; b < round; b++)
             for (int k = 0; k < 4; k++) xa.x[b][k] = xi_prev[b].c[k];
-        if (round <= 12) {
-            eq_table_kernel<<<(unsigned)((H + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(xa, 0, round, nullptr, 0,
-                                                                                                      eq, H);
-        } else {
-            const int lo_bits = round / 2, hi_bits = round - lo_bits;  // both <= 14
-            uint32_t* eq_hi = eq_lo + (size_t(4) << 14);
-            eq_table_kernel<<<(unsigned)(((size_t(1) << lo_bits) + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(
-                xa, 0, lo_bits, nullptr, 0, eq_lo, size_t(1) << lo_bits);
-            eq_table_kernel<<<(unsigned)(((size_t(1) << hi_bits) + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(
-                xa, lo_bits, hi_bits, nullptr, 0, eq_hi, size_t(1) << hi_bits);
-            ctx->launches += 2;
-            eq_combine_kernel<<<(unsigned)((H + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(eq_lo, eq_hi, lo_bits, eq, H);
+        {
+            const dim3 gA((unsigned)(((size_t(1) << nA) + GKR_BLOCK - 1) / GKR_BLOCK), nA + 1);
+            eq_suffix_kernel<<<gA, GKR_BLOCK, 0, ctx->stream>>>(xa, 1, nA, eqA);
+            SWIRL_LAUNCH_CHECK(ctx);
+            const dim3 gB((unsigned)(((size_t(1) << nB) + GKR_BLOCK - 1) / GKR_BLOCK), nB + 1);
+            eq_suffix_kernel<<<gB, GKR_BLOCK, 0, ctx->stream>>>(xa, v_split, nB, eqB);
+            SWIRL_LAUNCH_CHECK(ctx);
         }
-        SWIRL_LAUNCH_CHECK(ctx);
+        auto suffix = [](const uint32_t* base, int n_vars, int t) { return base + ((size_t(2) << n_vars) - (size_t(2) << (n_vars - t))) * 4; };
 
         RoundArgs a{};
         a.tree = layer_ptr(round + 1);
-        a.eq = eq;
         a.partials = rs->d_partials;
         a.ticket = rs->d_ticket;
         a.result = rs->d_result;
         for (int k = 0; k < 4; k++) a.lambda[k] = lambda.c[k];
+        for (int k = 0; k < 4; k++) a.c[k] = cst[round + 1].c[k];
+        const Ext tail_unit = ext_mul(lambda, ext_mul(cst[round + 1], cst[round + 1]));  // inner() of a constant row
+        const size_t rows_tree = (S[round + 1] + 1) / 2;  // stored rows of this layer's table
         std::vector<Ext> rho;
-        size_t h = H;  // height of the table the next kernel reads
+        Ext e_bound = one;
+        size_t rows = rows_tree;  // stored rows of the table the next kernel reads
         int cur = 0;
         for (int sr = 0; sr < round; sr++) {
-            SwirlTimed timed(ctx, SWIRL_T_GKR);
-            if (sr == 0) {
-                a.height = H;
-                gkr_round_kernel<true, false><<<round_grid(ctx, H >> 1), GKR_BLOCK, 0, ctx->stream>>>(a);
-            } else if (sr == 1) {
-                a.height = H;
-                a.out = tab[0];
-                a.out_stride = tab_stride;
-                gkr_round_kernel<true, true><<<round_grid(ctx, H >> 2), GKR_BLOCK, 0, ctx->stream>>>(a);
-                h = H >> 1;
-                cur = 0;
+            // tables of the remaining variables [sr+1, round)
+            if (sr + 1 < v_split) {
+                a.a_bits = v_split - 1 - sr;
+                a.A = suffix(eqA, nA, sr);
+                a.B = suffix(eqB, nB, 0);
             } else {
-                a.in = tab[cur];
-                a.in_stride = cur == 0 ? tab_stride : (tab_stride >> 1 ? tab_stride >> 1 : 1);
-                a.height = h;
-                a.out = tab[cur ^ 1];
-                a.out_stride = cur == 0 ? (tab_stride >> 1 ? tab_stride >> 1 : 1) : tab_stride;
-                gkr_round_kernel<false, true><<<round_grid(ctx, h >> 2), GKR_BLOCK, 0, ctx->stream>>>(a);
-                h >>= 1;
-                cur ^= 1;
+                a.a_bits = 0;
+                a.A = nullptr;
+                a.B = suffix(eqB, nB, sr + 1 - v_split);
             }
-            SWIRL_LAUNCH_CHECK(ctx);
-            SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+            size_t y_tail;
+            {
+                SwirlTimed timed(ctx, SWIRL_T_GKR);
+                if (sr == 0) {
+                    a.rows_in = rows_tree;
+                    a.ny = y_tail = (rows_tree + 1) / 2;
+                    gkr_round_kernel<true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                } else if (sr == 1) {
+                    a.rows_in = rows_tree;
+                    a.ny = y_tail = (rows_tree + 3) / 4;
+                    a.out = tab[0];
+                    a.out_stride = tab_stride[0];
+                    gkr_round_kernel<true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                    rows = 2 * a.ny;
+                    cur = 0;
+                } else {
+                    a.in = tab[cur];
+                    a.in_stride = tab_stride[cur];
+                    a.rows_in = rows;
+                    a.ny = y_tail = (rows + 3) / 4;
+                    a.out = tab[cur ^ 1];
+                    a.out_stride = tab_stride[cur ^ 1];
+                    gkr_round_kernel<false, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                    rows = 2 * a.ny;
+                    cur ^= 1;
+                }
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+            // the constant tail's share of t(X): lambda c^2 * sum_{y >= y_tail} eq(xi[sr+1..round), y)
+            const int m = round - 1 - sr;
+            const Ext tail = ext_mul(tail_unit, ext_sub(one, eq_prefix_sum(xi_prev, sr + 1, m, y_tail)));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             uint32_t* out = h_polys + (poly_off + sr) * 12;
-            memcpy(out, rs->h_result, 48);
-            for (int X = 0; X < 3; X++) tr.observe_ext(ext_from_words(out + 4 * X));
+            for (int X = 0; X < 3; X++) {
+                const Ext t = ext_add(ext_from_words(rs->h_result + 4 * X), tail);
+                const Ext sX = ext_mul(ext_mul(e_bound, hp::eq1(xi_prev[sr], X123[X])), t);
+                memcpy(out + 4 * X, sX.c, 16);
+                tr.observe_ext(sX);
+            }
             const Ext r = tr.sample_ext();
             rho.push_back(r);
+            e_bound = ext_mul(e_bound, hp::eq1(xi_prev[sr], r));
             for (int k = 0; k < 4; k++) a.r[k] = r.c[k];
         }
         // claims: fold the remaining 2-row table with the last challenge
         if (round == 1) {
-            a.height = 2;
+            a.rows_in = rows_tree;
             gkr_claims_kernel<true><<<1, 32, 0, ctx->stream>>>(a);
         } else {
             a.in = tab[cur];
-            a.in_stride = cur == 0 ? tab_stride : (tab_stride >> 1 ? tab_stride >> 1 : 1);
-            a.height = 2;
+            a.in_stride = tab_stride[cur];
+            a.rows_in = rows;
             gkr_claims_kernel<false><<<1, 32, 0, ctx->stream>>>(a);
         }
         SWIRL_LAUNCH_CHECK(ctx);
-        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         uint32_t* cl = h_claims + (size_t)round * 16;
         memcpy(cl, rs->h_result, 64);
         for (int i = 0; i < 4; i++) tr.observe_ext(ext_from_words(cl + 4 * i));
@@ -338,9 +415,17 @@ extern "C" int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* t
     }
     for (int b = 0; b < n; b++) memcpy(h_xi + 4 * b, xi_prev[b].c, 16);
     dev_free(ctx, tree);
-    dev_free(ctx, eq);
-    dev_free(ctx, eq_lo);
+    dev_free(ctx, eqA);
+    dev_free(ctx, eqB);
     dev_free(ctx, tab[0]);
     dev_free(ctx, tab[1]);
     return rc;
+}
+
+extern "C" int swirl_gkr_fractional_sumcheck(swirl_ctx* ctx, swirl_transcript* ts, const uint32_t* d_leaves, int log_n,
+                                             int assert_zero, uint32_t h_frac_sum[8], uint32_t* h_claims,
+                                             uint32_t* h_polys, uint32_t* h_xi) {
+    SWIRL_REQUIRE(log_n >= 1 && log_n <= 27, "log_n must be in [1, 27]");
+    return swirl_gkr_fractional_sumcheck_padded(ctx, ts, d_leaves, uint64_t(1) << log_n, nullptr, log_n, assert_zero,
+                                                h_frac_sum, h_claims, h_polys, h_xi);
 }

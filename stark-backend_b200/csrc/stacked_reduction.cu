@@ -269,7 +269,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
     std::map<int, HtTab> tabs;
     std::vector<void*> to_free;
     auto cleanup = [&]() {
-        for (void* p : to_free) cudaFreeAsync(p, ctx->stream);
+        for (void* p : to_free) arena_free_block(ctx, p);
     };
     for (const View& v : views) {
         if (tabs.count(v.log_height)) continue;
@@ -336,7 +336,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
         }
         std::vector<uint32_t> h_res((win.size() - 1) * (size_t)nv);
         SWIRL_CUDA(cudaMemcpyAsync(h_res.data(), d_res, h_res.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         // host: extend the three vectors of every window to the cosets g D, g^2 D and apply the Z-only factors
         const uint32_t g = bb::to_mont(31);
         for (size_t wi = 0; wi + 1 < win.size(); wi++) {
@@ -497,7 +497,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
             sr_mle_exhausted_kernel<<<grid, SR_BLOCK, 0, ctx->stream>>>(d_ex, hex.size(), rs->d_partials, rs->d_ticket, rs->d_result + 8);
             SWIRL_LAUNCH_CHECK(ctx);
         }
-        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         if (!items.empty()) {
             s1 = ext_add(s1, hp::from_words(rs->h_result));
             s2 = ext_add(s2, hp::from_words(rs->h_result + 4));
@@ -550,7 +550,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
         const size_t W = pcs[ci]->layout.width;
         SWIRL_REQUIRE(qh == 1, "internal: q_evals not fully folded");
         SWIRL_CUDA(cudaMemcpyAsync(p_out, qe[qcur][ci], W * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         for (size_t j = 0; j < W; j++) tr.observe_ext(hp::from_words(p_out + 4 * j));
         p_out += 4 * W;
     }

@@ -337,7 +337,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                 n >>= 1;
             }
             SWIRL_LAUNCH_CHECK(ctx);
-            SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             uint32_t* s = sec_polys + sc_i * 8;
             memcpy(s, rs->h_result, 32);
             tr.observe_ext(Ext{{s[0], s[1], s[2], s[3]}});
@@ -372,7 +372,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             SWIRL_TRY(merkle_commit(ctx, g_codeword, N, 4, k, g_layers));
             uint32_t* root = sec_commits + 8 * wr;
             SWIRL_CUDA(cudaMemcpyAsync(root, g_layers + (2 * S - 2) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-            SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             tr.observe_digest(root);
             z0 = tr.sample_ext();
             Ext zp = z0;
@@ -383,7 +383,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             whir_ood_kernel<<<wh_grid(ctx, n), WH_BLOCK, 0, ctx->stream>>>(soa, n, n, z0p, m - k, rs->d_partials, rs->d_ticket,
                                                                           rs->d_result);
             SWIRL_LAUNCH_CHECK(ctx);
-            SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             uint32_t* y0 = sec_ood + 4 * wr;
             memcpy(y0, rs->h_result, 16);
             tr.observe_ext(Ext{{y0[0], y0[1], y0[2], y0[3]}});
@@ -391,7 +391,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             // final polynomial: coefficients to the host (interleave the 4 coordinate columns)
             std::vector<uint32_t> cols(n * 4);
             SWIRL_CUDA(cudaMemcpyAsync(cols.data(), soa, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-            SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             for (size_t i = 0; i < n; i++) {
                 for (int c = 0; c < 4; c++) sec_final[4 * i + c] = cols[c * n + i];
                 tr.observe_ext(Ext{{sec_final[4 * i], sec_final[4 * i + 1], sec_final[4 * i + 2], sec_final[4 * i + 3]}});
@@ -417,7 +417,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                     SWIRL_CUDA(cudaMemcpyAsync(sec_rows0[ci], d_open, row_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
                     SWIRL_CUDA(cudaMemcpyAsync(sec_proofs0[ci], d_open + row_words, path_words * 4, cudaMemcpyDeviceToHost,
                                                ctx->stream));
-                    SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+                    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
                 }
             } else {
                 SWIRL_REQUIRE(rs_codeword && rs_layers, "RsTreeNone");
@@ -426,7 +426,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                 SWIRL_TRY(merkle_query_proofs(ctx, rs_layers, rs_height >> k, d_idx, nq, d_open + row_words));
                 SWIRL_CUDA(cudaMemcpyAsync(sec_vals[wr], d_open, row_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
                 SWIRL_CUDA(cudaMemcpyAsync(sec_proofs[wr], d_open + row_words, path_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+                SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             }
         }
         dev_free(ctx, rs_codeword);
@@ -461,7 +461,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                 dev_free(ctx, tabs);
             }
             // h_gam / h_zs are reused next round: make sure the copies have been consumed
-            SWIRL_CUDA(cudaStreamSynchronize(ctx->stream));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         }
         m -= k;
         log_rs -= 1;

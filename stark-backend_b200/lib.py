@@ -74,6 +74,7 @@ PROTOTYPES = {
     "swirl_ctx_timing_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_u64)]),
     "swirl_malloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
     "swirl_free": (_i, [_vp, _vp]),
+    "swirl_ctx_trim": (_i, [_vp]),
     "swirl_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "swirl_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz]),
     "swirl_poseidon2_permute": (_i, [_vp, _vp, _sz]),
@@ -90,6 +91,7 @@ PROTOTYPES = {
     "swirl_transcript_check_witness": (_i, [C.POINTER(TranscriptC), _i, _u32, C.POINTER(_i)]),
     "swirl_transcript_grind": (_i, [_vp, C.POINTER(TranscriptC), _i, C.POINTER(_u32)]),
     "swirl_gkr_fractional_sumcheck": (_i, [_vp, C.POINTER(TranscriptC), _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "swirl_gkr_fractional_sumcheck_padded": (_i, [_vp, C.POINTER(TranscriptC), _vp, _u64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "swirl_commit": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_commit_host": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_pcs_free": (_i, [_vp, _vp]),

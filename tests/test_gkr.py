@@ -93,6 +93,26 @@ def test_gpu_gkr_matches_oracle(dev, oracle, log_n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("log_n,n_stored", [(2, 4), (3, 4), (5, 4), (5, 20), (8, 128), (8, 132), (10, 516), (13, 4100), (14, 8192),
+                                            (15, 16388), (15, 24580), (16, 40000), (16, 65536)])
+def test_gpu_gkr_padded_tail_matches_oracle_on_full_leaves(dev, oracle, log_n, n_stored):
+    """Only the first n_stored leaves are given; the rest is the constant (0, pad_q) the interaction layout pads
+    with.  The proof must be the one the oracle produces from all 2^log_n leaves."""
+    rng = np.random.default_rng(1000 + log_n + n_stored)
+    leaves = oracle.random_field(rng, (1 << log_n, 8))
+    pad_q = oracle.random_field(rng, 4)
+    leaves[n_stored:, :4] = 0
+    leaves[n_stored:, 4:] = pad_q
+    st = seeded_sponge(oracle, 11)
+    ts = sb.Transcript(st)
+    want = oracle.gkr_prove(st, leaves, log_n, False)
+    got = dev.gkr_fractional_sumcheck(ts, dev.h2d(np.ascontiguousarray(leaves[:n_stored])), log_n, False, n_stored=n_stored, pad_q=pad_q)
+    for k in ("frac_sum", "claims", "polys", "xi"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(ts.words(), st)
+
+
+@pytest.mark.gpu
 def test_gpu_gkr_not_assert_zero_and_error(dev, oracle):
     rng = np.random.default_rng(9)
     leaves = oracle.random_field(rng, (1 << 9, 8))
