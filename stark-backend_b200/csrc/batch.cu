@@ -48,6 +48,8 @@ struct Instr {
 };
 constexpr int BC_BLOCK = 256;
 constexpr int BC_MAX_SLOTS = 256;
+constexpr size_t BC_MAX_CHUNKS = 32;   // sub-programs per AIR (result scratch: 256 (AIR, chunk) pairs per round)
+constexpr size_t BC_CHUNK_ROOTS = 16;  // constraint / interaction roots per sub-program
 
 // ---- host: DAG -> program ---------------------------------------------------------------------------
 struct Program {
@@ -564,6 +566,15 @@ struct TraceState {
     AirLayout L;
     Program prog;
     Instr* d_code = nullptr;
+    // the same program split by roots into independent sub-programs (their accumulators add up): one thread
+    // walks ~16 roots instead of the whole DAG, which multiplies the loads in flight per SM and divides the
+    // serial latency of the short tail rounds
+    struct Chunk {
+        Instr* d_code = nullptr;
+        uint32_t n_instr = 0;
+        int n_slots = 0;
+    };
+    std::vector<Chunk> chunks;
     BasePart* d_parts = nullptr;
     uint32_t* d_sels = nullptr;
     uint32_t* d_weights = nullptr;
@@ -744,6 +755,21 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         }
         SWIRL_TRY(compile_program(a, s.L, roots, &s.prog));
         SWIRL_TRY(upload(s.prog.code.data(), s.prog.code.size() * sizeof(Instr), (void**)&s.d_code));
+        {
+            const size_t k_max = std::max<size_t>(1, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
+            const size_t K = std::max<size_t>(1, std::min(k_max, (roots.size() + BC_CHUNK_ROOTS - 1) / BC_CHUNK_ROOTS));
+            for (size_t k = 0; k < K; k++) {
+                const size_t r0 = roots.size() * k / K, r1 = roots.size() * (k + 1) / K;
+                if (r0 == r1 && !(K == 1)) continue;
+                Program pr;
+                SWIRL_TRY(compile_program(a, s.L, std::vector<Root>(roots.begin() + r0, roots.begin() + r1), &pr));
+                TraceState::Chunk c;
+                c.n_instr = (uint32_t)pr.code.size();
+                c.n_slots = pr.n_slots;
+                SWIRL_TRY(upload(pr.code.data(), std::max<size_t>(pr.code.size(), 1) * sizeof(Instr), (void**)&c.d_code));
+                s.chunks.push_back(c);
+            }
+        }
     }
 
     // ---- LogUp input layer + GKR -----------------------------------------------------------------------
@@ -906,13 +932,15 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         }
         SWIRL_TRY(upload(tab.data(), tab.size() * 4, (void**)&d_lde[d]));
     }
-    std::vector<size_t> r0_off(n_airs + 1, 0);
+    // round-0 results: one [cd * N][12] block per (AIR, chunk), summed per AIR on the host
+    std::vector<size_t> r0_off(n_airs + 1, 0), r0_chunk_off;
     for (size_t t = 0; t < n_airs; t++) r0_off[t + 1] = r0_off[t] + (size_t)airs[t].constraint_degree * N * 12;
-    uint32_t* d_r0 = nullptr;
-    SWIRL_CUDA(dev_alloc(ctx, &d_r0, r0_off[n_airs] + 4));
-    to_free.push_back(d_r0);
+    size_t r0_words = 0;
     int max_slots = 1;
-    for (size_t t = 0; t < n_airs; t++) max_slots = std::max(max_slots, T[t].prog.n_slots);
+    for (size_t t = 0; t < n_airs; t++)
+        for (const auto& c : T[t].chunks) max_slots = std::max(max_slots, c.n_slots);
+    uint32_t* d_r0 = nullptr;
+    std::vector<std::pair<size_t, size_t>> r0_desc_air;  // (air, offset of the desc's result block)
     {
         std::vector<R0Args> descs;
         std::vector<uint16_t> block_air;
@@ -921,33 +949,42 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             TraceState& s = T[t];
             const int cd = (int)airs[t].constraint_degree;
             if (cd == 0) continue;
-            R0Args ra{};
-            ra.code = s.d_code;
-            ra.n_instr = (uint32_t)s.prog.code.size();
-            ra.parts = s.d_parts;
-            ra.weights = s.d_weights;
-            ra.lde = d_lde[cd];
-            ra.eq_xi = s.d_eq_xi;
-            ra.l_skip = l_skip;
-            ra.n_lift = s.n_lift;
-            ra.P = (int)(cd * N);
-            const int G = std::max(1, BC_BLOCK / ra.P);
-            const size_t nx = size_t(1) << s.n_lift;
-            ra.x_per_block = G * 4;
-            ra.n_blocks = (uint32_t)((nx + ra.x_per_block - 1) / ra.x_per_block);
-            ra.first_block = (uint32_t)block_air.size();
-            ra.partials = (uint32_t*)(uintptr_t)part_words;  // offset for now, rebased below
-            ra.result = d_r0 + r0_off[t];
-            part_words += (size_t)ra.n_blocks * ra.P * 12;
-            SWIRL_REQUIRE(descs.size() < 65535, "too many AIRs");
-            block_air.insert(block_air.end(), ra.n_blocks, (uint16_t)descs.size());
-            descs.push_back(ra);
+            for (const auto& ch : s.chunks) {
+                R0Args ra{};
+                ra.code = ch.d_code;
+                ra.n_instr = ch.n_instr;
+                ra.parts = s.d_parts;
+                ra.weights = s.d_weights;
+                ra.lde = d_lde[cd];
+                ra.eq_xi = s.d_eq_xi;
+                ra.l_skip = l_skip;
+                ra.n_lift = s.n_lift;
+                ra.P = (int)(cd * N);
+                const int G = std::max(1, BC_BLOCK / ra.P);
+                const size_t nx = size_t(1) << s.n_lift;
+                ra.x_per_block = G * (s.chunks.size() > 1 ? 16 : 4);
+                ra.n_blocks = (uint32_t)((nx + ra.x_per_block - 1) / ra.x_per_block);
+                ra.first_block = (uint32_t)block_air.size();
+                ra.partials = (uint32_t*)(uintptr_t)part_words;  // offsets for now, rebased below
+                ra.result = (uint32_t*)(uintptr_t)r0_words;
+                r0_desc_air.emplace_back(t, r0_words);
+                r0_words += (size_t)ra.P * 12;
+                part_words += (size_t)ra.n_blocks * ra.P * 12;
+                SWIRL_REQUIRE(descs.size() < 65535, "too many AIRs");
+                block_air.insert(block_air.end(), ra.n_blocks, (uint16_t)descs.size());
+                descs.push_back(ra);
+            }
         }
+        SWIRL_CUDA(dev_alloc(ctx, &d_r0, r0_words + 4));
+        to_free.push_back(d_r0);
         if (!descs.empty()) {
             uint32_t* part = nullptr;
             SWIRL_CUDA(dev_alloc(ctx, &part, part_words + 4));
             to_free.push_back(part);
-            for (auto& d : descs) d.partials = part + (size_t)(uintptr_t)d.partials;
+            for (auto& d : descs) {
+                d.partials = part + (size_t)(uintptr_t)d.partials;
+                d.result = d_r0 + (size_t)(uintptr_t)d.result;
+            }
             R0Args* d_descs = nullptr;
             uint16_t* d_ba = nullptr;
             SWIRL_TRY(upload(descs.data(), descs.size() * sizeof(R0Args), (void**)&d_descs));
@@ -975,9 +1012,13 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             SWIRL_LAUNCH_CHECK(ctx);
         }
     }
-    std::vector<uint32_t> h_r0(r0_off[n_airs] + 4);
-    SWIRL_CUDA(cudaMemcpyAsync(h_r0.data(), d_r0, r0_off[n_airs] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> h_r0c(r0_words + 4), h_r0(r0_off[n_airs] + 4, 0);
+    SWIRL_CUDA(cudaMemcpyAsync(h_r0c.data(), d_r0, r0_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+    for (const auto& da : r0_desc_air) {
+        const size_t t = da.first, nv = (size_t)airs[t].constraint_degree * N * 12;
+        for (size_t i = 0; i < nv; i++) h_r0[r0_off[t] + i] = bb::add(h_r0[r0_off[t] + i], h_r0c[da.second + i]);
+    }
     // host: per-trace s'_0 polynomials (cpu.rs:324-424)
     const size_t sp_0_deg = (size_t)D * (N - 1), s_0_deg = (size_t)(D + 1) * (N - 1);
     std::vector<std::vector<Ext>> sp0(3 * n_airs);  // [2t] numer, [2t+1] denom, [2n + t] zerocheck
@@ -1147,7 +1188,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     uint16_t *d_mle_ba = nullptr, *d_fold_ba = nullptr;
     size_t max_fold_blocks = 0;
     for (size_t t = 0; t < n_airs; t++) max_fold_blocks += ((size_t)T[t].total_cols * (T[t].h / 2) + BC_BLOCK - 1) / BC_BLOCK + 1;
-    SWIRL_CUDA(dev_alloc(ctx, &d_mle_descs, n_airs));
+    SWIRL_CUDA(dev_alloc(ctx, &d_mle_descs, 256));
     SWIRL_CUDA(dev_alloc(ctx, &d_fold_descs, n_airs));
     SWIRL_CUDA(dev_alloc(ctx, &d_mle_ba, (size_t)rs->max_blocks));
     SWIRL_CUDA(dev_alloc(ctx, &d_fold_ba, max_fold_blocks));
@@ -1164,6 +1205,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             if (round <= kv.first) SWIRL_TRY(build_eq(l_skip + round, kv.first));
         std::vector<MleArgs> descs;
         std::vector<uint16_t> block_air;
+        std::vector<size_t> desc_first(n_airs, 0), desc_count(n_airs, 0);
         for (size_t t = 0; t < n_airs; t++) {
             TraceState& s = T[t];
             if (airs[t].constraint_degree == 0 && !airs[t].n_interactions && !airs[t].n_constraints) {
@@ -1174,31 +1216,35 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 mode[t] = 2;
                 continue;
             }
-            MleArgs ma{};
-            ma.code = s.d_code;
-            ma.n_instr = (uint32_t)s.prog.code.size();
-            ma.base = s.ef[s.cur];
-            ma.h = s.h;
-            ma.weights = s.d_weights;
-            ma.eq_xi = s.d_eq_xi;
-            ma.ticket = rs->d_ticket + (t & 1023);
-            SWIRL_REQUIRE(n_airs <= 256, "too many AIRs for the result scratch");
-            ma.result = rs->d_result + t * 64;
-            if (round == s.n_lift + 1) {
-                mode[t] = 1;
-                ma.single = 1;
-                ma.ny = 1;
-                ma.n_blocks = 1;
-            } else {
-                const int log_ny = s.n_lift - round;
-                ma.single = 0;
-                ma.ny = size_t(1) << log_ny;
-                ma.n_blocks = (uint32_t)std::min<size_t>((ma.ny + 127) / 128, (size_t)ctx->sm_count * 8);
+            desc_first[t] = descs.size();
+            for (const auto& ch : s.chunks) {
+                MleArgs ma{};
+                ma.code = ch.d_code;
+                ma.n_instr = ch.n_instr;
+                ma.base = s.ef[s.cur];
+                ma.h = s.h;
+                ma.weights = s.d_weights;
+                ma.eq_xi = s.d_eq_xi;
+                SWIRL_REQUIRE(descs.size() < 256, "too many (AIR, program chunk) pairs for the result scratch");
+                ma.ticket = rs->d_ticket + descs.size();
+                ma.result = rs->d_result + descs.size() * 64;
+                if (round == s.n_lift + 1) {
+                    mode[t] = 1;
+                    ma.single = 1;
+                    ma.ny = 1;
+                    ma.n_blocks = 1;
+                } else {
+                    const int log_ny = s.n_lift - round;
+                    ma.single = 0;
+                    ma.ny = size_t(1) << log_ny;
+                    ma.n_blocks = (uint32_t)std::min<size_t>((ma.ny + 127) / 128, std::max<size_t>(1, (size_t)ctx->sm_count * 8 / s.chunks.size()));
+                }
+                ma.first_block = (uint32_t)block_air.size();
+                ma.partials = rs->d_partials + (size_t)ma.first_block * 64;
+                block_air.insert(block_air.end(), ma.n_blocks, (uint16_t)descs.size());
+                descs.push_back(ma);
             }
-            ma.first_block = (uint32_t)block_air.size();
-            ma.partials = rs->d_partials + (size_t)ma.first_block * 64;
-            block_air.insert(block_air.end(), ma.n_blocks, (uint16_t)descs.size());
-            descs.push_back(ma);
+            desc_count[t] = descs.size() - desc_first[t];
         }
         if (!descs.empty()) {
             SWIRL_REQUIRE(block_air.size() <= (size_t)rs->max_blocks, "too many blocks for the reduction scratch");
@@ -1219,7 +1265,9 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         std::vector<std::vector<Ext>> sp(3 * n_airs);
         for (size_t t = 0; t < n_airs; t++) {
             TraceState& s = T[t];
-            const uint32_t* res = rs->h_result + t * 64;
+            uint32_t res[64] = {0};  // sum over this AIR's program chunks
+            for (size_t k = 0; k < desc_count[t]; k++)
+                for (int i = 0; i < 64; i++) res[i] = bb::add(res[i], rs->h_result[(desc_first[t] + k) * 64 + i] % bb::P);
             const bool has_int = airs[t].n_interactions != 0;
             if (mode[t] == 3) {
                 sp[2 * n_airs + t].assign(D, bb::ext_zero());
