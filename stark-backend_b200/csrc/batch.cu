@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <type_traits>
 #include <vector>
 
 #include "ext.cuh"
@@ -41,7 +42,7 @@ using bb::ext_mul;
 using bb::ext_mul_base;
 using bb::ext_sub;
 
-enum : uint32_t { I_VAR = 0, I_CONST, I_ADD, I_SUB, I_MUL, I_NEG, I_ACC };
+enum : uint32_t { I_VAR = 0, I_CONST, I_ADD, I_SUB, I_MUL, I_NEG, I_PREF, I_ACC };
 struct Instr {
     uint32_t op_dst;  // op | dst << 8
     uint32_t a, b, c;
@@ -49,6 +50,8 @@ struct Instr {
 constexpr int BC_BLOCK = 256;
 constexpr int BC_MAX_SLOTS = 256;
 constexpr size_t BC_MAX_CHUNKS = 32;   // sub-programs per AIR (result scratch: 256 (AIR, chunk) pairs per round)
+constexpr size_t BC_PREFETCH_VARS = 8;  // I_PREF distance, in variables
+constexpr size_t BC_R0_SPLIT_BELOW = 8192;  // round 0 walks sub-programs only for traces with fewer hypercube points
 constexpr size_t BC_CHUNK_ROOTS = 16;  // constraint / interaction roots per sub-program
 
 // ---- host: DAG -> program ---------------------------------------------------------------------------
@@ -86,7 +89,8 @@ struct Root {
 
 // Compiles the sub-DAG reachable from `roots`; each root value is added into accumulator
 // root.acc with weight index root.weight right after it is computed.
-static int compile_program(const swirl_air_ctx& a, const AirLayout& L, const std::vector<Root>& roots, Program* out) {
+static int compile_program(const swirl_air_ctx& a, const AirLayout& L, const std::vector<Root>& roots, Program* out,
+                           size_t prefetch_distance = 0) {
     const size_t n = a.n_nodes;
     std::vector<uint8_t> needed(n, 0);
     std::vector<std::vector<uint32_t>> root_of(n);
@@ -193,6 +197,30 @@ static int compile_program(const swirl_air_ctx& a, const AirLayout& L, const std
     }
     SWIRL_REQUIRE(n_slots <= BC_MAX_SLOTS, "constraint DAG needs more live values than supported");
     out->n_slots = n_slots;
+    if (prefetch_distance) {
+        // every column load misses L1 (a chunk of a column is read by exactly one warp) and one thread walks its
+        // columns serially: I_PREF announces the load `prefetch_distance` variables ahead so the DRAM latency
+        // overlaps the evaluation of the variables in between
+        std::vector<size_t> vars;
+        for (size_t i = 0; i < out->code.size(); i++)
+            if ((out->code[i].op_dst & 0xff) == I_VAR) vars.push_back(i);
+        auto pref = [&](size_t j) {
+            const Instr& v = out->code[vars[j]];
+            return Instr{I_PREF, v.a, v.b, v.c};
+        };
+        std::vector<Instr> code;
+        code.reserve(out->code.size() + vars.size());
+        for (size_t j = 0; j < std::min(prefetch_distance, vars.size()); j++) code.push_back(pref(j));
+        size_t j = 0;
+        for (size_t i = 0; i < out->code.size(); i++) {
+            if (j < vars.size() && vars[j] == i) {
+                if (j + prefetch_distance < vars.size()) code.push_back(pref(j + prefetch_distance));
+                j++;
+            }
+            code.push_back(out->code[i]);
+        }
+        out->code.swap(code);
+    }
     return 0;
 }
 
@@ -231,38 +259,53 @@ struct SharedSlots {
     __device__ __forceinline__ Row operator[](uint32_t s) const { return Row{base + (size_t)s * LN * stride, stride}; }
 };
 
+struct PrefetchTag {};  // load_var(part, col, global_col, PrefetchTag{}) announces a later load of that variable
+template <class O>
+constexpr bool is_prefetch = std::is_same<typename std::decay<O>::type, PrefetchTag>::value;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <class V, int LN, class Slots, class LoadVar>
 __device__ __forceinline__ void run_program_on(Slots&& slots, const Instr* __restrict__ code, uint32_t n_instr,
                                                const uint32_t* __restrict__ weights, LoadVar load_var, Ext (&acc)[LN][3]) {
+    if (n_instr == 0) return;
+    // the next instruction is fetched while the current one executes (the decode is a dependent L1 load)
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(code));
     for (uint32_t pc = 0; pc < n_instr; pc++) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(code) + pc);
-        const uint32_t op = raw.x & 0xff, dst = raw.x >> 8;
+        const uint4 cur = raw;
+        if (pc + 1 < n_instr) raw = __ldg(reinterpret_cast<const uint4*>(code) + pc + 1);
+        const uint32_t op = cur.x & 0xff, dst = cur.x >> 8;
         switch (op) {
-            case I_VAR: load_var(raw.y, raw.z, raw.w, slots[dst]); break;
+            case I_VAR: load_var(cur.y, cur.z, cur.w, slots[dst]); break;
+            case I_PREF: load_var(cur.y, cur.z, cur.w, PrefetchTag{}); break;
             case I_CONST:
 #pragma unroll
-                for (int l = 0; l < LN; l++) slots[dst][l] = V::from_base(raw.y);
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::from_base(cur.y);
                 break;
             case I_ADD:
 #pragma unroll
-                for (int l = 0; l < LN; l++) slots[dst][l] = V::add(slots[raw.y][l], slots[raw.z][l]);
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::add(slots[cur.y][l], slots[cur.z][l]);
                 break;
             case I_SUB:
 #pragma unroll
-                for (int l = 0; l < LN; l++) slots[dst][l] = V::sub(slots[raw.y][l], slots[raw.z][l]);
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::sub(slots[cur.y][l], slots[cur.z][l]);
                 break;
             case I_MUL:
 #pragma unroll
-                for (int l = 0; l < LN; l++) slots[dst][l] = V::mul(slots[raw.y][l], slots[raw.z][l]);
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::mul(slots[cur.y][l], slots[cur.z][l]);
                 break;
             case I_NEG:
 #pragma unroll
-                for (int l = 0; l < LN; l++) slots[dst][l] = V::neg(slots[raw.y][l]);
+                for (int l = 0; l < LN; l++) slots[dst][l] = V::neg(slots[cur.y][l]);
                 break;
-            default: {  // I_ACC: acc[.][y] += weights[z] * slots[w]
-                const Ext wv = ldg_ext(weights + 4 * raw.z);
+            default: {  // I_ACC: acc[.][y] += weights[z] * slots[w]; static accumulator indices keep acc in registers
+                const Ext wv = ldg_ext(weights + 4 * cur.z);
 #pragma unroll
-                for (int l = 0; l < LN; l++) acc[l][raw.y] = ext_add(acc[l][raw.y], V::weigh(wv, slots[raw.w][l]));
+                for (int l = 0; l < LN; l++) {
+                    const Ext t = V::weigh(wv, slots[cur.w][l]);
+                    if (cur.y == 0) acc[l][0] = ext_add(acc[l][0], t);
+                    else if (cur.y == 1) acc[l][1] = ext_add(acc[l][1], t);
+                    else acc[l][2] = ext_add(acc[l][2], t);
+                }
             }
         }
     }
@@ -312,8 +355,10 @@ __global__ void __launch_bounds__(BC_BLOCK) logup_leaves_kernel(LeafArgs a) {
     const uint32_t p0 = a.prog_off[sigma], p1 = a.prog_off[sigma + 1];
     run_program<FVal, NS, 1>(a.code + p0, p1 - p0, a.weights,
                              [&](uint32_t part, uint32_t col, uint32_t, auto&& out) {
-                                 const BasePart bp = a.parts[part];
-                                 out[0] = __ldg(bp.ptr + (size_t)col * bp.height + ((i + bp.rot) & (bp.height - 1)));
+                                 if constexpr (!is_prefetch<decltype(out)>) {
+                                     const BasePart bp = a.parts[part];
+                                     out[0] = __ldg(bp.ptr + (size_t)col * bp.height + ((i + bp.rot) & (bp.height - 1)));
+                                 }
                              },
                              acc);
     const Ext numer = ext_mul_base(acc[0][1], a.norm);
@@ -334,6 +379,7 @@ __global__ void leaves_fill_kernel(uint32_t* __restrict__ leaves, size_t n, Ext 
 // Round 0: thread = (hypercube point x, coset point p).  partials[block][p * 12 + 4k + c] =
 // sum_x eq_xi[x] * acc_k at point p.  All present AIRs share one launch: block -> (AIR, chunk) through
 // block_air / first_block.
+constexpr int R0_SMEM_PARTS = 24;
 struct R0Args {
     const Instr* code;
     uint32_t n_instr;
@@ -343,6 +389,7 @@ struct R0Args {
     const uint32_t* eq_xi;  // 2^n_lift EF
     int l_skip, n_lift, P, x_per_block;
     uint32_t first_block, n_blocks;
+    uint32_t n_parts;
     uint32_t* partials;  // this AIR's [n_blocks][P * 12]
     uint32_t* result;    // this AIR's [P * 12]
 };
@@ -364,6 +411,11 @@ __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(const R0Args* __
     constexpr int LN = 2;
     const R0Args a = descs[block_air[blockIdx.x]];
     const uint32_t bidx = blockIdx.x - a.first_block;
+    // trace-part descriptors in shared memory: one dependent global load less in front of every column load
+    __shared__ BasePart sparts[R0_SMEM_PARTS];
+    if (threadIdx.x < a.n_parts && threadIdx.x < R0_SMEM_PARTS) sparts[threadIdx.x] = a.parts[threadIdx.x];
+    __syncthreads();
+    const bool parts_in_smem = a.n_parts <= R0_SMEM_PARTS;
     const int P = a.P, N = 1 << a.l_skip;
     const int G = blockDim.x / P;
     const bool idle = (int)threadIdx.x >= P * G;  // blockDim is fixed; P need not divide it
@@ -391,8 +443,12 @@ __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(const R0Args* __
 #pragma unroll
             for (int k = 0; k < 3; k++) acc[l][k] = bb::ext_zero();
         auto load_var = [&](uint32_t part, uint32_t col, uint32_t, auto&& out) {
-                                      const BasePart bp = a.parts[part];
+                                      const BasePart bp = parts_in_smem ? sparts[part] : a.parts[part];
                                       const uint32_t* c = bp.ptr + (size_t)col * bp.height;
+                                      if constexpr (is_prefetch<decltype(out)>) {
+#pragma unroll
+                                          for (int l = 0; l < LN; l++) prefetch_l1(c + (((xs[l] << a.l_skip) + bp.rot) & (bp.height - 1)));
+                                      } else {
 #pragma unroll
                                       for (int l = 0; l < LN; l++) {
                                           const size_t r0 = xs[l] << a.l_skip;
@@ -414,6 +470,7 @@ __global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(const R0Args* __
                                                   v = bb::add(v, bb::mul(__ldg(lde + i), __ldg(c + ((r0 + bp.rot + i) & (bp.height - 1)))));
                                               out[l] = v;
                                           }
+                                      }
                                       }
                                   };
         if (NS <= 64) {  // value slots in shared memory (short-scoreboard latency instead of local-memory round trips)
@@ -510,6 +567,9 @@ __global__ void __launch_bounds__(128, 4) batch_mle_kernel(const MleArgs* __rest
         run_program<EVal, NS, D>(a.code, a.n_instr, a.weights,
                                  [&](uint32_t, uint32_t, uint32_t gcol, auto&& out) {
                                      const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
+                                     if constexpr (is_prefetch<decltype(out)>) {
+                                         prefetch_l1(c + (a.single ? 0 : 8 * y));
+                                     } else {
                                      if (a.single) {
                                          out[0] = ldg_ext(c);
                                          return;
@@ -519,6 +579,7 @@ __global__ void __launch_bounds__(128, 4) batch_mle_kernel(const MleArgs* __rest
                                      out[0] = t1;
 #pragma unroll
                                      for (int X = 1; X < D; X++) out[X] = ext_add(out[X - 1], d);
+                                     }
                                  },
                                  acc);
 #pragma unroll
@@ -753,7 +814,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             roots.push_back(Root{it.count_node, 1, w++});
             for (uint32_t j = 0; j < it.msg_len; j++) roots.push_back(Root{a.msg_nodes[it.msg_offset + j], 2, w++});
         }
-        SWIRL_TRY(compile_program(a, s.L, roots, &s.prog));
+        SWIRL_TRY(compile_program(a, s.L, roots, &s.prog, BC_PREFETCH_VARS));
         SWIRL_TRY(upload(s.prog.code.data(), s.prog.code.size() * sizeof(Instr), (void**)&s.d_code));
         {
             const size_t k_max = std::max<size_t>(1, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
@@ -762,7 +823,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 const size_t r0 = roots.size() * k / K, r1 = roots.size() * (k + 1) / K;
                 if (r0 == r1 && !(K == 1)) continue;
                 Program pr;
-                SWIRL_TRY(compile_program(a, s.L, std::vector<Root>(roots.begin() + r0, roots.begin() + r1), &pr));
+                SWIRL_TRY(compile_program(a, s.L, std::vector<Root>(roots.begin() + r0, roots.begin() + r1), &pr, BC_PREFETCH_VARS));
                 TraceState::Chunk c;
                 c.n_instr = (uint32_t)pr.code.size();
                 c.n_slots = pr.n_slots;
@@ -939,6 +1000,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     int max_slots = 1;
     for (size_t t = 0; t < n_airs; t++)
         for (const auto& c : T[t].chunks) max_slots = std::max(max_slots, c.n_slots);
+    int max_slots_r0 = max_slots;
     uint32_t* d_r0 = nullptr;
     std::vector<std::pair<size_t, size_t>> r0_desc_air;  // (air, offset of the desc's result block)
     {
@@ -949,11 +1011,20 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             TraceState& s = T[t];
             const int cd = (int)airs[t].constraint_degree;
             if (cd == 0) continue;
-            for (const auto& ch : s.chunks) {
+            // enough hypercube points to fill the machine: one walk of the whole program per point (the per-point
+            // set-up is paid once); short traces take the sub-programs for their parallelism
+            std::vector<TraceState::Chunk> whole(1);
+            whole[0].d_code = s.d_code;
+            whole[0].n_instr = (uint32_t)s.prog.code.size();
+            whole[0].n_slots = s.prog.n_slots;
+            const bool split = (size_t(1) << s.n_lift) < BC_R0_SPLIT_BELOW;
+            if (!split) max_slots_r0 = std::max(max_slots_r0, s.prog.n_slots);
+            for (const auto& ch : split ? s.chunks : whole) {
                 R0Args ra{};
                 ra.code = ch.d_code;
                 ra.n_instr = ch.n_instr;
                 ra.parts = s.d_parts;
+                ra.n_parts = s.L.n_parts;
                 ra.weights = s.d_weights;
                 ra.lde = d_lde[cd];
                 ra.eq_xi = s.d_eq_xi;
@@ -962,7 +1033,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 ra.P = (int)(cd * N);
                 const int G = std::max(1, BC_BLOCK / ra.P);
                 const size_t nx = size_t(1) << s.n_lift;
-                ra.x_per_block = G * (s.chunks.size() > 1 ? 16 : 4);
+                ra.x_per_block = G * (split && s.chunks.size() > 1 ? 16 : 4);
                 ra.n_blocks = (uint32_t)((nx + ra.x_per_block - 1) / ra.x_per_block);
                 ra.first_block = (uint32_t)block_air.size();
                 ra.partials = (uint32_t*)(uintptr_t)part_words;  // offsets for now, rebased below
@@ -1003,7 +1074,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     } while (0)
             {
                 SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
-                BC_DISPATCH_NS(max_slots, BC_R0);
+                BC_DISPATCH_NS(max_slots_r0, BC_R0);
             }
 #undef BC_R0
             SWIRL_LAUNCH_CHECK(ctx);
