@@ -208,21 +208,19 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of the reference col-major prover; only its commit phase is multi-threaded"},
+                         "note": "C++ restatement of the reference col-major prover (oracle/); its commit phase and PoW searches use all host threads, its sumcheck phases run on one"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # kernel families of swirl_ctx_timing_read with the algorithmic bytes of one launch on this workload
-def family_bytes():
-    N, W = 1 << (LOG_ROWS + LOG_BLOWUP), COLS
-    H = 1 << LOG_ROWS
-    return {
-        # read the codeword once, write digest layer 0
-        "leaf": 4 * N * W + 32 * (N >> K_WHIR),
-        # read every column chunk once (the sweep over the H x W trace + 3 selector columns)
-        "bc_round0": 4 * H * (W + 3),
-    }
+# dram__bytes_read.sum + dram__bytes_write.sum of the family's largest launch, from the committed ncu --set full capture
+NCU_TRAFFIC = {
+    "leaf": {"bytes": 2149520000 + 11094784,
+             "note": "commit launch (2^21 x 256 codeword): 2.1495 GB read + 11.1 MB written vs 2.1517 GB algorithmic; "
+                     "profiles/r1h_bc_leaf_ncu.txt"},
+    "bc_round0": {"bytes": 1215332000 + 20032512, "note": "1.215 GB read + 20 MB written vs 1.086 GB algorithmic; profiles/r1m_round0_ncu.txt"},
+}
 
 
 def run_swirl(args):
@@ -356,11 +354,12 @@ def run_swirl(args):
 
     if rank == 0:
         pk_, pk_kind = peaks()
-        fam = {k: (v[0] / max(v[1], 1), v[1] // args.steps, v[0] / args.steps) for k, v in spans.items()}  # avg ms, launches/step, ms/step
-        fbytes = family_bytes()
-        dom = max(fbytes, key=lambda k: fam[k][2])
+        # per family: avg ms per launch, launches per step, ms per step, algorithmic bytes per step (accounted by the
+        # library for exactly the launches that were timed: leaf hashing and round 0)
+        fam = {k: (v[0] / max(v[1], 1), v[1] // args.steps, v[0] / args.steps, v[2] / args.steps) for k, v in spans.items()}
+        dom = max((k for k in fam if fam[k][3] > 0), key=lambda k: fam[k][2])
         dom_ms = fam[dom][0]
-        ach = fbytes[dom] / (dom_ms / 1e3) / 1e9 if dom_ms else 0.0
+        ach = fam[dom][3] / (fam[dom][2] / 1e3) / 1e9 if fam[dom][2] else 0.0
         leaf_perms = (1 << (LOG_ROWS + LOG_BLOWUP)) * (COLS // 8) + ((1 << (LOG_ROWS + LOG_BLOWUP)) - ((1 << (LOG_ROWS + LOG_BLOWUP)) >> K_WHIR))
         names = {"leaf": "leaf_tree_kernel (fused Poseidon2 row sponge + 2^k_whir strided tree levels)",
                  "bc_round0": "batch_round0_kernel (constraint DAG evaluation on the cosets of the skip domain)"}
@@ -379,13 +378,17 @@ def run_swirl(args):
             "clocks": clocks,
             "roofline": {
                 "kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": pk_["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk_["hbm_gbs"], "peak_source": pk_kind, "traffic": None, "ms_per_launch": dom_ms,
-                "launches_per_step": fam[dom][1],
+                "frac": ach / pk_["hbm_gbs"], "peak_source": pk_kind,
+                "traffic": NCU_TRAFFIC.get(dom, {}).get("bytes"), "traffic_note": NCU_TRAFFIC.get(dom, {}).get("note"),
+                "ms_per_launch": dom_ms, "launches_per_step": fam[dom][1], "algorithmic_bytes_per_step": fam[dom][3],
+                "achieved_definition": "algorithmic bytes of all launches of the family in a step / their summed duration",
                 "timing": "CUDA events around every launch of the family, over a repeat of the K timed steps",
-                "note": "both candidate dominant kernels are INT32-multiplier bound, not HBM bound (see int_pipe and DESIGN.md)",
+                "note": "the dominant kernel is bound by the 32-bit integer multiplier pipe, not by HBM: ncu shows the fma-heavy pipe "
+                        "82 % busy and 1.2 % of peak DRAM throughput (profiles/r1h_bc_leaf_ncu.txt); see int_pipe and DESIGN.md section 4",
                 "int_pipe": int_pipe_roofline(leaf_perms, fam["leaf"][2], clocks),
             },
             "phases_ms_per_step": {k: v[2] for k, v in fam.items()},
+            "phases_note": "kernel families with CUDA-event spans only; GKR tree/leaves, stacked reduction, WHIR and host latency are the rest",
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
                     "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk_["hbm_gbs"] if lde_ms else 0.0},
             "proof_bytes": len(proof.encode()),  # Proof::encode_to_vec() wire format (stark-backend_b200/codec.py)
@@ -398,7 +401,7 @@ def run_swirl(args):
             v, dt, sample = cpu_prove_sample(oracle, 12)
             out["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
                                    "seconds": dt,
-                                   "note": "C++ restatement of the reference col-major prover; only its commit phase is multi-threaded"}
+                                   "note": "C++ restatement of the reference col-major prover (oracle/); its commit phase and PoW searches use all host threads, its sumcheck phases run on one"}
         print(json.dumps(out))
     del trace_dev
     torch.cuda.synchronize()
@@ -418,7 +421,9 @@ def int_pipe_roofline(perms, ms, clocks):
     peak = 64 * 148 * mhz * 1e6 / passes / 1e9
     ach = perms / (ms / 1e3) / 1e9 if ms else 0.0
     return {"kernel": "leaf_tree_kernel", "perms_per_step": perms, "gperm_per_s": ach, "peak_gperm_per_s": peak, "frac": ach / peak,
-            "model": "fma-heavy pipe, 64 lanes/clk/SM x 148 SM x sm_max_mhz / 2911 multiplier passes per permutation"}
+            "model": "fma-heavy pipe, 64 lanes/clk/SM x 148 SM x sm_max_mhz / 2911 multiplier passes per permutation",
+            "ncu": "sm__pipe_fmaheavy_cycles_active 81.8 % of elapsed (the pipe also carries ~850 IMAD.IADD per permutation that ptxas "
+                   "places there; moving them to the ALU pipe was measured slower, profiles/r1_p2_v3_experiment_ncu.txt)"}
 
 
 def main():

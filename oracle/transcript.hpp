@@ -13,8 +13,12 @@
 // deterministic and returns the smallest valid witness, which is one of the reference's
 // admissible outputs.
 #pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
 #include <vector>
 
+#include "par.hpp"
 #include "poseidon2.hpp"
 
 namespace orc {
@@ -60,11 +64,27 @@ struct DuplexSponge {
     // smallest canonical witness >= start that passes; mutates the transcript with it
     F grind(int bits, uint32_t start = 0) {
         if (bits == 0) return f_zero();
-        for (uint64_t c = start; c < P; c++) {
-            DuplexSponge probe = *this;
-            F w = from_canonical(c);
-            if (probe.check_witness(bits, w)) {
-                bool ok = check_witness(bits, w);
+        // windows of candidates searched by all host threads (the reference searches with rayon); the smallest
+        // witness of the first window that holds one is the smallest witness overall
+        const uint64_t window = uint64_t(4096) * par_threads();
+        for (uint64_t base = start; base < P; base += window) {
+            const uint64_t n = std::min<uint64_t>(window, P - base);
+            std::atomic<uint64_t> found{UINT64_MAX};
+            const DuplexSponge snapshot = *this;
+            parallel_for(n, [&](size_t i0, size_t i1) {
+                for (size_t i = i0; i < i1; i++) {
+                    DuplexSponge probe = snapshot;
+                    if (probe.check_witness(bits, from_canonical(base + i))) {
+                        uint64_t cur = found.load();
+                        while (base + i < cur && !found.compare_exchange_weak(cur, base + i)) {}
+                        return;
+                    }
+                }
+            }, 256);
+            const uint64_t best = found.load();
+            if (best != UINT64_MAX) {
+                const F w = from_canonical(best);
+                const bool ok = check_witness(bits, w);
                 (void)ok;
                 return w;
             }

@@ -382,12 +382,13 @@ class B200Device:
         check(self.lib.swirl_ctx_timing_enable(self.ctx, 1 if on else 0))
 
     def timing_read(self):
-        """{family: (total_ms, launches)} since timing_enable(True)."""
+        """{family: (total_ms, launches, algorithmic_bytes)} since timing_enable(True)."""
         out = {}
         for name, slot in self.TIMING_SLOTS.items():
-            ms, n = C.c_double(), C.c_uint64()
+            ms, n, b = C.c_double(), C.c_uint64(), C.c_uint64()
             check(self.lib.swirl_ctx_timing_read(self.ctx, slot, C.byref(ms), C.byref(n)))
-            out[name] = (ms.value, int(n.value))
+            check(self.lib.swirl_ctx_timing_bytes(self.ctx, slot, C.byref(b)))
+            out[name] = (ms.value, int(n.value), int(b.value))
         return out
 
     def trim(self):

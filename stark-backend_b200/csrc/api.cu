@@ -212,6 +212,16 @@ int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* 
     return 0;
 }
 
+int swirl_ctx_timing_bytes(swirl_ctx* ctx, int slot, uint64_t* bytes) {
+    SWIRL_REQUIRE(ctx && bytes, "null argument");
+    SWIRL_REQUIRE(slot >= 0 && slot < SWIRL_T_SLOTS, "slot");
+    uint64_t n = 0;
+    for (auto& s : ctx->spans)
+        if (s.slot == slot) n += s.bytes;
+    *bytes = n;
+    return 0;
+}
+
 int swirl_malloc(swirl_ctx* ctx, size_t bytes, void** d_out) {
     SWIRL_REQUIRE(ctx && d_out, "null argument");
     SWIRL_CUDA(cudaSetDevice(ctx->device));

@@ -1001,6 +1001,9 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     for (size_t t = 0; t < n_airs; t++)
         for (const auto& c : T[t].chunks) max_slots = std::max(max_slots, c.n_slots);
     int max_slots_r0 = max_slots;
+    uint64_t r0_alg_bytes = 0;  // every trace part (and the 3 selector columns) read once
+    for (size_t t = 0; t < n_airs; t++)
+        if (airs[t].constraint_degree) r0_alg_bytes += (uint64_t)T[t].lifted * 3 * 4 + (uint64_t)T[t].height * (T[t].total_cols - 3) / T[t].L.stride * 4;
     uint32_t* d_r0 = nullptr;
     std::vector<std::pair<size_t, size_t>> r0_desc_air;  // (air, offset of the desc's result block)
     {
@@ -1073,7 +1076,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         }                                                                                                             \
     } while (0)
             {
-                SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0);
+                SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0, r0_alg_bytes);
                 BC_DISPATCH_NS(max_slots_r0, BC_R0);
             }
 #undef BC_R0

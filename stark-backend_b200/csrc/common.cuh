@@ -39,6 +39,7 @@ struct swirl_ctx {
     struct TimedSpan {
         int slot;
         cudaEvent_t a, b;
+        uint64_t bytes;  // algorithmic bytes of the launch (0 = not accounted)
     };
     std::vector<TimedSpan> spans;
     // Arena of large device blocks (>= ARENA_MIN bytes), see dev_alloc below.
@@ -64,13 +65,13 @@ enum {
 struct SwirlTimed {  // RAII: records an event pair around a launch when ctx->timing is on
     swirl_ctx* ctx;
     cudaEvent_t b = nullptr;
-    SwirlTimed(swirl_ctx* c, int slot) : ctx(c) {
+    SwirlTimed(swirl_ctx* c, int slot, uint64_t bytes = 0) : ctx(c) {
         if (!c->timing) return;
         cudaEvent_t a;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
         cudaEventRecord(a, c->stream);
-        c->spans.push_back({slot, a, b});
+        c->spans.push_back({slot, a, b, bytes});
     }
     ~SwirlTimed() {
         if (b) cudaEventRecord(b, ctx->stream);

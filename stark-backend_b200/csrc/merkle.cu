@@ -284,7 +284,8 @@ int merkle_commit_columns(swirl_ctx* ctx, const uint32_t* d_matrix, size_t heigh
         const size_t grid = S >> log_yb;
         SWIRL_REQUIRE(grid < (size_t(1) << 31), "grid too large");
         {
-            SwirlTimed timed(ctx, SWIRL_T_LEAF);
+            // algorithmic traffic: the matrix once, digest layer 0 once
+            SwirlTimed timed(ctx, SWIRL_T_LEAF, (uint64_t)height * width * 4 + (last ? (uint64_t)S * 32 : 0));
             leaf_tree_kernel<<<(unsigned)grid, 1 << (log_yb + log_rpq), 0, ctx->stream>>>(
                 d_matrix, height, (uint32_t)width, S, log_rpq, log_yb, d_layers, first ? nullptr : d_state,
                 last ? nullptr : d_state);
