@@ -36,6 +36,7 @@ namespace swirl {
 
 using bb::ext_add;
 using bb::ext_mul;
+using bb::ext_mul_base;
 using bb::ext_sub;
 
 constexpr int GKR_BLOCK = 256;
@@ -96,7 +97,7 @@ struct RoundArgs {
     uint32_t lambda[4];
     uint32_t* partials;
     unsigned int* ticket;
-    uint32_t* result;  // 12 words: t(1), t(2), t(3)
+    uint32_t* result;  // 8 words: t(1) and the leading coefficient of t
 };
 
 template <bool FROM_TREE>
@@ -118,23 +119,17 @@ __device__ __forceinline__ void load_row(const RoundArgs& a, size_t x, const Ext
     }
 }
 
-// contribution of the pair (lo, hi) = rows (2y, 2y+1) to t(1), t(2), t(3):
-// E * (p0 q1 + p1 q0 + lambda q0 q1) = E * (p0 q1 + q0 (p1 + lambda q1)), every factor linear in X
-__device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ext (&hi)[4], const Ext& lambda, const Ext& E, Ext (&s)[3]) {
-    const Ext w_lo = ext_add(lo[2], ext_mul(lambda, lo[3])), w_hi = ext_add(hi[2], ext_mul(lambda, hi[3]));
-    const Ext d0 = ext_sub(hi[0], lo[0]), d1 = ext_sub(hi[1], lo[1]), d3 = ext_sub(hi[3], lo[3]), dw = ext_sub(w_hi, w_lo);
-    Ext p0 = hi[0], q0 = hi[1], q1 = hi[3], w = w_hi;  // X = 1
-#pragma unroll
-    for (int X = 0; X < 3; X++) {
-        const Ext inner = ext_add(ext_mul(p0, q1), ext_mul(q0, w));
-        s[X] = ext_add(s[X], ext_mul(E, inner));
-        if (X < 2) {
-            p0 = ext_add(p0, d0);
-            q0 = ext_add(q0, d1);
-            q1 = ext_add(q1, d3);
-            w = ext_add(w, dw);
-        }
-    }
+// contribution of the pair (lo, hi) = rows (2y, 2y+1) to t(1) and to the leading coefficient of the quadratic
+// t(X) = sum_y E[y] * inner(X, y), inner = p0 q1 + p1 q0 + lambda q0 q1 = p0 q1 + q0 (p1 + lambda q1) with every
+// factor linear in X.  Two values are enough: t(0) follows on the host from the sumcheck identity s(0) + s(1) = claim,
+// so the round costs 8 extension multiplications per pair instead of 12.
+__device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ext (&hi)[4], const Ext& lambda, const Ext& E, Ext (&s)[2]) {
+    const Ext d0 = ext_sub(hi[0], lo[0]), d1 = ext_sub(hi[1], lo[1]), d2 = ext_sub(hi[2], lo[2]), d3 = ext_sub(hi[3], lo[3]);
+    const Ext w_hi = ext_add(hi[2], ext_mul(lambda, hi[3])), dw = ext_add(d2, ext_mul(lambda, d3));
+    const Ext at1 = ext_add(ext_mul(hi[0], hi[3]), ext_mul(hi[1], w_hi));
+    const Ext lead = ext_add(ext_mul(d0, d3), ext_mul(d1, dw));
+    s[0] = ext_add(s[0], ext_mul(E, at1));
+    s[1] = ext_add(s[1], ext_mul(E, lead));
 }
 
 // One sumcheck round.  FOLD = false: table rows are read as they are (first round of a layer).
@@ -145,7 +140,7 @@ __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
     const Ext lambda = Ext{{a.lambda[0], a.lambda[1], a.lambda[2], a.lambda[3]}};
     const Ext r = Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
     const Ext c = Ext{{a.c[0], a.c[1], a.c[2], a.c[3]}};
-    Ext s[3] = {bb::ext_zero(), bb::ext_zero(), bb::ext_zero()};
+    Ext s[2] = {bb::ext_zero(), bb::ext_zero()};
     const size_t a_mask = (size_t(1) << a.a_bits) - 1;
     for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)gridDim.x * blockDim.x) {
         Ext lo[4], hi[4];
@@ -172,12 +167,12 @@ __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
         if (a.a_bits) E = ext_mul(E, ldg_ext(a.A + (y & a_mask) * 4));
         accumulate(lo, hi, lambda, E, s);
     }
-    uint32_t v[12];
+    uint32_t v[8];
 #pragma unroll
-    for (int X = 0; X < 3; X++)
+    for (int X = 0; X < 2; X++)
 #pragma unroll
         for (int k = 0; k < 4; k++) v[X * 4 + k] = s[X].c[k];
-    grid_sum<12>(v, a.partials, a.ticket, a.result);
+    grid_sum<8>(v, a.partials, a.ticket, a.result);
 }
 
 // Last fold of a layer: the 2-row table -> its single row = the four layer claims (p0, q0, p1, q1).
@@ -304,7 +299,9 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
         SWIRL_CUDA(dev_alloc(ctx, &tab[1], 4 * tab_stride[1] * 4));
     }
     const Ext one = bb::ext_one();
-    const Ext X123[3] = {bb::ext_from(bb::mont(1)), bb::ext_from(bb::mont(2)), bb::ext_from(bb::mont(3))};
+    const uint32_t inv2 = bb::inv(bb::mont(2)), inv6 = bb::inv(bb::mont(6));
+    // claims of the previous layer: p(xi, 0), q(xi, 0), p(xi, 1), q(xi, 1)
+    Ext prev_claims[4] = {ext_from_words(top + 8), ext_from_words(top + 12), ext_from_words(top + 16), ext_from_words(top + 20)};
     size_t poly_off = 0;
     for (int round = 1; round < n && rc == 0; round++) {
         const Ext lambda = tr.sample_ext();
@@ -336,6 +333,9 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
         const size_t rows_tree = (S[round + 1] + 1) / 2;  // stored rows of this layer's table
         std::vector<Ext> rho;
         Ext e_bound = one;
+        // what this layer's sumcheck proves (verifier/fractional_sumcheck_gkr.rs:100-104): p(mu) + lambda q(mu) of the layer above
+        const Ext mu_prev = xi_prev[0];
+        Ext claim = ext_add(ext_lerp(prev_claims[0], prev_claims[2], mu_prev), ext_mul(lambda, ext_lerp(prev_claims[1], prev_claims[3], mu_prev)));
         size_t rows = rows_tree;  // stored rows of the table the next kernel reads
         int cur = 0;
         for (int sr = 0; sr < round; sr++) {
@@ -382,17 +382,45 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             const Ext tail = ext_mul(tail_unit, ext_sub(one, eq_prefix_sum(xi_prev, sr + 1, m, y_tail)));
             SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             uint32_t* out = h_polys + (poly_off + sr) * 12;
+            // s(X) = e_bound * eq1(xi_sr, X) * t(X): t(1) and the leading coefficient come from the device (the tail adds a
+            // constant), t(0) from s(0) = claim - s(1), then t(2), t(3) by extrapolating the quadratic
+            const Ext xs = xi_prev[sr], one_minus_xs = ext_one_minus(xs);
+            const Ext t1 = ext_add(ext_from_words(rs->h_result), tail), c2 = ext_from_words(rs->h_result + 4);
+            const Ext s1 = ext_mul(ext_mul(e_bound, xs), t1);
+            const Ext den = ext_mul(e_bound, one_minus_xs);
+            if (hp::is_zero(den)) {
+                set_error("degenerate sumcheck challenge (eq factor is zero)");
+                rc = SWIRL_ERR_INVALID;
+                break;
+            }
+            const Ext s0 = ext_sub(claim, s1);
+            const Ext t0 = ext_mul(s0, bb::ext_inv(den));
+            const Ext c2x2 = ext_add(c2, c2);
+            const Ext t2 = ext_add(ext_sub(ext_add(t1, t1), t0), c2x2);
+            const Ext t3 = ext_add(ext_sub(ext_add(ext_add(t1, t1), t1), ext_add(t0, t0)), ext_add(ext_add(c2x2, c2x2), c2x2));
+            // eq1(xs, 2) = 3 xs - 1, eq1(xs, 3) = 5 xs - 2
+            const Ext xs2 = ext_add(xs, xs), xs3 = ext_add(xs2, xs), xs5 = ext_add(xs3, xs2);
+            const Ext s2 = ext_mul(ext_mul(e_bound, ext_sub(xs3, one)), t2);
+            const Ext s3 = ext_mul(ext_mul(e_bound, ext_sub(xs5, ext_add(one, one))), t3);
+            const Ext sX[3] = {s1, s2, s3};
             for (int X = 0; X < 3; X++) {
-                const Ext t = ext_add(ext_from_words(rs->h_result + 4 * X), tail);
-                const Ext sX = ext_mul(ext_mul(e_bound, hp::eq1(xi_prev[sr], X123[X])), t);
-                memcpy(out + 4 * X, sX.c, 16);
-                tr.observe_ext(sX);
+                memcpy(out + 4 * X, sX[X].c, 16);
+                tr.observe_ext(sX[X]);
             }
             const Ext r = tr.sample_ext();
             rho.push_back(r);
+            {  // claim <- s(r): cubic through (0, s0), (1, s1), (2, s2), (3, s3)
+                const Ext r1 = ext_sub(r, one), r2 = ext_sub(r1, one), r3 = ext_sub(r2, one);
+                const Ext l0 = bb::ext_neg(ext_mul_base(ext_mul(ext_mul(r1, r2), r3), inv6));
+                const Ext l1 = ext_mul_base(ext_mul(ext_mul(r, r2), r3), inv2);
+                const Ext l2 = bb::ext_neg(ext_mul_base(ext_mul(ext_mul(r, r1), r3), inv2));
+                const Ext l3 = ext_mul_base(ext_mul(ext_mul(r, r1), r2), inv6);
+                claim = ext_add(ext_add(ext_mul(l0, s0), ext_mul(l1, s1)), ext_add(ext_mul(l2, s2), ext_mul(l3, s3)));
+            }
             e_bound = ext_mul(e_bound, hp::eq1(xi_prev[sr], r));
             for (int k = 0; k < 4; k++) a.r[k] = r.c[k];
         }
+        if (rc != 0) break;
         // claims: fold the remaining 2-row table with the last challenge
         if (round == 1) {
             a.rows_in = rows_tree;
@@ -407,7 +435,10 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
         SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         uint32_t* cl = h_claims + (size_t)round * 16;
         memcpy(cl, rs->h_result, 64);
-        for (int i = 0; i < 4; i++) tr.observe_ext(ext_from_words(cl + 4 * i));
+        for (int i = 0; i < 4; i++) {
+            prev_claims[i] = ext_from_words(cl + 4 * i);
+            tr.observe_ext(prev_claims[i]);
+        }
         const Ext mu = tr.sample_ext();
         xi_prev.assign(1, mu);
         xi_prev.insert(xi_prev.end(), rho.begin(), rho.end());
