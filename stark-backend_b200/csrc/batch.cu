@@ -405,7 +405,7 @@ __device__ __forceinline__ uint32_t chunk_dot16(const uint32_t (&l)[16], const u
 // LOGN = 4: the thread's 16 Lagrange coefficients live in registers and chunks are fetched as four
 // 16-byte loads; LOGN = 0: generic l_skip.  Two hypercube points per thread run in lockstep.
 template <int NS, int LOGN>
-__global__ void __launch_bounds__(BC_BLOCK) batch_round0_kernel(const R0Args* __restrict__ descs,
+__global__ void __launch_bounds__(BC_BLOCK, 3) batch_round0_kernel(const R0Args* __restrict__ descs,
                                                                 const uint16_t* __restrict__ block_air) {
     extern __shared__ uint32_t sm[];  // [blockDim][13] reduction scratch, then [NS][LN][blockDim] value slots
     constexpr int LN = 2;
