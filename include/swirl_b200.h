@@ -140,6 +140,11 @@ int swirl_transcript_check_witness(swirl_transcript* ts, int bits, uint32_t witn
 /* grind (traits.rs:71-86): finds the smallest canonical witness, observes it, writes it (canonical). */
 int swirl_transcript_grind(swirl_ctx* ctx, swirl_transcript* ts, int bits, uint32_t* witness);
 
+/* Linear fold of the low variable of a column-major EF matrix with even height (the MLE / FRI-style fold of every
+ * sumcheck round): out[j] = in[2j] + (in[2j+1] - in[2j]) * r over the flat array, n_out = width * height / 2.
+ * Reference: fold_mle_evals (prover/sumcheck.rs:395-414), GPU `fold_mle` (cuda-backend/cuda/src/sumcheck.cu). */
+int swirl_fold_mle(swirl_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t n_out, const uint32_t r[4]);
+
 /* ---- phase level: LogUp-GKR fractional sumcheck (reference: fractional_sumcheck,
  *      prover/logup_zerocheck/fractional_sumcheck_gkr.rs:60-213; GPU fractional_sumcheck_gpu,
  *      cuda-backend/src/logup_zerocheck/fractional.rs:649-) --------------------------------------

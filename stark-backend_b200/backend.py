@@ -484,6 +484,16 @@ class B200Device:
         return int(w.value)
 
     # -- LogUp-GKR (fractional_sumcheck, fractional_sumcheck_gkr.rs:60-213) ---------------------------
+    def fold_mle(self, table, r, out=None):
+        """table: CUDA int32 tensor of 2n EF (flat, column-major matrix of even height); r: 4 Montgomery words.
+        Returns the n folded EF: out[j] = t[2j] + (t[2j+1] - t[2j]) r (fold_mle_evals, sumcheck.rs:395-414)."""
+        n_out = table.numel() // 8
+        out = out if out is not None else self.alloc(n_out * 4)
+        rr = np.ascontiguousarray(r, dtype=np.uint32)
+        self._sync_torch()
+        check(self.lib.swirl_fold_mle(self.ctx, table.data_ptr(), out.data_ptr(), n_out, rr.ctypes.data))
+        return out
+
     def gkr_fractional_sumcheck(self, ts, leaves, log_n, assert_zero=True, n_stored=None, pad_q=None):
         """leaves: CUDA int32 tensor of 2^log_n Frac<EF> (8 words each) — or only the first n_stored of
         them when the rest is the constant fraction (0, pad_q).  Returns dict(frac_sum,

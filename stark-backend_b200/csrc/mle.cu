@@ -177,7 +177,16 @@ fold_ple_kernel(const uint32_t* __restrict__ mat, size_t height, size_t new_heig
     const uint32_t* col = mat + c * height;
     Ext acc = bb::ext_zero();
     const int N = 1 << l_skip;
-    for (int i = 0; i < N; i++) {
+    int i = 0;
+    for (; i + 4 <= N; i += 4) {  // four terms per Montgomery reduction (bb::dot4)
+        uint32_t q[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) q[j] = __ldg(col + ((x << l_skip) + i + j + rot) % height);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            acc.c[k] = bb::add(acc.c[k], bb::dot4(la.L[i][k], q[0], la.L[i + 1][k], q[1], la.L[i + 2][k], q[2], la.L[i + 3][k], q[3]));
+    }
+    for (; i < N; i++) {
         const size_t row = ((x << l_skip) + i + rot) % height;
         acc = bb::ext_add(acc, bb::ext_mul_base(Ext{{la.L[i][0], la.L[i][1], la.L[i][2], la.L[i][3]}}, __ldg(col + row)));
     }
@@ -196,3 +205,10 @@ int fold_ple(swirl_ctx* ctx, const uint32_t* mat, size_t height, size_t width, b
 }
 
 }  // namespace swirl
+
+extern "C" int swirl_fold_mle(swirl_ctx* ctx, const uint32_t* d_in, uint32_t* d_out, size_t n_out, const uint32_t r[4]) {
+    SWIRL_REQUIRE(ctx && r && ((d_in && d_out) || n_out == 0), "null argument");
+    SWIRL_REQUIRE((((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0, "EF buffers must be 16-byte aligned");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return swirl::ef_fold_flat(ctx, d_in, d_out, n_out, bb::Ext{{r[0], r[1], r[2], r[3]}});
+}

@@ -56,14 +56,33 @@ sr_round0_kernel(const R0View* __restrict__ views, const uint32_t* __restrict__ 
     const size_t nx = size_t(1) << n_lift;
     const size_t x0 = (size_t)blockIdx.x * xc;
     const size_t x1 = min(x0 + (size_t)xc, nx);
-    Ext a1 = bb::ext_zero(), a2 = bb::ext_zero();
-    for (size_t x = x0 + g; x < x1; x += G) {
-        const uint32_t q = __ldg(v.q + (x << l_skip) + i);
-        const Ext e = ldg_ext(eq + 4 * x);
-        const Ext ep = ldg_ext(eq + 4 * (x == 0 ? nx - 1 : x - 1));
-        a1 = ext_add(a1, ext_mul_base(e, q));
-        a2 = ext_add(a2, ext_mul_base(ext_sub(ep, e), q));
+    // a1 = sum_x eq[x] q[x], b = sum_x eq[x-1] q[x] (a2 = b - a1): EF x base products summed four at a time in 64 bits
+    // (4 p^2 < 2^64) with one Montgomery reduction per coefficient per group instead of one per product
+    Ext a1 = bb::ext_zero(), b1 = bb::ext_zero();
+    const uint64_t PP = (uint64_t)bb::P << 32;
+    for (size_t xb = x0 + g; xb < x1; xb += 4 * (size_t)G) {
+        uint64_t s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const size_t x = xb + (size_t)j * G;
+            if (x < x1) {
+                const uint32_t q = __ldg(v.q + (x << l_skip) + i);
+                const Ext e = ldg_ext(eq + 4 * x);
+                const Ext ep = ldg_ext(eq + 4 * (x == 0 ? nx - 1 : x - 1));
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    s1[k] += (uint64_t)e.c[k] * q;
+                    s2[k] += (uint64_t)ep.c[k] * q;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            a1.c[k] = bb::add(a1.c[k], bb::reduce(s1[k] >= PP ? s1[k] - PP : s1[k]));
+            b1.c[k] = bb::add(b1.c[k], bb::reduce(s2[k] >= PP ? s2[k] - PP : s2[k]));
+        }
     }
+    const Ext a2 = ext_sub(b1, a1);
     const Ext le = Ext{{v.lam_eq[0], v.lam_eq[1], v.lam_eq[2], v.lam_eq[3]}};
     const Ext lr = Ext{{v.lam_rot[0], v.lam_rot[1], v.lam_rot[2], v.lam_rot[3]}};
     const Ext o0 = ext_mul(a1, le), o1 = ext_mul(a1, lr), o2 = ext_mul(a2, lr);
@@ -104,7 +123,14 @@ sr_fold_ple_kernel(const uint32_t* __restrict__ q, size_t H, size_t total /* W *
     const uint32_t* p = q + (g << l_skip);
     Ext acc = bb::ext_zero();
     const int N = 1 << l_skip;
-    for (int i = 0; i < N; i++) {
+    int i = 0;
+    for (; i + 4 <= N; i += 4) {  // four terms per Montgomery reduction (bb::dot4)
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + i));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            acc.c[k] = bb::add(acc.c[k], bb::dot4(la.L[i][k], q.x, la.L[i + 1][k], q.y, la.L[i + 2][k], q.z, la.L[i + 3][k], q.w));
+    }
+    for (; i < N; i++) {
         const Ext L = Ext{{la.L[i][0], la.L[i][1], la.L[i][2], la.L[i][3]}};
         acc = ext_add(acc, ext_mul_base(L, __ldg(p + i)));
     }

@@ -40,8 +40,22 @@ whir_batch_kernel(const uint32_t* __restrict__ M, size_t H, uint32_t W, const ui
         a0 = acc[i]; a1 = acc[H + i]; a2 = acc[2 * H + i]; a3 = acc[3 * H + i];
     }
     const uint32_t* p = M + i;
-#pragma unroll 4
-    for (uint32_t c = 0; c < W; c++) {
+    // four columns per Montgomery reduction: sum of four 62-bit products < 2^64 (bb::dot4)
+    uint32_t c = 0;
+    for (; c + 4 <= W; c += 4) {
+        uint32_t x[4];
+        uint4 m[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            x[j] = __ldg(p + (size_t)(c + j) * H);
+            m[j] = __ldg(reinterpret_cast<const uint4*>(mu_pows) + c + j);
+        }
+        a0 = bb::add(a0, bb::dot4(m[0].x, x[0], m[1].x, x[1], m[2].x, x[2], m[3].x, x[3]));
+        a1 = bb::add(a1, bb::dot4(m[0].y, x[0], m[1].y, x[1], m[2].y, x[2], m[3].y, x[3]));
+        a2 = bb::add(a2, bb::dot4(m[0].z, x[0], m[1].z, x[1], m[2].z, x[2], m[3].z, x[3]));
+        a3 = bb::add(a3, bb::dot4(m[0].w, x[0], m[1].w, x[1], m[2].w, x[2], m[3].w, x[3]));
+    }
+    for (; c < W; c++) {
         const uint32_t x = __ldg(p + (size_t)c * H);
         const uint4 m = __ldg(reinterpret_cast<const uint4*>(mu_pows) + c);
         a0 = bb::add(a0, bb::mul(m.x, x));

@@ -352,3 +352,23 @@ def test_commit_host_pipelined_matches_device_commit(dev, oracle):
     assert np.array_equal(pcs_h.matrix(), vals)
     pcs_d.free()
     pcs_h.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n", [1, 4, 11, 16])
+def test_fold_mle_matches_oracle(dev, oracle, log_n):
+    """swirl_fold_mle = fold_mle_evals (prover/sumcheck.rs:395-414): one fold checked entry by entry with the oracle's
+    field arithmetic, log_n folds checked against the oracle's MLE evaluation at the same point."""
+    rng = np.random.default_rng(300 + log_n)
+    evals = oracle.random_field(rng, (1 << log_n, 4))
+    point = oracle.random_field(rng, (log_n, 4))
+    t = dev.h2d(evals)
+    first = dev._d2h(dev.fold_mle(t, point[0]).data_ptr(), (1 << (log_n - 1)) * 4).reshape(-1, 4)
+    for j in list(range(min(4, len(first)))) + [len(first) - 1]:
+        d = (evals[2 * j + 1].astype(np.int64) - evals[2 * j].astype(np.int64)) % sb.P
+        want = (evals[2 * j].astype(np.int64) + oracle.ef_mul(d.astype(np.uint32), point[0]).astype(np.int64)) % sb.P
+        assert np.array_equal(first[j], want.astype(np.uint32))
+    for i in range(log_n):
+        t = dev.fold_mle(t, point[i])
+    got = dev._d2h(t.data_ptr(), 4)
+    assert np.array_equal(got, oracle.eval_mle_evals_at_point(evals, log_n, point))

@@ -147,3 +147,12 @@ if "c5" in which:
         dt = timeit(lambda: dev.merkle_tree(m, 4, out=out), 3)
         perms = h * (-(-width // 8)) + h - 1
         emit(config="C5 Poseidon2 leaf hash + tree", rows=h, width=width, ms=dt * 1e3, gperm_per_s=perms / dt / 1e9)
+    # FRI/WHIR-style fold of an EF table by one challenge (fold_mle): 32 B read + 16 B written per output
+    for log_n in (16, 20, 24, 26):
+        t = torch.randint(0, sb.P, ((1 << log_n) * 4,), dtype=torch.int32, device="cuda")
+        o = dev.alloc((1 << (log_n - 1)) * 4)
+        r = np.array([5, 6, 7, 8], dtype=np.uint32)
+        dt = timeit(lambda: dev.fold_mle(t, r, out=o), 5)
+        emit(config="C5 fold (fold_mle of 2^log_n EF)", log_n=log_n, ms=dt * 1e3, ef_per_s=(1 << log_n) / dt,
+             gb_s_alg=(1 << log_n) * 24 / dt / 1e9)
+        del t, o
