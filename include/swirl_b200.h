@@ -64,6 +64,8 @@ const char* swirl_last_error(void);
  * Reference: gpu_metrics_span_on, cuda-common/src/stream.rs:278-303. */
 int swirl_ctx_timing_enable(swirl_ctx* ctx, int on);
 int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* count);
+/* Stream synchronisations issued by the library on this context so far and the wall time spent inside them. */
+int swirl_ctx_sync_stats(swirl_ctx* ctx, uint64_t* count, double* wait_ms);
 /* Algorithmic bytes of the recorded launches of a family; 0 for families without accounting. */
 int swirl_ctx_timing_bytes(swirl_ctx* ctx, int slot, uint64_t* bytes);
 

@@ -378,6 +378,12 @@ class B200Device:
     TIMING_SLOTS = {"leaf": 0, "tree": 1, "chunk": 2, "ntt_pass": 3, "ntt_final": 4, "stack": 5, "gkr": 6, "bc_round0": 7,
                     "bc_mle": 8}
 
+    def sync_stats(self):
+        """(stream synchronisations issued by the library so far, milliseconds spent inside them)."""
+        n, ms = C.c_uint64(), C.c_double()
+        check(self.lib.swirl_ctx_sync_stats(self.ctx, C.byref(n), C.byref(ms)))
+        return int(n.value), ms.value
+
     def timing_enable(self, on=True):
         check(self.lib.swirl_ctx_timing_enable(self.ctx, 1 if on else 0))
 

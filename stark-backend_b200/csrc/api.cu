@@ -212,6 +212,13 @@ int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* 
     return 0;
 }
 
+int swirl_ctx_sync_stats(swirl_ctx* ctx, uint64_t* count, double* wait_ms) {
+    SWIRL_REQUIRE(ctx && count && wait_ms, "null argument");
+    *count = ctx->sync_count;
+    *wait_ms = ctx->sync_ms;
+    return 0;
+}
+
 int swirl_ctx_timing_bytes(swirl_ctx* ctx, int slot, uint64_t* bytes) {
     SWIRL_REQUIRE(ctx && bytes, "null argument");
     SWIRL_REQUIRE(slot >= 0 && slot < SWIRL_T_SLOTS, "slot");

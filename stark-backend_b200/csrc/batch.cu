@@ -19,6 +19,8 @@
 // at a single row (the tail terms of the front-loaded batching).  The constant zerofier /
 // normalisation factors and all polynomial bookkeeping stay on the host with the transcript.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <type_traits>
@@ -724,6 +726,16 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         return 0;
     };
 
+    // SWIRL_TRACE=1: wall-clock per phase on stderr (each mark synchronises the stream first)
+    static const bool trace_on = getenv("SWIRL_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto mark = [&](const char* name) {
+        if (!trace_on) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[swirl trace] bc %-14s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     // ---- traces ------------------------------------------------------------------------------------
     std::vector<TraceState> T(n_airs);
     uint64_t total_interactions = 0;
@@ -787,6 +799,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         }
     }
 
+    mark("grind+setup");
     // ---- per trace: selector matrix, base parts, programs ---------------------------------------------
     for (size_t t = 0; t < n_airs; t++) {
         TraceState& s = T[t];
@@ -833,6 +846,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         }
     }
 
+    mark("programs");
     // ---- LogUp input layer + GKR -----------------------------------------------------------------------
     std::vector<Ext> xi;
     if (total_interactions > 0) {
@@ -898,6 +912,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
 #undef BC_LEAVES
             SWIRL_LAUNCH_CHECK(ctx);
         }
+        mark("leaves");
         uint32_t frac_sum[8];
         std::vector<uint32_t> xi_w((size_t)L * 4);
         SWIRL_TRY(swirl_gkr_fractional_sumcheck_padded(ctx, ts, leaves, n_leaves, alpha.c, L, 1, frac_sum, sec_claims, sec_gkr_polys,
@@ -910,6 +925,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     const int n_global = std::max(n_max, n_logup);
     while ((int)xi.size() != l_skip + n_global) xi.push_back(tr.sample_ext());
 
+    mark("gkr");
     // ---- batching randomness, weights, eq tables --------------------------------------------------------
     const Ext lambda = tr.sample_ext();
     for (size_t t = 0; t < n_airs; t++) {
@@ -970,6 +986,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         s.d_eq_xi = eq_tab[s.n_lift];
     }
 
+    mark("weights+eq");
     // ---- round 0 ---------------------------------------------------------------------------------------
     const uint32_t g = bb::to_mont(31), omega_skip = bb::two_adic_generator(l_skip);
     std::vector<uint32_t*> d_lde(D + 1, nullptr);  // per constraint degree d: [d * N][N] Lagrange table
@@ -1093,6 +1110,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         const size_t t = da.first, nv = (size_t)airs[t].constraint_degree * N * 12;
         for (size_t i = 0; i < nv; i++) h_r0[r0_off[t] + i] = bb::add(h_r0[r0_off[t] + i], h_r0c[da.second + i]);
     }
+    mark("round0 device");
     // host: per-trace s'_0 polynomials (cpu.rs:324-424)
     const size_t sp_0_deg = (size_t)D * (N - 1), s_0_deg = (size_t)(D + 1) * (N - 1);
     std::vector<std::vector<Ext>> sp0(3 * n_airs);  // [2t] numer, [2t+1] denom, [2n + t] zerocheck
@@ -1204,6 +1222,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     const Ext r_0 = r[0];
     Ext prev_s_eval = hp::horner(s_0, r_0);
 
+    mark("round0 host");
     // ---- fold_ple: all row parts of a trace into one EF buffer -------------------------------------------
     {
         LagrangeArgs la;
@@ -1255,6 +1274,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         eq_sharp_ns.push_back(res);
     }
 
+    mark("fold_ple");
     // ---- MLE rounds (mod.rs:314-395, cpu.rs:463-597) --------------------------------------------------------
     const int s_deg = D + 1;
     MleArgs* d_mle_descs = nullptr;
@@ -1444,6 +1464,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         eq_sharp_ns.push_back(ext_mul(eq_sharp_ns[round - 1], eq_r));
     }
 
+    mark("mle rounds");
     // ---- column openings (cpu.rs:644-694), observed common-main first (mod.rs:404-421) ------------------------
     std::vector<std::vector<uint32_t>> rows(n_airs);
     for (size_t t = 0; t < n_airs; t++) {
@@ -1484,5 +1505,6 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     for (size_t t = 0; t < n_airs; t++)
         for (size_t pt = 1; pt < openings[t].size(); pt++) observe_part(openings[t][pt], airs[t].need_rot != 0);
     for (size_t i = 0; i < r.size(); i++) memcpy(h_r + 4 * i, r[i].c, 16);
+    mark("openings");
     return 0;
 }

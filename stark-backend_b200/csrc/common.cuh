@@ -46,6 +46,9 @@ struct swirl_ctx {
     std::multimap<size_t, void*> arena_free;        // size -> idle block
     std::unordered_map<void*, size_t> arena_live;   // block handed out -> size
     size_t arena_bytes = 0;                         // idle + live
+    // host-side synchronisation statistics (swirl_ctx_sync_stats): how much of a proof is spent waiting on the stream
+    uint64_t sync_count = 0;
+    double sync_ms = 0;
 };
 
 // kernel families for swirl_ctx_timing_read
@@ -92,11 +95,12 @@ double stall_debug_ms();
 void stall_report(const char* what, const char* file, int line, double ms, size_t bytes);
 inline cudaError_t stream_sync(swirl_ctx* ctx, const char* file, int line) {
     const double lim = stall_debug_ms();
-    if (lim <= 0) return cudaStreamSynchronize(ctx->stream);
     const auto t0 = std::chrono::steady_clock::now();
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    if (ms > lim) stall_report("cudaStreamSynchronize", file, line, ms, 0);
+    ctx->sync_count++;
+    ctx->sync_ms += ms;
+    if (lim > 0 && ms > lim) stall_report("cudaStreamSynchronize", file, line, ms, 0);
     return e;
 }
 

@@ -12,6 +12,7 @@
 #pragma once
 #include "../../include/swirl_b200.h"
 #include "poseidon2.cuh"
+#include "poseidon2_host.hpp"
 
 namespace swirl {
 
@@ -20,7 +21,7 @@ struct Transcript {
     explicit Transcript(swirl_transcript* p) : t(p) {}
 
     void permute() {
-        p2::permute(t->state);
+        p2host::permute(t->state);  // AVX2 on the host (poseidon2_host.hpp), same function as p2::permute
         t->absorb_idx = 0;
         t->sample_idx = 8;
     }

@@ -77,3 +77,20 @@ def test_mont_helpers_roundtrip(oracle):
     x = np.array([0, 1, 2, 31, sb.P - 1, 123456789], dtype=np.uint64)
     assert np.array_equal(sb.to_mont(x), oracle.to_mont(x))
     assert np.array_equal(sb.from_mont(sb.to_mont(x)), x.astype(np.uint32))
+
+
+def test_host_transcript_matches_oracle(oracle):
+    """The product's host transcript (AVX2 Poseidon2 in csrc/poseidon2_host.hpp, duplex sponge of transcript.hpp) against
+    the oracle's scalar restatement of duplex_sponge.rs:60-83 over random observe / sample sequences."""
+    rng = np.random.default_rng(1)
+    ts, st = sb.Transcript(), np.zeros(18, np.uint32)
+    for _ in range(300):
+        w = oracle.random_field(rng, int(rng.integers(1, 40)))
+        ts.observe(w)
+        oracle.sponge_observe(st, w)
+        n = int(rng.integers(1, 12))
+        assert np.array_equal(ts.sample(n), oracle.sponge_sample(st, n))
+    edge = np.array([0, sb.P - 1, 1, sb.P - 2] * 4, dtype=np.uint32)  # extreme canonical words
+    ts.observe(sb.to_mont(edge))
+    oracle.sponge_observe(st, sb.to_mont(edge))
+    assert np.array_equal(ts.words(), st)
