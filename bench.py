@@ -32,7 +32,15 @@ import time
 
 import numpy as np
 
-os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+# rank 0 prints exactly one JSON line on stdout: NCCL (version banner at WARN and above), torchrun and any other library
+# write to file descriptor 1 as well, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+# saved original descriptor (emit_json)
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -202,7 +210,7 @@ def run_reference(args):
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = (1 << log_rows) * COLS / (ms / 1e3)
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "trace_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
@@ -210,7 +218,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "C++ restatement of the reference col-major prover (oracle/); its commit phase and PoW searches use all host threads, its sumcheck phases run on one"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # kernel families of swirl_ctx_timing_read with the algorithmic bytes of one launch on this workload
@@ -402,7 +410,7 @@ def run_swirl(args):
             out["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
                                    "seconds": dt,
                                    "note": "C++ restatement of the reference col-major prover (oracle/); its commit phase and PoW searches use all host threads, its sumcheck phases run on one"}
-        print(json.dumps(out))
+        emit_json(out)
     del trace_dev
     torch.cuda.synchronize()
     dev.close()

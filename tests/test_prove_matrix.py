@@ -1,0 +1,170 @@
+"""Whole proofs over the fixture x trace-height x l_skip grid of the reference's backend test suite
+(crates/backend-tests/src/lib.rs:181-247 e2e on Fib / Interactions / Cached / Preprocessed / SelfInteraction / Mixture at
+log-heights {10, 3, 2, 1, 0} around l_skip = 2; :254-375 parameter round trips with l_skip in {2, 3, 5, 6}; :642-1071
+optional AIRs): the oracle's proof must pass the oracle's verifier chain (CPU), and the CUDA proof must equal the
+oracle's word for word and byte for byte in the reference wire format (GPU)."""
+import zlib
+
+import numpy as np
+import pytest
+
+import airs as A
+import stark_backend_b200 as sb
+import verify_chain
+from stark_backend_b200 import codec
+
+
+def fib(h):
+    return lambda rng: [A.fibonacci(h)]
+
+
+def interactions(hs, hr):
+    return lambda rng: list(A.sender_receiver(hs, hr, rng))
+
+
+def self_interaction(h, cols=3, pairs=2):
+    return lambda rng: [A.benchmark(h, cols, cols, pairs, rng)]
+
+
+def parts(h):
+    return lambda rng: [A.with_parts(h, rng)]
+
+
+def mixture(hf, hb, hs, hr, hp):
+    def make(rng):
+        s, r = A.sender_receiver(hs, hr, rng)
+        return [A.fibonacci(hf), A.benchmark(hb, 4, 4, 2, rng), s, r, A.with_parts(hp, rng)]
+    return make
+
+
+# (name, l_skip, n_stack, make_airs, optional AIR ids)
+CASES = [
+    ("fib_h10", 2, 8, fib(10), ()),
+    ("fib_h3", 2, 3, fib(3), ()),
+    ("fib_h2", 2, 2, fib(2), ()),
+    ("fib_h1", 2, 2, fib(1), ()),
+    ("fib_h0", 2, 2, fib(0), ()),
+    ("interactions_h10_5", 2, 8, interactions(10, 5), ()),
+    ("interactions_h3_1", 2, 3, interactions(3, 1), ()),
+    ("interactions_h1_0", 2, 2, interactions(1, 0), ()),
+    ("self_interaction_h3", 2, 3, self_interaction(3), ()),
+    ("self_interaction_h0", 2, 2, self_interaction(0), ()),
+    ("cached_preprocessed_h4", 2, 3, parts(4), ()),
+    ("cached_preprocessed_h1", 2, 2, parts(1), ()),
+    ("mixture_l2", 2, 5, mixture(6, 4, 5, 2, 5), (1, 4)),
+    ("mixture_l3", 3, 4, mixture(6, 4, 5, 2, 5), (4,)),
+    ("mixture_l5", 5, 2, mixture(6, 4, 5, 2, 3), ()),
+    ("mixture_l6_short", 6, 1, mixture(5, 4, 5, 2, 3), (0,)),
+]
+
+
+def params_for(l_skip, n_stack):
+    m = l_skip + n_stack
+    k = 2 if m >= 4 else 1
+    rounds = 2 if m >= 2 * k + 1 else 1
+    whir = dict(k=k, num_queries=[5, 4][:rounds], mu_pow_bits=2, query_phase_pow_bits=3, folding_pow_bits=1)
+    return dict(l_skip=l_skip, n_stack=n_stack, log_blowup=1, D=3, logup_pow=2, whir=whir)
+
+
+def mont1(x):
+    return np.array([A.to_mont(x)], dtype=np.uint32)
+
+
+def oracle_prove(oracle, P, airs, is_required, vk):
+    order = sorted(range(len(airs)), key=lambda i: (-airs[i].height, i))
+    sa = [airs[i] for i in order]
+    commit1 = lambda m: oracle.stacked_commit(P["l_skip"], P["n_stack"], P["log_blowup"], P["whir"]["k"], [m], want_codeword=False)[0]
+    st = np.zeros(18, np.uint32)
+    oracle.sponge_observe(st, vk)
+    root = oracle.stacked_commit(P["l_skip"], P["n_stack"], P["log_blowup"], P["whir"]["k"], [a.common_main for a in sa],
+                                 want_codeword=False)[0]
+    oracle.sponge_observe(st, root)
+    pre_cached = []
+    for air_id, a in enumerate(airs):
+        if not is_required[air_id]:
+            oracle.sponge_observe(st, mont1(1))
+        prep_root = commit1(a.preprocessed) if a.preprocessed is not None else None
+        oracle.sponge_observe(st, prep_root if prep_root is not None else mont1(a.height.bit_length() - 1))
+        cached_roots = [commit1(c) for c in a.cached]
+        for c in cached_roots:
+            oracle.sponge_observe(st, c)
+        oracle.sponge_observe(st, a.public_values)
+        pre_cached.append((prep_root, cached_roots))
+    n_max = max(sa[0].height.bit_length() - 1 - P["l_skip"], 0)
+    bc, r = oracle.bc_prove(st, P["l_skip"], P["D"], P["logup_pow"], A.flatten(sa), len(sa), n_max)
+    commits = [[a.common_main + (a.need_rot,) for a in sa]]
+    for a in sa:
+        for m in ([a.preprocessed] if a.preprocessed is not None else []) + a.cached:
+            commits.append([m + (a.need_rot,)])
+    stacking, u, _ = oracle.stacked_reduction_prove(st, P["l_skip"], P["n_stack"], commits, r)
+    u_cube = [u[0]]
+    for _ in range(P["l_skip"] - 1):
+        u_cube.append(oracle.ef_mul(u_cube[-1], u_cube[-1]))
+    u_cube = np.array(u_cube + list(u[1:]), dtype=np.uint32)
+    mats = [oracle.stacked_matrix(P["l_skip"], P["n_stack"], [(v, h, w) for v, h, w, _ in c]) for c in commits]
+    _, whir = oracle.whir_prove(st, P["l_skip"], P["log_blowup"], P["whir"], mats, 1 << (P["l_skip"] + P["n_stack"]), u_cube)
+    lifted = lambda a: max(a.height, 1 << P["l_skip"])
+    total = sum(len(a.interactions) * lifted(a) for a in sa)
+    shape = codec.ProofShape(
+        l_skip=P["l_skip"], n_stack=P["n_stack"], log_blowup=P["log_blowup"], max_constraint_degree=P["D"], k_whir=P["whir"]["k"],
+        num_queries=P["whir"]["num_queries"],
+        airs=[codec.AirShape([a.common_main[2]] + ([a.preprocessed[2]] if a.preprocessed is not None else []) + [c[2] for c in a.cached],
+                             a.need_rot) for a in sa],
+        gkr_layers=total.bit_length() if total else 0, n_max=n_max, commit_widths=[w for _, w in mats],
+        trace_vdata=[(a.height.bit_length() - 1, pc[1]) for a, pc in zip(airs, pre_cached)],
+        public_values=[a.public_values for a in airs])
+    return dict(root=root, bc=bc, r=r, stacking=stacking, whir=whir, st=st, pre_cached=pre_cached, shape=shape)
+
+
+def make_case(case):
+    name, l_skip, n_stack, make, optional = case
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    airs = make(rng)
+    is_required = [i not in optional for i in range(len(airs))]
+    return params_for(l_skip, n_stack), airs, is_required
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_oracle_proof_passes_oracle_verifier(oracle, case):
+    P, airs, is_required = make_case(case)
+    vk = oracle.to_mont(np.arange(40, 48))
+    pr = oracle_prove(oracle, P, airs, is_required, vk)
+    ok, st = verify_chain.verify(oracle, P["l_skip"], P["n_stack"], P["log_blowup"], P["D"], P["logup_pow"], P["whir"], vk, airs,
+                                 is_required, pr["root"], pr["pre_cached"], pr["bc"], pr["stacking"], pr["whir"])
+    assert ok is True, st
+    assert np.array_equal(st, pr["st"])
+    data = codec.encode_proof(pr["shape"], pr["root"], pr["bc"], pr["stacking"], pr["whir"])
+    flat = codec.flat_to_montgomery(codec.decode_proof(data))
+    assert np.array_equal(flat["constraints_proof"], pr["bc"]) and np.array_equal(flat["whir_proof"], pr["whir"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_gpu_proof_equals_oracle_proof(dev, oracle, case):
+    P, airs, is_required = make_case(case)
+    vk = oracle.to_mont(np.arange(40, 48))
+    want = oracle_prove(oracle, P, airs, is_required, vk)
+    params = sb.SystemParams(P["l_skip"], P["n_stack"], P["log_blowup"], sb.WhirConfig(**P["whir"]), P["logup_pow"], P["D"])
+    dm = lambda m: sb.DeviceMatrix(dev.h2d(m[0]), m[1], m[2])
+
+    def committed(m):
+        mat = dm(m)
+        root, data = dev.commit(params.pcs(), [mat])
+        return sb.CommittedTraceData(root, mat, data)
+
+    per_air_pk, per_trace = [], []
+    for air_id, a in enumerate(airs):
+        prep = committed(a.preprocessed) if a.preprocessed is not None else None
+        cached = [committed(c) for c in a.cached]
+        per_air_pk.append(sb.AirProvingKey(is_required[air_id], prep))
+        ctx = sb.AirProvingContext(a.nodes, a.constraint_idx, a.interactions, a.constraint_degree, a.need_rot, dm(a.common_main),
+                                   a.public_values, [c.trace for c in cached], prep.trace if prep else None)
+        per_trace.append((air_id, ctx, cached))
+    coord = sb.Coordinator(dev, params)
+    proof = coord.prove(vk, per_air_pk, per_trace)
+    assert np.array_equal(proof.common_main_commit, want["root"])
+    assert np.array_equal(proof.constraints_proof, want["bc"])
+    assert np.array_equal(proof.stacking_proof, want["stacking"])
+    assert np.array_equal(proof.whir_proof, want["whir"])
+    assert np.array_equal(coord.transcript.words(), want["st"])
+    assert proof.encode() == codec.encode_proof(want["shape"], want["root"], want["bc"], want["stacking"], want["whir"])
