@@ -636,8 +636,10 @@ struct TraceState {
         Instr* d_code = nullptr;
         uint32_t n_instr = 0;
         int n_slots = 0;
+        bool zerocheck_only = false;  // only constraint roots: round 0 needs it on d - 1 cosets, not d
     };
     std::vector<Chunk> chunks;
+    Chunk whole[2];  // the constraint roots / the interaction roots as one program each (round 0 of tall traces)
     BasePart* d_parts = nullptr;
     uint32_t* d_sels = nullptr;
     uint32_t* d_weights = nullptr;
@@ -830,17 +832,40 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         SWIRL_TRY(compile_program(a, s.L, roots, &s.prog, BC_PREFETCH_VARS));
         SWIRL_TRY(upload(s.prog.code.data(), s.prog.code.size() * sizeof(Instr), (void**)&s.d_code));
         {
-            const size_t k_max = std::max<size_t>(1, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
-            const size_t K = std::max<size_t>(1, std::min(k_max, (roots.size() + BC_CHUNK_ROOTS - 1) / BC_CHUNK_ROOTS));
-            for (size_t k = 0; k < K; k++) {
-                const size_t r0 = roots.size() * k / K, r1 = roots.size() * (k + 1) / K;
-                if (r0 == r1 && !(K == 1)) continue;
+            // sub-programs never mix constraint and interaction roots: the zerocheck part of round 0 is needed on one
+            // coset fewer than the LogUp part (cpu.rs:338-361 vs :405-409)
+            const size_t nc = a.n_constraints;
+            auto compile_range = [&](size_t r0, size_t r1, bool zc, TraceState::Chunk* c) -> int {
                 Program pr;
                 SWIRL_TRY(compile_program(a, s.L, std::vector<Root>(roots.begin() + r0, roots.begin() + r1), &pr, BC_PREFETCH_VARS));
+                c->n_instr = (uint32_t)pr.code.size();
+                c->n_slots = pr.n_slots;
+                c->zerocheck_only = zc;
+                c->d_code = nullptr;  // an empty program is never dereferenced
+                if (!pr.code.empty()) SWIRL_TRY(upload(pr.code.data(), pr.code.size() * sizeof(Instr), (void**)&c->d_code));
+                return 0;
+            };
+            SWIRL_TRY(compile_range(0, nc, true, &s.whole[0]));
+            SWIRL_TRY(compile_range(nc, roots.size(), false, &s.whole[1]));
+            const size_t k_max = std::max<size_t>(2, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
+            const size_t K = std::max<size_t>(1, std::min(k_max, (roots.size() + BC_CHUNK_ROOTS - 1) / BC_CHUNK_ROOTS));
+            // K chunks shared between the two classes in proportion to their roots, at least one per non-empty class
+            size_t k_zc = nc ? std::max<size_t>(1, K * nc / std::max<size_t>(roots.size(), 1)) : 0;
+            size_t k_lg = roots.size() > nc ? std::max<size_t>(1, K - std::min(K, k_zc)) : 0;
+            if (k_zc + k_lg > k_max && k_zc > 1) k_zc = k_max - k_lg;
+            for (int cls = 0; cls < 2; cls++) {
+                const size_t base = cls == 0 ? 0 : nc, cnt = cls == 0 ? nc : roots.size() - nc, kk = cls == 0 ? k_zc : k_lg;
+                for (size_t k = 0; k < kk; k++) {
+                    const size_t r0 = base + cnt * k / kk, r1 = base + cnt * (k + 1) / kk;
+                    if (r0 == r1) continue;
+                    TraceState::Chunk c;
+                    SWIRL_TRY(compile_range(r0, r1, cls == 0, &c));
+                    s.chunks.push_back(c);
+                }
+            }
+            if (s.chunks.empty()) {  // no roots at all: one empty program keeps the descriptor logic uniform
                 TraceState::Chunk c;
-                c.n_instr = (uint32_t)pr.code.size();
-                c.n_slots = pr.n_slots;
-                SWIRL_TRY(upload(pr.code.data(), std::max<size_t>(pr.code.size(), 1) * sizeof(Instr), (void**)&c.d_code));
+                SWIRL_TRY(compile_range(0, 0, false, &c));
                 s.chunks.push_back(c);
             }
         }
@@ -1022,7 +1047,10 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     for (size_t t = 0; t < n_airs; t++)
         if (airs[t].constraint_degree) r0_alg_bytes += (uint64_t)T[t].lifted * 3 * 4 + (uint64_t)T[t].height * (T[t].total_cols - 3) / T[t].L.stride * 4;
     uint32_t* d_r0 = nullptr;
-    std::vector<std::pair<size_t, size_t>> r0_desc_air;  // (air, offset of the desc's result block)
+    struct R0Block {
+        size_t air, off, len;  // the desc's result block [off, off + len) adds into the first `len` words of its AIR's block
+    };
+    std::vector<R0Block> r0_desc_air;
     {
         std::vector<R0Args> descs;
         std::vector<uint16_t> block_air;
@@ -1031,15 +1059,15 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             TraceState& s = T[t];
             const int cd = (int)airs[t].constraint_degree;
             if (cd == 0) continue;
-            // enough hypercube points to fill the machine: one walk of the whole program per point (the per-point
-            // set-up is paid once); short traces take the sub-programs for their parallelism
-            std::vector<TraceState::Chunk> whole(1);
-            whole[0].d_code = s.d_code;
-            whole[0].n_instr = (uint32_t)s.prog.code.size();
-            whole[0].n_slots = s.prog.n_slots;
+            // enough hypercube points to fill the machine: one walk of the whole constraint / interaction program per
+            // point (the per-point set-up is paid once); short traces take the sub-programs for their parallelism
+            std::vector<TraceState::Chunk> whole{s.whole[0], s.whole[1]};
             const bool split = (size_t(1) << s.n_lift) < BC_R0_SPLIT_BELOW;
-            if (!split) max_slots_r0 = std::max(max_slots_r0, s.prog.n_slots);
             for (const auto& ch : split ? s.chunks : whole) {
+                // zerocheck: the quotient lives on d - 1 cosets; LogUp numerators / denominators need d
+                const int cosets = ch.zerocheck_only ? cd - 1 : cd;
+                if (cosets == 0 || ch.n_instr == 0) continue;
+                max_slots_r0 = std::max(max_slots_r0, ch.n_slots);
                 R0Args ra{};
                 ra.code = ch.d_code;
                 ra.n_instr = ch.n_instr;
@@ -1050,7 +1078,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 ra.eq_xi = s.d_eq_xi;
                 ra.l_skip = l_skip;
                 ra.n_lift = s.n_lift;
-                ra.P = (int)(cd * N);
+                ra.P = (int)(cosets * N);
                 const int G = std::max(1, BC_BLOCK / ra.P);
                 const size_t nx = size_t(1) << s.n_lift;
                 ra.x_per_block = G * (split && s.chunks.size() > 1 ? 16 : 4);
@@ -1058,7 +1086,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 ra.first_block = (uint32_t)block_air.size();
                 ra.partials = (uint32_t*)(uintptr_t)part_words;  // offsets for now, rebased below
                 ra.result = (uint32_t*)(uintptr_t)r0_words;
-                r0_desc_air.emplace_back(t, r0_words);
+                r0_desc_air.push_back(R0Block{t, r0_words, (size_t)ra.P * 12});
                 r0_words += (size_t)ra.P * 12;
                 part_words += (size_t)ra.n_blocks * ra.P * 12;
                 SWIRL_REQUIRE(descs.size() < 65535, "too many AIRs");
@@ -1106,10 +1134,8 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     std::vector<uint32_t> h_r0c(r0_words + 4), h_r0(r0_off[n_airs] + 4, 0);
     SWIRL_CUDA(cudaMemcpyAsync(h_r0c.data(), d_r0, r0_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
-    for (const auto& da : r0_desc_air) {
-        const size_t t = da.first, nv = (size_t)airs[t].constraint_degree * N * 12;
-        for (size_t i = 0; i < nv; i++) h_r0[r0_off[t] + i] = bb::add(h_r0[r0_off[t] + i], h_r0c[da.second + i]);
-    }
+    for (const R0Block& da : r0_desc_air)
+        for (size_t i = 0; i < da.len; i++) h_r0[r0_off[da.air] + i] = bb::add(h_r0[r0_off[da.air] + i], h_r0c[da.off + i]);
     mark("round0 device");
     // host: per-trace s'_0 polynomials (cpu.rs:324-424)
     const size_t sp_0_deg = (size_t)D * (N - 1), s_0_deg = (size_t)(D + 1) * (N - 1);
