@@ -98,6 +98,7 @@ struct RoundArgs {
     uint32_t* partials;
     unsigned int* ticket;
     uint32_t* result;  // 8 words: t(1) and the leading coefficient of t
+    uint32_t* last_rows;  // non-null in the last round of a layer: the final 2-row table (lo then hi, 8 EF) for the claims
 };
 
 template <bool FROM_TREE>
@@ -163,6 +164,13 @@ __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
             load_row<FROM_TREE>(a, 2 * y, c, lo);
             load_row<FROM_TREE>(a, 2 * y + 1, c, hi);
         }
+        if (a.last_rows && y == 0) {  // the host folds these two rows with the last challenge into the layer claims
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                st_ext(a.last_rows + 4 * k, lo[k]);
+                st_ext(a.last_rows + 16 + 4 * k, hi[k]);
+            }
+        }
         Ext E = ldg_ext(a.B + (y >> a.a_bits) * 4);
         if (a.a_bits) E = ext_mul(E, ldg_ext(a.A + (y & a_mask) * 4));
         accumulate(lo, hi, lambda, E, s);
@@ -173,27 +181,6 @@ __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
 #pragma unroll
         for (int k = 0; k < 4; k++) v[X * 4 + k] = s[X].c[k];
     grid_sum<8>(v, a.partials, a.ticket, a.result);
-}
-
-// Last fold of a layer: the 2-row table -> its single row = the four layer claims (p0, q0, p1, q1).
-template <bool FROM_TREE>
-__global__ void gkr_claims_kernel(RoundArgs a) {
-    if (threadIdx.x >= 4) return;
-    const Ext r = Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
-    const Ext c = Ext{{a.c[0], a.c[1], a.c[2], a.c[3]}};
-    Ext lo[4], hi[4];
-    load_row<FROM_TREE>(a, 0, c, lo);
-    load_row<FROM_TREE>(a, 1, c, hi);
-    Ext sel_lo = lo[0], sel_hi = hi[0];
-#pragma unroll
-    for (int k = 1; k < 4; k++)
-        if ((int)threadIdx.x == k) {
-            sel_lo = lo[k];
-            sel_hi = hi[k];
-        }
-    const Ext v = ext_lerp(sel_lo, sel_hi, r);
-#pragma unroll
-    for (int k = 0; k < 4; k++) a.result[threadIdx.x * 4 + k] = v.c[k];
 }
 
 static int round_grid(const swirl_ctx* ctx, size_t work_items) {
@@ -350,6 +337,7 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
                 a.B = suffix(eqB, nB, sr + 1 - v_split);
             }
             size_t y_tail;
+            a.last_rows = sr == round - 1 ? rs->d_result + 16 : nullptr;
             {
                 SwirlTimed timed(ctx, SWIRL_T_GKR);
                 if (sr == 0) {
@@ -421,20 +409,15 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             for (int k = 0; k < 4; k++) a.r[k] = r.c[k];
         }
         if (rc != 0) break;
-        // claims: fold the remaining 2-row table with the last challenge
-        if (round == 1) {
-            a.rows_in = rows_tree;
-            gkr_claims_kernel<true><<<1, 32, 0, ctx->stream>>>(a);
-        } else {
-            a.in = tab[cur];
-            a.in_stride = tab_stride[cur];
-            a.rows_in = rows;
-            gkr_claims_kernel<false><<<1, 32, 0, ctx->stream>>>(a);
+        // claims: the last round kernel left its 2-row table in mapped memory; fold it with the last challenge here
+        {
+            const Ext r_last = rho.back();
+            for (int k = 0; k < 4; k++) {
+                const Ext v = ext_lerp(ext_from_words(rs->h_result + 16 + 4 * k), ext_from_words(rs->h_result + 32 + 4 * k), r_last);
+                memcpy(h_claims + (size_t)round * 16 + 4 * k, v.c, 16);
+            }
         }
-        SWIRL_LAUNCH_CHECK(ctx);
-        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
         uint32_t* cl = h_claims + (size_t)round * 16;
-        memcpy(cl, rs->h_result, 64);
         for (int i = 0; i < 4; i++) {
             prev_claims[i] = ext_from_words(cl + 4 * i);
             tr.observe_ext(prev_claims[i]);
