@@ -224,10 +224,10 @@ def run_reference(args):
 # kernel families of swirl_ctx_timing_read with the algorithmic bytes of one launch on this workload
 # dram__bytes_read.sum + dram__bytes_write.sum of the family's largest launch, from the committed ncu --set full capture
 NCU_TRAFFIC = {
-    "leaf": {"bytes": 2149520000 + 11094784,
-             "note": "commit launch (2^21 x 256 codeword): 2.1495 GB read + 11.1 MB written vs 2.1517 GB algorithmic; "
-                     "profiles/r1h_bc_leaf_ncu.txt"},
-    "bc_round0": {"bytes": 1215332000 + 20032512, "note": "1.215 GB read + 20 MB written vs 1.086 GB algorithmic; profiles/r1m_round0_ncu.txt"},
+    "leaf": {"bytes": 2150351000 + 8435968,
+             "note": "commit launch (2^21 x 256 codeword): 2.1504 GB read + 8.4 MB written vs 2.1517 GB algorithmic; "
+                     "profiles/r1q_top_kernels_ncu.txt"},
+    "bc_round0": {"bytes": 1249211000 + 60525056, "note": "1.249 GB read + 61 MB written vs 1.086 GB algorithmic; profiles/r1q_top_kernels_ncu.txt"},
 }
 
 
@@ -392,7 +392,7 @@ def run_swirl(args):
                 "achieved_definition": "algorithmic bytes of all launches of the family in a step / their summed duration",
                 "timing": "CUDA events around every launch of the family, over a repeat of the K timed steps",
                 "note": "the dominant kernel is bound by the 32-bit integer multiplier pipe, not by HBM: ncu shows the fma-heavy pipe "
-                        "82 % busy and 1.2 % of peak DRAM throughput (profiles/r1h_bc_leaf_ncu.txt); see int_pipe and DESIGN.md section 4",
+                        "82 % busy and 1.2 % of peak DRAM throughput (profiles/r1q_top_kernels_ncu.txt); see int_pipe and DESIGN.md section 4",
                 "int_pipe": int_pipe_roofline(leaf_perms, fam["leaf"][2], clocks),
             },
             "phases_ms_per_step": {k: v[2] for k, v in fam.items()},
