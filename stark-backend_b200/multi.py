@@ -33,3 +33,93 @@ def max_over_ranks(value, device=None):
         t = t.to(device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- one commitment sharded over the ranks (commit row) ------------------------------------------------
+# The stacked matrix is split by columns: RS encoding is per column, so every rank encodes its own slice with no
+# communication.  Leaf hashing needs whole rows, so ONE exchange follows: rank r receives, for all W columns, the
+# 2^k strided row segments {q + t S : q in [r S/G, (r+1) S/G), t < 2^k} (S = query stride).  Laid out as
+# [column][t][q'] that is exactly a codeword of height B H / G with query stride S / G, so the ordinary Merkle commit
+# of the shard yields the global tree's node (level log2(S/G), index r); the G sub-roots are all-gathered (32 bytes
+# each) and the top log2 G levels are compressed redundantly on every rank.  The root equals the single-GPU root.
+# reference: MerkleTree::new / query layout, crates/stark-backend/src/prover/stacked_pcs.rs:413-485.
+
+
+def column_slice(width, world, rank):
+    """Contiguous stacked-column range [c0, c1) owned by `rank` (ragged when world does not divide width)."""
+    return width * rank // world, width * (rank + 1) // world
+
+
+def pack_codeword_slice(cw, log_rpq, world):
+    """cw: (Wl, N) tensor, the rank's columns of the codeword (column-major rows).  Returns the send buffer
+    (world, Wl, 2^k, S/world): for every destination rank the row segments of its queries."""
+    wl, n = cw.shape
+    s = n >> log_rpq
+    assert s % world == 0 and s >= world, "query stride must be a multiple of the number of ranks"
+    return cw.view(wl, 1 << log_rpq, world, s // world).permute(2, 0, 1, 3).contiguous()
+
+
+def exchange_rows(send, width, world, rank):
+    """all-to-all of the packed slices.  Returns the (width, N / world) row shard: all columns (in global order) of the
+    rows of this rank's queries."""
+    per_dest = send.shape[2] * send.shape[3]
+    in_split = [send.shape[1] * per_dest] * world
+    out_split = [(column_slice(width, world, r)[1] - column_slice(width, world, r)[0]) * per_dest for r in range(world)]
+    recv = send.new_empty(sum(out_split))
+    if world == 1:
+        recv.copy_(send.reshape(-1))
+    else:
+        dist.all_to_all_single(recv, send.reshape(-1), output_split_sizes=out_split, input_split_sizes=in_split)
+    return recv.view(width, per_dest)
+
+
+class DeviceCommitBackend:
+    """The three compute steps of the sharded commit on a B200Device (C-ABI primitives)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def rs_encode(self, trace_slice, height, wl, l_skip, log_blowup):
+        from .backend import DeviceMatrix
+
+        out = self.dev.rs_encode(DeviceMatrix(trace_slice, height, wl), l_skip, log_blowup)
+        self.dev.synchronize()
+        return out.buffer.view(wl, height << log_blowup)
+
+    def merkle_layers(self, shard, log_rpq):
+        """shard: (W, rows) tensor.  Returns the concatenated digest layers (device tensor) of its tree."""
+        from .backend import DeviceMatrix
+
+        w, rows = shard.shape
+        layers = self.dev.merkle_tree(DeviceMatrix(shard.reshape(-1), rows, w), log_rpq)
+        self.dev.synchronize()
+        return layers
+
+    def compress(self, left, right):
+        pairs = torch.cat([left.view(1, 8), right.view(1, 8)], dim=1).reshape(-1).contiguous()
+        out = self.dev.poseidon2_compress(pairs)
+        self.dev.synchronize()
+        return out.view(8)
+
+
+def sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_rpq, world, rank):
+    """Commit to a height x width matrix (already stacked: height = 2^(l_skip + n_stack)) whose columns
+    [column_slice(width, world, rank)) are in `trace_slice` (flat column-major tensor on the backend's device).
+    Returns dict(root (8 words, numpy), shard (W, N/world) rows of this rank's queries, layers (local digest layers),
+    sub_roots (world, 8))."""
+    c0, c1 = column_slice(width, world, rank)
+    cw = backend.rs_encode(trace_slice, height, c1 - c0, l_skip, log_blowup)
+    send = pack_codeword_slice(cw, log_rpq, world)
+    shard = exchange_rows(send, width, world, rank)
+    layers = backend.merkle_layers(shard, log_rpq)
+    sub_root = layers.view(-1)[-8:].clone()
+    if world > 1:
+        gathered = [torch.empty_like(sub_root) for _ in range(world)]
+        dist.all_gather(gathered, sub_root)
+    else:
+        gathered = [sub_root]
+    level = gathered
+    while len(level) > 1:  # the top log2(world) levels, identical on every rank
+        level = [backend.compress(level[2 * i], level[2 * i + 1]) for i in range(len(level) // 2)]
+    as_words = lambda t: t.detach().cpu().numpy().view(np.uint32).copy()
+    return dict(root=as_words(level[0]), shard=shard, layers=layers, sub_roots=np.stack([as_words(g) for g in gathered]))

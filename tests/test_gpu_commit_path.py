@@ -372,3 +372,17 @@ def test_fold_mle_matches_oracle(dev, oracle, log_n):
         t = dev.fold_mle(t, point[i])
     got = dev._d2h(t.data_ptr(), 4)
     assert np.array_equal(got, oracle.eval_mle_evals_at_point(evals, log_n, point))
+
+
+@pytest.mark.gpu
+def test_sharded_commit_device_backend_single_rank(dev, oracle):
+    """multi.sharded_commit through the C-ABI primitives (world size 1: no collective; the exchange / layout logic for
+    world size 2 is covered with gloo in tests/test_multi_rank.py, the NCCL run by tools/sharded_commit.py)."""
+    from stark_backend_b200 import multi
+
+    l_skip, n_stack, log_blowup, k, width = 3, 7, 1, 3, 9
+    H = 1 << (l_skip + n_stack)
+    full = oracle.random_field(np.random.default_rng(77), H * width)
+    res = multi.sharded_commit(multi.DeviceCommitBackend(dev), dev.h2d(full), H, width, l_skip, log_blowup, k, 1, 0)
+    root = oracle.stacked_commit(l_skip, n_stack, log_blowup, k, [(full, H, width)], want_codeword=False)[0]
+    assert np.array_equal(res["root"], root)

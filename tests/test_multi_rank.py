@@ -43,3 +43,81 @@ def test_world_size_2_gloo(tmp_path, oracle):
         assert np.array_equal(r0[8 * rank : 8 * rank + 8], oracle.stacked_commit(2, 4, 1, 2, [trace], want_codeword=False)[0])
     assert r0[16:18].view(np.float64)[0] == 11.0 and r1[16:18].view(np.float64)[0] == 11.0  # max over ranks
     assert list(r0[18:]) == [0, 2, 4] and list(r1[18:]) == [1, 3]
+
+
+class OracleCommitBackend:
+    """The compute steps of multi.sharded_commit done by the CPU oracle (CPU tensors, gloo): the test exercises the
+    exchange / index logic that the GPU path shares (DeviceCommitBackend does the same steps through the C ABI)."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def rs_encode(self, trace_slice, height, wl, l_skip, log_blowup):
+        import torch
+
+        cw = self.o.rs_code_matrix(l_skip, log_blowup, trace_slice.numpy().view(np.uint32), height, wl)
+        return torch.from_numpy(cw.view(np.int32)).view(wl, height << log_blowup)
+
+    def merkle_layers(self, shard, log_rpq):
+        import torch
+
+        w, rows = shard.shape
+        layers = self.o.merkle_tree(shard.numpy().view(np.uint32).reshape(-1), rows, w, 1 << log_rpq)
+        return torch.from_numpy(np.concatenate([l.reshape(-1) for l in layers]).view(np.int32))
+
+    def compress(self, left, right):
+        import torch
+
+        return torch.from_numpy(self.o.compress(left.numpy().view(np.uint32), right.numpy().view(np.uint32)).view(np.int32))
+
+
+def _sharded_worker(rank, world, port, out_dir, width):
+    import sys
+
+    import torch
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib
+    from stark_backend_b200 import multi
+
+    oracle = oracle_lib.Oracle(os.path.join(ROOT, "oracle", "libswirl_oracle.so"))
+    l_skip, n_stack, log_blowup, k = 2, 4, 1, 2
+    H = 1 << (l_skip + n_stack)
+    full = oracle.random_field(np.random.default_rng(7), H * width)  # the same matrix on every rank; each keeps its columns
+    c0, c1 = multi.column_slice(width, world, rank)
+    mine = torch.from_numpy(full[c0 * H:c1 * H].view(np.int32).copy())
+    res = multi.sharded_commit(OracleCommitBackend(oracle), mine, H, width, l_skip, log_blowup, k, world, rank)
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), np.concatenate([res["root"], res["shard"].numpy().view(np.uint32).reshape(-1)]))
+    dist.destroy_process_group()
+
+
+def _run_sharded(tmp_path, oracle, width):
+    world, port = 2, 31500 + (os.getpid() + width) % 2000
+    mp.spawn(_sharded_worker, args=(world, port, str(tmp_path), width), nprocs=world, join=True)
+    l_skip, n_stack, log_blowup, k = 2, 4, 1, 2
+    H = 1 << (l_skip + n_stack)
+    full = oracle.random_field(np.random.default_rng(7), H * width)
+    root, cw, layers, w = oracle.stacked_commit(l_skip, n_stack, log_blowup, k, [(full, H, width)])
+    assert w == width
+    N, S = H << log_blowup, (H << log_blowup) >> k
+    cw = cw.reshape(width, N)
+    for rank in range(world):
+        got = np.load(tmp_path / f"s{rank}.npy")
+        assert np.array_equal(got[:8], root), "sharded commitment differs from the single-device commitment"
+        shard = got[8:].reshape(width, N // world)
+        # the shard holds, for every column, the rows q + t S of the rank's queries q, as [t][q']
+        sg = S // world
+        for t in range(1 << k):
+            assert np.array_equal(shard[:, t * sg:(t + 1) * sg], cw[:, t * S + rank * sg:t * S + (rank + 1) * sg])
+
+
+def test_sharded_commit_world_size_2_gloo(tmp_path, oracle):
+    _run_sharded(tmp_path, oracle, 6)
+
+
+def test_sharded_commit_ragged_columns_world_size_2_gloo(tmp_path, oracle):
+    _run_sharded(tmp_path, oracle, 5)
