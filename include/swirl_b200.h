@@ -207,6 +207,15 @@ const uint32_t* swirl_pcs_layers(const swirl_pcs* pcs);         /* device, conca
  * Reference: StackedLayout::sorted_cols, prover/stacked_pcs.rs:34-41. */
 uint64_t swirl_pcs_layout(const swirl_pcs* pcs, uint64_t* h_out);
 
+/* Sharded commitment (one commitment over G ranks, column-sharded RS encode): the row exchange in front of the leaf
+ * hashing as one kernel over peer memory.  d_src: this rank's `cols` codeword columns (rows x cols, column-major, global
+ * columns [col_offset, col_offset + cols)); peer_bases[r]: rank r's shard buffer (W x rows/world words, column-major),
+ * mapped into this process (CUDA IPC / symmetric memory over NVLink).  Writes, for every destination r, the 2^k strided
+ * row segments of r's queries at [(col_offset + c) * rows/world + t * S/world + q'].  The caller synchronises the ranks
+ * before (buffers free) and after (data complete).  No reference counterpart (the reference commits on one GPU). */
+int swirl_scatter_rows_to_peers(swirl_ctx* ctx, const uint32_t* d_src, uint64_t rows, uint64_t cols, uint64_t col_offset,
+                                int log_rows_per_query, int world, void* const* peer_bases);
+
 /* Host-side layout computation only (StackedLayout::new, prover/stacked_pcs.rs:144-203). */
 int swirl_stacked_layout(int l_skip, int log_stacked_height, size_t n_mats, const uint64_t* widths,
                          const int32_t* log_heights, uint64_t* out_width, uint64_t* out_n,

@@ -309,3 +309,54 @@ int swirl_stacked_layout(int l_skip, int log_stacked_height, size_t n_mats, cons
 }
 
 }  // extern "C"
+
+
+// ---- sharded commitment: the row exchange as ONE kernel over NVLink peer memory ------------------------------------
+// After the per-column RS encode, rank `me` holds columns [col0, col0 + cols) of the codeword.  Rank r must hash the rows
+// q + t S of its queries q in [r S/G, (r+1) S/G) over ALL columns.  Instead of packing a send buffer and calling a
+// collective, every rank stores its elements straight into the peers' shard buffers (symmetric memory mapped over
+// NVLink / NVSwitch): dst[r][(col0 + c) * (N/G) + t * S/G + q'] = src[c * N + t * S + r * S/G + q'], 16 bytes per
+// thread, source reads coalesced along q' and so are the remote writes.  Reference counterpart: none (the reference is
+// single-GPU); layout = MerkleTree::new's query layout, prover/stacked_pcs.rs:413-485.
+namespace swirl {
+struct PeerPtrs {
+    uint32_t* p[16];
+};
+__global__ void __launch_bounds__(256)
+scatter_rows_peer_kernel(const uint32_t* __restrict__ src, size_t N, size_t cols, size_t col0, int log_rpq, int world, PeerPtrs peers) {
+    const size_t S = N >> log_rpq, Sg = S / world, shard_rows = N / world;
+    const size_t vec_per_seg = Sg >> 2;                              // uint4 per (column, t, destination) segment
+    const size_t total = cols * (size_t(1) << log_rpq) * world * vec_per_seg;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = i % vec_per_seg;
+        size_t rest = i / vec_per_seg;
+        const int r = (int)(rest % world);
+        rest /= world;
+        const size_t t = rest & ((size_t(1) << log_rpq) - 1), c = rest >> log_rpq;
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + c * N + t * S + (size_t)r * Sg) + v);
+        reinterpret_cast<uint4*>(peers.p[r] + (col0 + c) * shard_rows + t * Sg)[v] = x;
+    }
+}
+}  // namespace swirl
+
+extern "C" int swirl_scatter_rows_to_peers(swirl_ctx* ctx, const uint32_t* d_src, uint64_t rows, uint64_t cols, uint64_t col_offset,
+                                           int log_rows_per_query, int world, void* const* peer_bases) {
+    SWIRL_REQUIRE(ctx && d_src && peer_bases, "null argument");
+    SWIRL_REQUIRE(world >= 1 && world <= 16, "world size must be in [1, 16]");
+    SWIRL_REQUIRE(swirl::is_pow2(rows) && log_rows_per_query >= 0 && (rows >> log_rows_per_query) >= (uint64_t)world,
+                  "rows must be a power of two with at least one query per rank");
+    const uint64_t Sg = (rows >> log_rows_per_query) / world;
+    SWIRL_REQUIRE(((rows >> log_rows_per_query) % world) == 0 && (Sg & 3) == 0, "queries per rank must be a multiple of 4");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    swirl::PeerPtrs pp{};
+    for (int r = 0; r < world; r++) {
+        SWIRL_REQUIRE(peer_bases[r] && ((uintptr_t)peer_bases[r] & 15) == 0, "peer buffers must be 16-byte aligned");
+        pp.p[r] = (uint32_t*)peer_bases[r];
+    }
+    if (!cols) return 0;
+    const size_t total = cols * (size_t(1) << log_rows_per_query) * world * (Sg >> 2);
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+    swirl::scatter_rows_peer_kernel<<<grid, 256, 0, ctx->stream>>>(d_src, rows, cols, col_offset, log_rows_per_query, world, pp);
+    SWIRL_LAUNCH_CHECK(ctx);
+    return 0;
+}

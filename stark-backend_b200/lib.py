@@ -92,6 +92,7 @@ PROTOTYPES = {
     "swirl_transcript_sample_bits": (_i, [C.POINTER(TranscriptC), _i, C.POINTER(_u32)]),
     "swirl_transcript_check_witness": (_i, [C.POINTER(TranscriptC), _i, _u32, C.POINTER(_i)]),
     "swirl_transcript_grind": (_i, [_vp, C.POINTER(TranscriptC), _i, C.POINTER(_u32)]),
+    "swirl_scatter_rows_to_peers": (_i, [_vp, _vp, _u64, _u64, _u64, _i, _i, _vp]),
     "swirl_fold_mle": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "swirl_gkr_fractional_sumcheck": (_i, [_vp, C.POINTER(TranscriptC), _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "swirl_gkr_fractional_sumcheck_padded": (_i, [_vp, C.POINTER(TranscriptC), _vp, _u64, _vp, _i, _i, _vp, _vp, _vp, _vp]),

@@ -102,15 +102,55 @@ class DeviceCommitBackend:
         return out.view(8)
 
 
-def sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_rpq, world, rank):
+class PeerExchange:
+    """Row exchange of the sharded commit over NVLink peer memory instead of a collective: every rank owns a shard buffer
+    in torch symmetric memory (mapped into all ranks), and one kernel of the library (`swirl_scatter_rows_to_peers`)
+    stores this rank's codeword columns straight into the peers' buffers.  Barriers on the symmetric-memory signal pads
+    fence the buffers before and after."""
+
+    def __init__(self, dev, width, rows, world, rank):
+        import ctypes as C
+
+        self.dev, self.width, self.rows, self.world, self.rank = dev, width, rows, world, rank
+        n = width * (rows // world)
+        if world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.buf = symm_mem.empty(n, dtype=torch.int32, device=dev.torch_device)
+            self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        else:
+            self.buf, self.hdl = torch.empty(n, dtype=torch.int32, device=dev.torch_device), None
+            ptrs = [self.buf.data_ptr()]
+        self.ptrs = (C.c_void_p * world)(*ptrs)
+
+    def exchange(self, cw, col0, log_rpq):
+        """cw: (Wl, rows) tensor of this rank's codeword columns.  Returns the (width, rows / world) shard."""
+        from .lib import check
+
+        if self.hdl is not None:
+            self.hdl.barrier()  # every rank is done reading its shard of the previous commitment
+        torch.cuda.current_stream().synchronize()
+        check(self.dev.lib.swirl_scatter_rows_to_peers(self.dev.ctx, cw.data_ptr(), self.rows, cw.shape[0], col0, log_rpq, self.world,
+                                                       self.ptrs))
+        self.dev.synchronize()
+        if self.hdl is not None:
+            self.hdl.barrier()  # all peers have finished writing into this rank's shard
+        return self.buf.view(self.width, self.rows // self.world)
+
+
+def sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_rpq, world, rank, peer_exchange=None):
     """Commit to a height x width matrix (already stacked: height = 2^(l_skip + n_stack)) whose columns
     [column_slice(width, world, rank)) are in `trace_slice` (flat column-major tensor on the backend's device).
     Returns dict(root (8 words, numpy), shard (W, N/world) rows of this rank's queries, layers (local digest layers),
     sub_roots (world, 8))."""
     c0, c1 = column_slice(width, world, rank)
     cw = backend.rs_encode(trace_slice, height, c1 - c0, l_skip, log_blowup)
-    send = pack_codeword_slice(cw, log_rpq, world)
-    shard = exchange_rows(send, width, world, rank)
+    if peer_exchange is not None:  # one kernel storing into the peers' shard buffers over NVLink
+        shard = peer_exchange.exchange(cw, c0, log_rpq)
+    else:                          # pack + all_to_all_single (also the CPU / gloo path of the tests)
+        send = pack_codeword_slice(cw, log_rpq, world)
+        shard = exchange_rows(send, width, world, rank)
     layers = backend.merkle_layers(shard, log_rpq)
     sub_root = layers.view(-1)[-8:].clone()
     if world > 1:

@@ -386,3 +386,34 @@ def test_sharded_commit_device_backend_single_rank(dev, oracle):
     res = multi.sharded_commit(multi.DeviceCommitBackend(dev), dev.h2d(full), H, width, l_skip, log_blowup, k, 1, 0)
     root = oracle.stacked_commit(l_skip, n_stack, log_blowup, k, [(full, H, width)], want_codeword=False)[0]
     assert np.array_equal(res["root"], root)
+    # the same with the row exchange done by swirl_scatter_rows_to_peers (the only peer is this rank)
+    px = multi.PeerExchange(dev, width, H << log_blowup, 1, 0)
+    res2 = multi.sharded_commit(multi.DeviceCommitBackend(dev), dev.h2d(full), H, width, l_skip, log_blowup, k, 1, 0, peer_exchange=px)
+    assert np.array_equal(res2["root"], root)
+    assert np.array_equal(res2["shard"].cpu().numpy(), res["shard"].cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_scatter_rows_to_peers_layout(dev, oracle):
+    """swirl_scatter_rows_to_peers with 4 destination buffers on one device: every buffer must hold, for all columns, the rows
+    q + t S of its quarter of the queries as [column][t][q'] (the layout multi.pack_codeword_slice + all-to-all produce)."""
+    import ctypes as C
+
+    import torch
+
+    from stark_backend_b200 import multi
+    from stark_backend_b200.lib import check
+
+    rows, cols, col0, width, k, world = 1 << 9, 3, 2, 7, 2, 4
+    src = oracle.random_field(np.random.default_rng(5), rows * cols)
+    bufs = [torch.zeros(width * (rows // world), dtype=torch.int32, device=dev.torch_device) for _ in range(world)]
+    ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    d_src = dev.h2d(src)
+    torch.cuda.synchronize()
+    check(dev.lib.swirl_scatter_rows_to_peers(dev.ctx, d_src.data_ptr(), rows, cols, col0, k, world, ptrs))
+    dev.synchronize()
+    want = multi.pack_codeword_slice(torch.from_numpy(src.view(np.int32)).view(cols, rows), k, world)  # (world, cols, 2^k, Sg)
+    for r in range(world):
+        got = bufs[r].cpu().view(width, rows // world)
+        assert torch.equal(got[col0:col0 + cols], want[r].reshape(cols, -1))
+        assert int(got[:col0].abs().sum()) == 0 and int(got[col0 + cols:].abs().sum()) == 0
