@@ -47,10 +47,40 @@ for it in range(6):
     if it < 5:
         del res
 ms = multi.max_over_ranks(min(times[1:]), dev.torch_device)
+
+# size-independent check on every rank: two of its own queries hash up to the global root (rows from the shard, path =
+# local subtree path + the top levels over the gathered sub-roots), recomputed with the CPU oracle
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib
+oracle = oracle_lib.Oracle(os.path.join(ROOT, "oracle", "libswirl_oracle.so"))
+N = H << LOG_BLOWUP
+Sg = (N >> K) // world
+shard = res["shard"]
+paths_ok = True
+for ql in (0, Sg - 1):
+    rows = dev.matrix_open_rows(shard.data_ptr(), N // world, cols, Sg, K, [ql])[0]
+    path = dev.merkle_query_proofs(res["layers"].data_ptr(), Sg, [ql])[0]
+    nodes = [oracle.hash_slice(rows[t]) for t in range(1 << K)]
+    while len(nodes) > 1:
+        nodes = [oracle.compress(nodes[2 * j], nodes[2 * j + 1]) for j in range(len(nodes) // 2)]
+    cur, i = nodes[0], ql
+    for sib in path:
+        cur = oracle.compress(cur, sib) if i % 2 == 0 else oracle.compress(sib, cur)
+        i >>= 1
+    level, i = [res["sub_roots"][r] for r in range(world)], rank
+    while len(level) > 1:
+        cur = oracle.compress(cur, level[i ^ 1]) if i % 2 == 0 else oracle.compress(level[i ^ 1], cur)
+        level = [oracle.compress(level[2 * j], level[2 * j + 1]) for j in range(len(level) // 2)]
+        i >>= 1
+    paths_ok &= bool(np.array_equal(cur, res["root"]))
+paths_ok = multi.max_over_ranks(0.0 if paths_ok else 1.0, dev.torch_device) == 0.0
 out = {"config": f"sharded commit 2^{log_rows} x {cols}, blowup 2, k_whir 4", "n_gpus": world, "exchange": "peer-memory scatter kernel (NVLink stores)" if use_peer else "pack + NCCL all_to_all_single",
        "sharded_commit_ms": ms,
        "cells_per_s": H * cols / (ms / 1e3)}
-if rank == 0:
+out["merkle_paths_verify_on_every_rank"] = paths_ok
+if rank == 0 and H * cols * 4 * 4 > 150e9:  # the whole matrix + codeword do not fit one GPU: no single-GPU comparison
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
+elif rank == 0:
     full = torch.cat([column(c) for c in range(cols)])
     params = sb.PcsParams(L_SKIP, log_rows - L_SKIP, LOG_BLOWUP, K)
     single = []
