@@ -360,6 +360,15 @@ def run_swirl(args):
     assert all(np.array_equal(a, b) for a, b in zip(roots, roots_e2e)), "device and host paths disagree"
     assert np.array_equal(proof.words(), proof_e2e.words()), "device and host paths produce different proofs"
 
+    # N > 1 also measures ONE commitment of the same shape sharded over the ranks (SURVEY section 8e commit row): column-sharded
+    # RS encode, row exchange by one kernel over NVLink peer memory, local fused leaf hash, all-gather of 32-byte sub-roots
+    sharded = None
+    if world > 1:
+        try:
+            sharded = multi.sharded_commit_benchmark(dev, LOG_ROWS, COLS, L_SKIP, LOG_BLOWUP, K_WHIR, world, rank)
+        except Exception as e:  # the replica measurement above stands on its own
+            sharded = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         pk_, pk_kind = peaks()
         # per family: avg ms per launch, launches per step, ms per step, algorithmic bytes per step (accounted by the
@@ -399,6 +408,7 @@ def run_swirl(args):
             "phases_note": "kernel families with CUDA-event spans only; GKR tree/leaves, stacked reduction, WHIR and host latency are the rest",
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
                     "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk_["hbm_gbs"] if lde_ms else 0.0},
+            "sharded_commit": sharded,
             "proof_bytes": len(proof.encode()),  # Proof::encode_to_vec() wire format (stark-backend_b200/codec.py)
             "host_step_ms": stalls.pop("step_ms"),
             "remeasured_after_host_stall": stalls or None,

@@ -163,3 +163,49 @@ def sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_
         level = [backend.compress(level[2 * i], level[2 * i + 1]) for i in range(len(level) // 2)]
     as_words = lambda t: t.detach().cpu().numpy().view(np.uint32).copy()
     return dict(root=as_words(level[0]), shard=shard, layers=layers, sub_roots=np.stack([as_words(g) for g in gathered]))
+
+
+def sharded_commit_benchmark(dev, log_rows, cols, l_skip, log_blowup, log_rpq, world, rank, reps=5, compare_single=True):
+    """Times one commitment of a 2^log_rows x cols matrix sharded over the ranks (peer-memory exchange) on the device
+    (max over ranks) and, on rank 0, the same commitment on one GPU; returns a dict for the bench line."""
+    from .backend import DeviceMatrix, PcsParams
+
+    h = 1 << log_rows
+
+    def column(c):  # column c of the common matrix, identical on every rank
+        g = torch.Generator(device=dev.torch_device).manual_seed(1000 + c)
+        return torch.randint(0, 0x78000001, (h,), dtype=torch.int32, device=dev.torch_device, generator=g)
+
+    c0, c1 = column_slice(cols, world, rank)
+    mine = torch.cat([column(c) for c in range(c0, c1)])
+    backend, px = DeviceCommitBackend(dev), PeerExchange(dev, cols, h << log_blowup, world, rank)
+    stream, times, res = dev.torch_stream(), [], None
+    for _ in range(reps + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a.record(stream)
+        res = sharded_commit(backend, mine, h, cols, l_skip, log_blowup, log_rpq, world, rank, peer_exchange=px)
+        torch.cuda.synchronize()
+        b.record(stream)
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = max_over_ranks(min(times[1:]), dev.torch_device)
+    out = {"workload": f"one commitment of 2^{log_rows} x {cols} sharded by columns over {world} GPUs", "ms": ms,
+           "cells_per_s": h * cols / (ms / 1e3), "exchange": "peer-memory scatter kernel over NVLink (symmetric memory)"}
+    if compare_single and rank == 0:
+        full = torch.cat([column(c) for c in range(cols)])
+        single = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            root, pcs = dev.commit(PcsParams(l_skip, log_rows - l_skip, log_blowup, log_rpq), [DeviceMatrix(full, h, cols)])
+            dev.synchronize()
+            b.record(stream)
+            torch.cuda.synchronize()
+            single.append(a.elapsed_time(b))
+            pcs.free()
+        out.update(single_gpu_ms=min(single), speedup=min(single) / ms, roots_equal=bool(np.array_equal(root, res["root"])))
+    return out
