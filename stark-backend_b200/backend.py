@@ -414,8 +414,11 @@ class B200Device:
         return out
 
     def _sync_torch(self):
-        # torch work on its current stream must be visible to the ctx stream
-        torch.cuda.current_stream(self.torch_device).synchronize()
+        # torch work on its current stream must be visible to the ctx stream (nothing to do when torch is already
+        # running on the ctx stream: `with torch.cuda.stream(dev.torch_stream())`)
+        cur = torch.cuda.current_stream(self.torch_device)
+        if cur.cuda_stream != self.stream_ptr():
+            cur.synchronize()
 
     # -- kernel-level primitives ------------------------------------------------------------
     def poseidon2_permute(self, states):

@@ -79,11 +79,15 @@ class DeviceCommitBackend:
     def __init__(self, dev):
         self.dev = dev
 
+    def stream_scope(self):
+        """torch ops, NCCL / symmetric-memory barriers and the library's kernels all run on the context's stream inside this
+        scope, so the steps of a sharded commit are ordered on the device and need no host synchronisation in between."""
+        return torch.cuda.stream(self.dev.torch_stream())
+
     def rs_encode(self, trace_slice, height, wl, l_skip, log_blowup):
         from .backend import DeviceMatrix
 
         out = self.dev.rs_encode(DeviceMatrix(trace_slice, height, wl), l_skip, log_blowup)
-        self.dev.synchronize()
         return out.buffer.view(wl, height << log_blowup)
 
     def merkle_layers(self, shard, log_rpq):
@@ -91,15 +95,11 @@ class DeviceCommitBackend:
         from .backend import DeviceMatrix
 
         w, rows = shard.shape
-        layers = self.dev.merkle_tree(DeviceMatrix(shard.reshape(-1), rows, w), log_rpq)
-        self.dev.synchronize()
-        return layers
+        return self.dev.merkle_tree(DeviceMatrix(shard.reshape(-1), rows, w), log_rpq)
 
-    def compress(self, left, right):
-        pairs = torch.cat([left.view(1, 8), right.view(1, 8)], dim=1).reshape(-1).contiguous()
-        out = self.dev.poseidon2_compress(pairs)
-        self.dev.synchronize()
-        return out.view(8)
+    def compress_level(self, level):
+        """level: (n, 8) digests -> (n / 2, 8): adjacent pairs compressed in one launch."""
+        return self.dev.poseidon2_compress(level.reshape(-1).contiguous()).view(-1, 8)
 
 
 class PeerExchange:
@@ -130,11 +130,12 @@ class PeerExchange:
 
         if self.hdl is not None:
             self.hdl.barrier()  # every rank is done reading its shard of the previous commitment
-        torch.cuda.current_stream().synchronize()
+        self.dev._sync_torch()
         check(self.dev.lib.swirl_scatter_rows_to_peers(self.dev.ctx, cw.data_ptr(), self.rows, cw.shape[0], col0, log_rpq, self.world,
                                                        self.ptrs))
-        self.dev.synchronize()
         if self.hdl is not None:
+            if torch.cuda.current_stream(self.dev.torch_device).cuda_stream != self.dev.stream_ptr():
+                self.dev.synchronize()  # the barrier below is enqueued on torch's stream, the scatter ran on the library's
             self.hdl.barrier()  # all peers have finished writing into this rank's shard
         return self.buf.view(self.width, self.rows // self.world)
 
@@ -144,6 +145,14 @@ def sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_
     [column_slice(width, world, rank)) are in `trace_slice` (flat column-major tensor on the backend's device).
     Returns dict(root (8 words, numpy), shard (W, N/world) rows of this rank's queries, layers (local digest layers),
     sub_roots (world, 8))."""
+    import contextlib
+
+    scope = backend.stream_scope() if hasattr(backend, "stream_scope") else contextlib.nullcontext()
+    with scope:
+        return _sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_rpq, world, rank, peer_exchange)
+
+
+def _sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_rpq, world, rank, peer_exchange):
     c0, c1 = column_slice(width, world, rank)
     cw = backend.rs_encode(trace_slice, height, c1 - c0, l_skip, log_blowup)
     if peer_exchange is not None:  # one kernel storing into the peers' shard buffers over NVLink
@@ -153,16 +162,16 @@ def sharded_commit(backend, trace_slice, height, width, l_skip, log_blowup, log_
         shard = exchange_rows(send, width, world, rank)
     layers = backend.merkle_layers(shard, log_rpq)
     sub_root = layers.view(-1)[-8:].clone()
+    gathered = sub_root.new_empty(world * 8)
     if world > 1:
-        gathered = [torch.empty_like(sub_root) for _ in range(world)]
-        dist.all_gather(gathered, sub_root)
+        dist.all_gather_into_tensor(gathered, sub_root)
     else:
-        gathered = [sub_root]
-    level = gathered
-    while len(level) > 1:  # the top log2(world) levels, identical on every rank
-        level = [backend.compress(level[2 * i], level[2 * i + 1]) for i in range(len(level) // 2)]
+        gathered.copy_(sub_root)
+    level = gathered.view(world, 8)
+    while level.shape[0] > 1:  # the top log2(world) levels, identical on every rank
+        level = backend.compress_level(level)
     as_words = lambda t: t.detach().cpu().numpy().view(np.uint32).copy()
-    return dict(root=as_words(level[0]), shard=shard, layers=layers, sub_roots=np.stack([as_words(g) for g in gathered]))
+    return dict(root=as_words(level.reshape(-1)), shard=shard, layers=layers, sub_roots=as_words(gathered).reshape(world, 8))
 
 
 def sharded_commit_benchmark(dev, log_rows, cols, l_skip, log_blowup, log_rpq, world, rank, reps=5, compare_single=True):

@@ -65,10 +65,12 @@ class OracleCommitBackend:
         layers = self.o.merkle_tree(shard.numpy().view(np.uint32).reshape(-1), rows, w, 1 << log_rpq)
         return torch.from_numpy(np.concatenate([l.reshape(-1) for l in layers]).view(np.int32))
 
-    def compress(self, left, right):
+    def compress_level(self, level):
         import torch
 
-        return torch.from_numpy(self.o.compress(left.numpy().view(np.uint32), right.numpy().view(np.uint32)).view(np.int32))
+        lv = level.numpy().view(np.uint32).reshape(-1, 8)
+        out = np.stack([self.o.compress(lv[2 * i], lv[2 * i + 1]) for i in range(len(lv) // 2)])
+        return torch.from_numpy(out.view(np.int32))
 
 
 def _sharded_worker(rank, world, port, out_dir, width):
