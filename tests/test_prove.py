@@ -114,3 +114,51 @@ def test_gpu_whole_proof_matches_oracle(dev, oracle):
     assert np.array_equal(proof.stacking_proof, want["stacking"])
     assert np.array_equal(proof.whir_proof, want["whir"])
     assert np.array_equal(coord.transcript.words(), want["st"])
+
+
+@pytest.mark.gpu
+def test_gpu_concurrent_coordinators_on_threads(oracle):
+    """Coordinators on separate OS threads, each with its own library context and stream, prove at the same time and every
+    proof equals the oracle's (the reference runs concurrent provers the same way: cuda-backend/examples/keccakf.rs with
+    NUM_THREADS=3 in CI)."""
+    import threading
+
+    airs, order = fixture_airs(2)
+    is_required = [True, True, True, True, False]
+    vk = oracle.to_mont(np.arange(100, 108))
+    want = oracle_prove(oracle, airs, order, is_required, vk)
+    params = sb.SystemParams(L_SKIP, N_STACK, LOG_BLOWUP, sb.WhirConfig(**WHIR), LOGUP_POW, D)
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            dev = sb.B200Device(0)
+            dm = lambda m: sb.DeviceMatrix(dev.h2d(m[0]), m[1], m[2])
+
+            def committed(m):
+                mat = dm(m)
+                root, data = dev.commit(params.pcs(), [mat])
+                return sb.CommittedTraceData(root, mat, data)
+
+            for rep in range(3):
+                per_air_pk, per_trace = [], []
+                for air_id, a in enumerate(airs):
+                    prep = committed(a.preprocessed) if a.preprocessed is not None else None
+                    cached = [committed(c) for c in a.cached]
+                    per_air_pk.append(sb.AirProvingKey(is_required[air_id], prep))
+                    ctx = sb.AirProvingContext(a.nodes, a.constraint_idx, a.interactions, a.constraint_degree, a.need_rot,
+                                               dm(a.common_main), a.public_values, [c.trace for c in cached], prep.trace if prep else None)
+                    per_trace.append((air_id, ctx, cached))
+                results[(tid, rep)] = sb.Coordinator(dev, params).prove(vk, per_air_pk, per_trace).words()
+            dev.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    expect = np.concatenate([want["root"], want["bc"], want["stacking"], want["whir"]])
+    assert len(results) == 9 and all(np.array_equal(w, expect) for w in results.values())
