@@ -24,6 +24,7 @@
 // t(1), t(2), t(3) (the eq-free inner sums) leave the device through one grid-wide reduction per
 // round (ext.cuh) into mapped pinned memory; the host transcript (transcript.hpp) turns them into
 // s(1), s(2), s(3) and the next challenge.
+#include <array>
 #include <cstring>
 #include <vector>
 
@@ -40,6 +41,7 @@ using bb::ext_mul_base;
 using bb::ext_sub;
 
 constexpr int GKR_BLOCK = 256;
+constexpr int GKR_HOST_LOG = 4;  // sumcheck rounds on tables of <= 2^4 rows run on the host (a kernel round trip costs more)
 
 // parent[i] = child[2i] + child[2i+1] (projective fraction addition) for the stored prefix of a layer;
 // parents whose children lie in the constant tail are the constant (0, c_parent).
@@ -98,7 +100,8 @@ struct RoundArgs {
     uint32_t* partials;
     unsigned int* ticket;
     uint32_t* result;  // 8 words: t(1) and the leading coefficient of t
-    uint32_t* last_rows;  // non-null in the last round of a layer: the final 2-row table (lo then hi, 8 EF) for the claims
+    uint32_t* last_rows;  // non-null in the last device round of a layer: this round's whole table (rows 2y = lo, 2y+1 = hi,
+                          // 4 EF each, at most 32 rows) for the host, which finishes the layer
 };
 
 template <bool FROM_TREE>
@@ -124,7 +127,7 @@ __device__ __forceinline__ void load_row(const RoundArgs& a, size_t x, const Ext
 // t(X) = sum_y E[y] * inner(X, y), inner = p0 q1 + p1 q0 + lambda q0 q1 = p0 q1 + q0 (p1 + lambda q1) with every
 // factor linear in X.  Two values are enough: t(0) follows on the host from the sumcheck identity s(0) + s(1) = claim,
 // so the round costs 8 extension multiplications per pair instead of 12.
-__device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ext (&hi)[4], const Ext& lambda, const Ext& E, Ext (&s)[2]) {
+__host__ __device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ext (&hi)[4], const Ext& lambda, const Ext& E, Ext (&s)[2]) {
     const Ext d0 = ext_sub(hi[0], lo[0]), d1 = ext_sub(hi[1], lo[1]), d2 = ext_sub(hi[2], lo[2]), d3 = ext_sub(hi[3], lo[3]);
     const Ext w_hi = ext_add(hi[2], ext_mul(lambda, hi[3])), dw = ext_add(d2, ext_mul(lambda, d3));
     const Ext at1 = ext_add(ext_mul(hi[0], hi[3]), ext_mul(hi[1], w_hi));
@@ -164,11 +167,11 @@ __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
             load_row<FROM_TREE>(a, 2 * y, c, lo);
             load_row<FROM_TREE>(a, 2 * y + 1, c, hi);
         }
-        if (a.last_rows && y == 0) {  // the host folds these two rows with the last challenge into the layer claims
+        if (a.last_rows) {  // the host finishes the layer from this (small) table
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                st_ext(a.last_rows + 4 * k, lo[k]);
-                st_ext(a.last_rows + 16 + 4 * k, hi[k]);
+                st_ext(a.last_rows + (2 * y) * 16 + 4 * k, lo[k]);
+                st_ext(a.last_rows + (2 * y + 1) * 16 + 4 * k, hi[k]);
             }
         }
         Ext E = ldg_ext(a.B + (y >> a.a_bits) * 4);
@@ -250,10 +253,16 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             layer_ptr(k + 1), tree + off[k] * 8, S[k], S[k + 1], cst[k]);
         SWIRL_LAUNCH_CHECK(ctx);
     }
-    // root (layer 0) + layer 1 -> host
+    // root (layer 0) + layer 1 -> host, and the stored nodes of the layers whose sumchecks run entirely on the host
+    // (tables of at most HOST_ROWS rows)
     uint32_t top[24];
     SWIRL_CUDA(cudaMemcpyAsync(top, layer_ptr(0), 32, cudaMemcpyDeviceToHost, ctx->stream));
     SWIRL_CUDA(cudaMemcpyAsync(top + 8, layer_ptr(1), 64, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<std::vector<uint32_t>> top_layers(std::min(n, GKR_HOST_LOG + 1) + 1);
+    for (int k = 2; k < (int)top_layers.size(); k++) {
+        top_layers[k].resize(S[k] * 8);
+        SWIRL_CUDA(cudaMemcpyAsync(top_layers[k].data(), layer_ptr(k), S[k] * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     memcpy(h_frac_sum, top, 32);
     int rc = 0;
@@ -325,61 +334,36 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
         Ext claim = ext_add(ext_lerp(prev_claims[0], prev_claims[2], mu_prev), ext_mul(lambda, ext_lerp(prev_claims[1], prev_claims[3], mu_prev)));
         size_t rows = rows_tree;  // stored rows of the table the next kernel reads
         int cur = 0;
-        for (int sr = 0; sr < round; sr++) {
-            // tables of the remaining variables [sr+1, round)
-            if (sr + 1 < v_split) {
-                a.a_bits = v_split - 1 - sr;
-                a.A = suffix(eqA, nA, sr);
-                a.B = suffix(eqB, nB, 0);
-            } else {
-                a.a_bits = 0;
-                a.A = nullptr;
-                a.B = suffix(eqB, nB, sr + 1 - v_split);
-            }
-            size_t y_tail;
-            a.last_rows = sr == round - 1 ? rs->d_result + 16 : nullptr;
-            {
-                SwirlTimed timed(ctx, SWIRL_T_GKR);
-                if (sr == 0) {
-                    a.rows_in = rows_tree;
-                    a.ny = y_tail = (rows_tree + 1) / 2;
-                    gkr_round_kernel<true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
-                } else if (sr == 1) {
-                    a.rows_in = rows_tree;
-                    a.ny = y_tail = (rows_tree + 3) / 4;
-                    a.out = tab[0];
-                    a.out_stride = tab_stride[0];
-                    gkr_round_kernel<true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
-                    rows = 2 * a.ny;
-                    cur = 0;
-                } else {
-                    a.in = tab[cur];
-                    a.in_stride = tab_stride[cur];
-                    a.rows_in = rows;
-                    a.ny = y_tail = (rows + 3) / 4;
-                    a.out = tab[cur ^ 1];
-                    a.out_stride = tab_stride[cur ^ 1];
-                    gkr_round_kernel<false, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
-                    rows = 2 * a.ny;
-                    cur ^= 1;
+        // Host side of a small table: stored rows (p0, q0, p1, q1); rows beyond are the constant (0, c, 0, c).
+        using HRow = std::array<Ext, 4>;
+        const Ext c_tail = cst[round + 1];
+        const HRow const_row{bb::ext_zero(), c_tail, bb::ext_zero(), c_tail};
+        std::vector<HRow> ht;
+        auto row_at = [&](const std::vector<HRow>& t, size_t i) -> const HRow& { return i < t.size() ? t[i] : const_row; };
+        const int sr_host = std::max(0, round - GKR_HOST_LOG);  // first round that runs on the host
+        if (sr_host == 0) {  // the whole layer: rows straight from the tree copy
+            const std::vector<uint32_t>& lay = top_layers[round + 1];
+            ht.resize(rows_tree);
+            for (size_t x = 0; x < rows_tree; x++)
+                for (int k = 0; k < 4; k++) {
+                    const size_t node = 2 * x + (k >> 1);
+                    ht[x][k] = node < S[round + 1] ? ext_from_words(&lay[node * 8 + 4 * (k & 1)]) : const_row[k];
                 }
-                SWIRL_LAUNCH_CHECK(ctx);
-            }
-            // the constant tail's share of t(X): lambda c^2 * sum_{y >= y_tail} eq(xi[sr+1..round), y)
+        }
+        // s(X) = e_bound * eq1(xi_sr, X) * t(X): t(1) and the leading coefficient come from the table sweep (the tail adds a
+        // constant), t(0) from s(0) = claim - s(1), then t(2), t(3) by extrapolating the quadratic
+        auto finish_round = [&](int sr, const Ext& t1_swept, const Ext& c2, size_t y_tail) -> int {
             const int m = round - 1 - sr;
+            // the constant tail's share of t(X): lambda c^2 * sum_{y >= y_tail} eq(xi[sr+1..round), y)
             const Ext tail = ext_mul(tail_unit, ext_sub(one, eq_prefix_sum(xi_prev, sr + 1, m, y_tail)));
-            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
             uint32_t* out = h_polys + (poly_off + sr) * 12;
-            // s(X) = e_bound * eq1(xi_sr, X) * t(X): t(1) and the leading coefficient come from the device (the tail adds a
-            // constant), t(0) from s(0) = claim - s(1), then t(2), t(3) by extrapolating the quadratic
             const Ext xs = xi_prev[sr], one_minus_xs = ext_one_minus(xs);
-            const Ext t1 = ext_add(ext_from_words(rs->h_result), tail), c2 = ext_from_words(rs->h_result + 4);
+            const Ext t1 = ext_add(t1_swept, tail);
             const Ext s1 = ext_mul(ext_mul(e_bound, xs), t1);
             const Ext den = ext_mul(e_bound, one_minus_xs);
             if (hp::is_zero(den)) {
                 set_error("degenerate sumcheck challenge (eq factor is zero)");
-                rc = SWIRL_ERR_INVALID;
-                break;
+                return SWIRL_ERR_INVALID;
             }
             const Ext s0 = ext_sub(claim, s1);
             const Ext t0 = ext_mul(s0, bb::ext_inv(den));
@@ -407,13 +391,92 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             }
             e_bound = ext_mul(e_bound, hp::eq1(xi_prev[sr], r));
             for (int k = 0; k < 4; k++) a.r[k] = r.c[k];
+            return 0;
+        };
+        for (int sr = 0; sr < round && rc == 0; sr++) {
+            if (sr >= sr_host) {
+                // ---- host round: fold the small table with the previous challenge, then sweep it -------------------
+                if (sr > 0) {
+                    const Ext r_prev = rho.back();
+                    const size_t ny = (ht.size() + 3) / 4;
+                    std::vector<HRow> nt(2 * ny);
+                    for (size_t y = 0; y < ny; y++)
+                        for (int k = 0; k < 4; k++) {
+                            nt[2 * y][k] = ext_lerp(row_at(ht, 4 * y)[k], row_at(ht, 4 * y + 1)[k], r_prev);
+                            nt[2 * y + 1][k] = ext_lerp(row_at(ht, 4 * y + 2)[k], row_at(ht, 4 * y + 3)[k], r_prev);
+                        }
+                    ht.swap(nt);
+                }
+                const size_t ny = (ht.size() + 1) / 2;
+                const int m = round - 1 - sr;
+                Ext sw[2] = {bb::ext_zero(), bb::ext_zero()};
+                for (size_t y = 0; y < ny; y++) {
+                    Ext E = one;  // eq(xi[sr+1 .. round), y)
+                    for (int b = 0; b < m; b++) E = ext_mul(E, hp::eq1(xi_prev[sr + 1 + b], ((y >> b) & 1) != 0));
+                    Ext lo[4], hi[4];
+                    for (int k = 0; k < 4; k++) {
+                        lo[k] = row_at(ht, 2 * y)[k];
+                        hi[k] = row_at(ht, 2 * y + 1)[k];
+                    }
+                    accumulate(lo, hi, lambda, E, sw);
+                }
+                rc = finish_round(sr, sw[0], sw[1], ny);
+                continue;
+            }
+            // ---- device round ---------------------------------------------------------------------------------------
+            // tables of the remaining variables [sr+1, round)
+            if (sr + 1 < v_split) {
+                a.a_bits = v_split - 1 - sr;
+                a.A = suffix(eqA, nA, sr);
+                a.B = suffix(eqB, nB, 0);
+            } else {
+                a.a_bits = 0;
+                a.A = nullptr;
+                a.B = suffix(eqB, nB, sr + 1 - v_split);
+            }
+            size_t y_tail;
+            a.last_rows = sr == sr_host - 1 ? rs->d_result + 64 : nullptr;  // the table the host continues from
+            {
+                SwirlTimed timed(ctx, SWIRL_T_GKR);
+                if (sr == 0) {
+                    a.rows_in = rows_tree;
+                    a.ny = y_tail = (rows_tree + 1) / 2;
+                    gkr_round_kernel<true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                } else if (sr == 1) {
+                    a.rows_in = rows_tree;
+                    a.ny = y_tail = (rows_tree + 3) / 4;
+                    a.out = tab[0];
+                    a.out_stride = tab_stride[0];
+                    gkr_round_kernel<true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                    rows = 2 * a.ny;
+                    cur = 0;
+                } else {
+                    a.in = tab[cur];
+                    a.in_stride = tab_stride[cur];
+                    a.rows_in = rows;
+                    a.ny = y_tail = (rows + 3) / 4;
+                    a.out = tab[cur ^ 1];
+                    a.out_stride = tab_stride[cur ^ 1];
+                    gkr_round_kernel<false, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                    rows = 2 * a.ny;
+                    cur ^= 1;
+                }
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+            if (a.last_rows) {  // this round's table (2 ny <= 2^(GKR_HOST_LOG+1) rows) for the host rounds that follow
+                ht.resize(2 * a.ny);
+                for (size_t i = 0; i < ht.size(); i++)
+                    for (int k = 0; k < 4; k++) ht[i][k] = ext_from_words(rs->h_result + 64 + i * 16 + 4 * k);
+            }
+            rc = finish_round(sr, ext_from_words(rs->h_result), ext_from_words(rs->h_result + 4), y_tail);
         }
         if (rc != 0) break;
-        // claims: the last round kernel left its 2-row table in mapped memory; fold it with the last challenge here
+        // claims: fold the final 2-row table with the last challenge
         {
             const Ext r_last = rho.back();
             for (int k = 0; k < 4; k++) {
-                const Ext v = ext_lerp(ext_from_words(rs->h_result + 16 + 4 * k), ext_from_words(rs->h_result + 32 + 4 * k), r_last);
+                const Ext v = ext_lerp(row_at(ht, 0)[k], row_at(ht, 1)[k], r_last);
                 memcpy(h_claims + (size_t)round * 16 + 4 * k, v.c, 16);
             }
         }
