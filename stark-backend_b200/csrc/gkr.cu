@@ -41,7 +41,7 @@ using bb::ext_mul_base;
 using bb::ext_sub;
 
 constexpr int GKR_BLOCK = 256;
-constexpr int GKR_HOST_LOG = 4;  // sumcheck rounds on tables of <= 2^4 rows run on the host (a kernel round trip costs more)
+constexpr int GKR_HOST_LOG = 5;  // sumcheck rounds on tables of <= 2^4 rows run on the host (a kernel round trip costs more)
 
 // parent[i] = child[2i] + child[2i+1] (projective fraction addition) for the stored prefix of a layer;
 // parents whose children lie in the constant tail are the constant (0, c_parent).
