@@ -6,11 +6,14 @@
 // cuda-common/include/launcher.cuh:43-55 (CHECK_KERNEL).  We use the driver's stream-ordered pool
 // (cudaMallocAsync with an unbounded release threshold) instead of the reference's VPMM pool.
 #pragma once
+#include <algorithm>
 #include <chrono>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -49,6 +52,9 @@ struct swirl_ctx {
     // host-side synchronisation statistics (swirl_ctx_sync_stats): how much of a proof is spent waiting on the stream
     uint64_t sync_count = 0;
     double sync_ms = 0;
+    // pinned staging area for device-to-host copies into caller (pageable) memory, see d2h_staged
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
 };
 
 // kernel families for swirl_ctx_timing_read
@@ -101,6 +107,40 @@ inline cudaError_t stream_sync(swirl_ctx* ctx, const char* file, int line) {
     ctx->sync_count++;
     ctx->sync_ms += ms;
     if (lim > 0 && ms > lim) stall_report("cudaStreamSynchronize", file, line, ms, 0);
+    return e;
+}
+
+// SWIRL_TRACE=1: wall-clock per phase on stderr; every mark synchronises the stream first.
+inline void trace_mark(swirl_ctx* ctx, const char* phase, const char* name, std::chrono::steady_clock::time_point* prev) {
+    static const bool on = getenv("SWIRL_TRACE") != nullptr;
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto now = std::chrono::steady_clock::now();
+    if (name) fprintf(stderr, "[swirl trace] %s %-18s %8.3f ms\n", phase, name, std::chrono::duration<double, std::milli>(now - *prev).count());
+    *prev = now;
+}
+
+// Device -> caller memory.  Proof buffers belong to the caller and are usually pageable; a direct cudaMemcpyAsync into
+// them is staged by the driver in small chunks and blocks (~1 ms for the 3 MB of opened rows).  Copies of 64 KiB and more
+// go through one pinned buffer of the context instead: one DMA at full PCIe rate, one synchronisation, one memcpy.
+// Returns with the data in `dst` (the stream is synchronised).
+inline cudaError_t d2h_staged(swirl_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
+    if (bytes < (size_t(64) << 10)) {
+        cudaError_t e = cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+    }
+    if (ctx->h_stage_bytes < bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_bytes = 0;
+        const size_t want = std::max(bytes, size_t(8) << 20);
+        cudaError_t e = cudaHostAlloc(&ctx->h_stage, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        ctx->h_stage_bytes = want;
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->h_stage, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) memcpy(dst, ctx->h_stage, bytes);
     return e;
 }
 

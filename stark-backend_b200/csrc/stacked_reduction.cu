@@ -248,6 +248,8 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
     RoundScratch* rs;
     SWIRL_TRY(round_scratch_get(ctx, &rs));
 
+    auto t_prev = std::chrono::steady_clock::now();
+    swirl::trace_mark(ctx, "sr", nullptr, &t_prev);
     // ---- views ---------------------------------------------------------------------------------
     struct View {
         size_t com, col_idx, row_idx;
@@ -320,6 +322,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
         tabs[v.log_height] = t;
     }
 
+    swirl::trace_mark(ctx, "sr", "views + eq", &t_prev);
     // ---- round 0 -------------------------------------------------------------------------------
     const size_t s0_len = 2 * (N - 1) + 1;
     std::vector<Ext> total_evals(2 * N, bb::ext_zero());  // [z_idx * 2 + coset]
@@ -411,6 +414,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
     std::vector<Ext> u_vec{tr.sample_ext()};
     const Ext u_0 = u_vec[0];
 
+    swirl::trace_mark(ctx, "sr", "round 0", &t_prev);
     // ---- fold_ple: q_evals[ci] = EF matrix (H >> l_skip) x W, ping-pong --------------------------------
     std::vector<uint32_t*> qe[2];
     qe[0].resize(n_commits);
@@ -456,6 +460,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
         }
     }
 
+    swirl::trace_mark(ctx, "sr", "fold_ple", &t_prev);
     // ---- MLE rounds ------------------------------------------------------------------------------
     std::vector<Ext> eq_ub(views.size(), bb::ext_one());
     MleView *d_views = nullptr, *d_ex = nullptr;
@@ -571,6 +576,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
             }
         }
     }
+    swirl::trace_mark(ctx, "sr", "mle rounds", &t_prev);
     // ---- stacking openings ------------------------------------------------------------------------
     for (size_t ci = 0; ci < n_commits; ci++) {
         const size_t W = pcs[ci]->layout.width;

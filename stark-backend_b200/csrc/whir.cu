@@ -258,6 +258,8 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
     for (int r = 1; r < R; r++) { sec_proofs[r] = p; p += (size_t)cfg->num_queries[r] * (m + log_blowup - r - k) * 8; }
     uint32_t* sec_final = p;
 
+    auto t_prev = std::chrono::steady_clock::now();
+    swirl::trace_mark(ctx, "whir", nullptr, &t_prev);
     // ---- mu batching -----------------------------------------------------------------------------
     uint32_t wm = 0;
     SWIRL_TRY(transcript_grind(ctx, ts, cfg->mu_pow_bits, &wm));
@@ -321,6 +323,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
         SWIRL_TRY(mle_tensor_table(ctx, t, m, w[0]));
     }
 
+    swirl::trace_mark(ctx, "whir", "mu batch + tables", &t_prev);
     // ---- WHIR rounds ---------------------------------------------------------------------------
     int cur = 0;             // f[cur], w[cur] hold the current tables of n entries
     size_t n = H;
@@ -360,6 +363,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             const Ext alpha = tr.sample_ext();
             memcpy(a.alpha, alpha.c, 16);
         }
+        swirl::trace_mark(ctx, "whir", "sumcheck rounds", &t_prev);
         // materialise the last fold of this WHIR round
         a.f_in = f[cur];
         a.w_in = w[cur];
@@ -411,6 +415,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                 tr.observe_ext(Ext{{sec_final[4 * i], sec_final[4 * i + 1], sec_final[4 * i + 2], sec_final[4 * i + 3]}});
             }
         }
+        swirl::trace_mark(ctx, "whir", "fold+commit+ood", &t_prev);
         // ---- query phase ---------------------------------------------------------------------------
         const int nq = cfg->num_queries[wr];
         SWIRL_TRY(transcript_grind(ctx, ts, cfg->query_phase_pow_bits, &sec_query_pow[wr]));
@@ -428,21 +433,19 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                     SWIRL_TRY(matrix_open_rows(ctx, pcs[ci]->codeword, pcs[ci]->codeword_height, widths[ci], pcs[ci]->query_stride,
                                                k, d_idx, nq, d_open));
                     SWIRL_TRY(merkle_query_proofs(ctx, pcs[ci]->layers, pcs[ci]->query_stride, d_idx, nq, d_open + row_words));
-                    SWIRL_CUDA(cudaMemcpyAsync(sec_rows0[ci], d_open, row_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                    SWIRL_CUDA(cudaMemcpyAsync(sec_proofs0[ci], d_open + row_words, path_words * 4, cudaMemcpyDeviceToHost,
-                                               ctx->stream));
-                    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+                    SWIRL_CUDA(swirl::d2h_staged(ctx, sec_rows0[ci], d_open, row_words * 4));
+                    SWIRL_CUDA(swirl::d2h_staged(ctx, sec_proofs0[ci], d_open + row_words, path_words * 4));
                 }
             } else {
                 SWIRL_REQUIRE(rs_codeword && rs_layers, "RsTreeNone");
                 const size_t row_words = (size_t)nq * (size_t(4) << k), path_words = (size_t)nq * depth * 8;
                 SWIRL_TRY(matrix_open_rows(ctx, rs_codeword, rs_height, 4, rs_height >> k, k, d_idx, nq, d_open));
                 SWIRL_TRY(merkle_query_proofs(ctx, rs_layers, rs_height >> k, d_idx, nq, d_open + row_words));
-                SWIRL_CUDA(cudaMemcpyAsync(sec_vals[wr], d_open, row_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                SWIRL_CUDA(cudaMemcpyAsync(sec_proofs[wr], d_open + row_words, path_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+                SWIRL_CUDA(swirl::d2h_staged(ctx, sec_vals[wr], d_open, row_words * 4));
+                SWIRL_CUDA(swirl::d2h_staged(ctx, sec_proofs[wr], d_open + row_words, path_words * 4));
             }
         }
+        swirl::trace_mark(ctx, "whir", "grind+queries", &t_prev);
         dev_free(ctx, rs_codeword);
         dev_free(ctx, rs_layers);
         rs_codeword = g_codeword;
