@@ -115,13 +115,16 @@ __device__ __forceinline__ void dif_regs(uint32_t (&x)[1 << G], const uint32_t* 
         for (int a = 0; a < half; a++) {
             uint32_t e = (((uint32_t)a << b0) + lo) << shift;
             if (inverse) e = ((1u << TW_HI_BITS) - e) & TW_HI_MASK;
-            const uint32_t w = __ldg(tw_hi + e);
+            // lowest group of a transform (b0 == 0, so lo == 0): the a == 0 butterflies have twiddle w^0 = 1 -- 7 of
+            // the 12 products of a radix-8 group, 15 of 32 of a radix-16 group -- and need no multiplication
+            const bool unit = b0 == 0 && a == 0;
+            const uint32_t w = unit ? bb::R1 : __ldg(tw_hi + e);
 #pragma unroll
             for (int blk = 0; blk < (1 << t); blk++) {
                 const int i0 = blk * 2 * half + a, i1 = i0 + half;
                 const uint32_t u = x[i0], v = x[i1];
                 x[i0] = bb::add(u, v);
-                x[i1] = bb::mul_diff(u, v, w);
+                x[i1] = unit ? bb::sub(u, v) : bb::mul_diff(u, v, w);
             }
         }
     }
