@@ -44,7 +44,7 @@ using bb::ext_mul;
 using bb::ext_mul_base;
 using bb::ext_sub;
 
-enum : uint32_t { I_VAR = 0, I_CONST, I_ADD, I_SUB, I_MUL, I_NEG, I_PREF, I_ACC };
+enum : uint32_t { I_VAR = 0, I_CONST, I_ADD, I_SUB, I_MUL, I_NEG, I_PREF, I_MULACC, I_ACC };
 struct Instr {
     uint32_t op_dst;  // op | dst << 8
     uint32_t a, b, c;
@@ -193,6 +193,14 @@ static int compile_program(const swirl_air_ctx& a, const AirLayout& L, const std
         }
         slot[i] = s;
         ins.op_dst = op | ((uint32_t)s << 8);
+        if (op == I_MUL && last_use[i] < 0 && root_of[i].size() == 1) {
+            // a product that only feeds one accumulator (the typical constraint root): multiply and accumulate in one
+            // instruction, no slot written.  op_dst = op | acc << 8, a / b = operand slots, c = weight index
+            const Root& rt = roots[root_of[i][0]];
+            out->code.push_back(Instr{I_MULACC | (rt.acc << 8), ins.a, ins.b, rt.weight});
+            release((uint32_t)i, i);
+            continue;
+        }
         out->code.push_back(ins);
         for (uint32_t ri : root_of[i]) out->code.push_back(Instr{I_ACC, roots[ri].acc, roots[ri].weight, (uint32_t)s});
         if (last_use[i] < 0) release((uint32_t)i, i);  // only consumed by accumulations
@@ -279,6 +287,17 @@ __device__ __forceinline__ void run_program_on(Slots&& slots, const Instr* __res
         switch (op) {
             case I_VAR: load_var(cur.y, cur.z, cur.w, slots[dst]); break;
             case I_PREF: load_var(cur.y, cur.z, cur.w, PrefetchTag{}); break;
+            case I_MULACC: {  // acc[.][dst] += weights[w] * (slots[y] * slots[z])
+                const Ext wv = ldg_ext(weights + 4 * cur.w);
+#pragma unroll
+                for (int l = 0; l < LN; l++) {
+                    const Ext t = V::weigh(wv, V::mul(slots[cur.y][l], slots[cur.z][l]));
+                    if (dst == 0) acc[l][0] = ext_add(acc[l][0], t);
+                    else if (dst == 1) acc[l][1] = ext_add(acc[l][1], t);
+                    else acc[l][2] = ext_add(acc[l][2], t);
+                }
+                break;
+            }
             case I_CONST:
 #pragma unroll
                 for (int l = 0; l < LN; l++) slots[dst][l] = V::from_base(cur.y);
