@@ -94,3 +94,10 @@ def test_host_transcript_matches_oracle(oracle):
     ts.observe(sb.to_mont(edge))
     oracle.sponge_observe(st, sb.to_mont(edge))
     assert np.array_equal(ts.words(), st)
+
+
+def test_rust_ffi_lists_every_symbol():
+    """bindings/rust/src/ffi.rs (the extern block a maintainer links against) declares every entry point of the header."""
+    ffi = open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (swirl_[a-z0-9_]+)\(", ffi))
+    assert declared == set(_declared())
