@@ -397,6 +397,27 @@ class B200Device:
             out[name] = (ms.value, int(n.value), int(b.value))
         return out
 
+    # -- host proof buffers -------------------------------------------------------------------------------------
+    # Fresh multi-megabyte numpy buffers are fresh anonymous pages: the first write into each 4 KiB page faults, which costs
+    # ~1 ms for the 3.4 MB WHIR proof.  Buffers handed back by Proof.__del__ are reused (what a pooling allocator such as
+    # the reference's mimalloc does for the Rust Vecs).
+    def host_buffer(self, n_words):
+        pool = self.__dict__.setdefault("_host_pool", {})
+        free = pool.get(int(n_words))
+        if free:
+            return free.pop()
+        return np.zeros(int(n_words), dtype=np.uint32)
+
+    def recycle_host_buffer(self, buf):
+        import sys
+
+        if isinstance(buf, np.ndarray) and buf.base is None and buf.dtype == np.uint32 and buf.size >= (1 << 16) \
+                and sys.getrefcount(buf) <= 3:  # nobody else holds it: safe to hand out again
+            pool = self.__dict__.setdefault("_host_pool", {})
+            lst = pool.setdefault(int(buf.size), [])
+            if len(lst) < 4:
+                lst.append(buf)
+
     def trim(self):
         """Return the idle scratch blocks the context keeps for the next proof to the driver."""
         check(self.lib.swirl_ctx_trim(self.ctx))
@@ -573,7 +594,7 @@ class B200Device:
         n_wh = int(self.lib.swirl_whir_proof_words(C.byref(pc), C.byref(cc), len(pcs_list), widths.ctypes.data))
         if n_wh == 0:
             raise _lib.SwirlError(10001, "invalid WHIR configuration")
-        st, wh = np.zeros(n_st, dtype=np.uint32), np.zeros(n_wh, dtype=np.uint32)
+        st, wh = self.host_buffer(n_st), self.host_buffer(n_wh)  # every word is written by the library
         rots = [np.asarray([1 if b else 0 for b in rr], dtype=np.uint8) for rr in need_rot_per_commit]
         rot_ptrs = (C.c_void_p * len(rots))(*[a.ctypes.data for a in rots])
         r = np.ascontiguousarray(r, dtype=np.uint32)

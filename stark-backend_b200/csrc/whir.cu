@@ -419,11 +419,13 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
         // ---- query phase ---------------------------------------------------------------------------
         const int nq = cfg->num_queries[wr];
         SWIRL_TRY(transcript_grind(ctx, ts, cfg->query_phase_pow_bits, &sec_query_pow[wr]));
+        swirl::trace_mark(ctx, "whir", "  query grind", &t_prev);
         const uint32_t omega = bb::two_adic_generator(log_rs - k);
         for (int q = 0; q < nq; q++) {
             h_idx[q] = tr.sample_bits(log_rs - k);
             h_zs[q] = bb::pow(omega, h_idx[q]);
         }
+        swirl::trace_mark(ctx, "whir", "  sample indices", &t_prev);
         const size_t depth = (size_t)(log_rs - k);
         if (nq > 0) {
             SWIRL_CUDA(cudaMemcpyAsync(d_idx, h_idx.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -433,6 +435,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
                     SWIRL_TRY(matrix_open_rows(ctx, pcs[ci]->codeword, pcs[ci]->codeword_height, widths[ci], pcs[ci]->query_stride,
                                                k, d_idx, nq, d_open));
                     SWIRL_TRY(merkle_query_proofs(ctx, pcs[ci]->layers, pcs[ci]->query_stride, d_idx, nq, d_open + row_words));
+                    swirl::trace_mark(ctx, "whir", "  open kernels", &t_prev);
                     SWIRL_CUDA(swirl::d2h_staged(ctx, sec_rows0[ci], d_open, row_words * 4));
                     SWIRL_CUDA(swirl::d2h_staged(ctx, sec_proofs0[ci], d_open + row_words, path_words * 4));
                 }

@@ -46,6 +46,14 @@ class Proof:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
+    def __del__(self):
+        dev = self.__dict__.pop("_device", None)
+        if dev is not None:  # large host buffers go back to the device's pool when nobody else references them
+            for name in ("whir_proof", "stacking_proof", "constraints_proof"):
+                buf = self.__dict__.pop(name, None)
+                if buf is not None:
+                    dev.recycle_host_buffer(buf)
+
     def words(self):
         return np.concatenate([self.common_main_commit, self.constraints_proof, self.stacking_proof, self.whir_proof])
 
@@ -142,7 +150,7 @@ class Coordinator:
             public_values=[present[i][1].public_values if i in present else np.zeros(0, np.uint32)
                            for i in range(len(per_air_pk))])
         self.phase_ms = {marks[i][0]: 1e3 * (marks[i][1] - marks[i - 1][1]) for i in range(1, len(marks))}
-        return Proof(common_main_commit=root, constraints_proof=constraints_proof, stacking_proof=stacking, whir_proof=whir, shape=shape,
+        return Proof(common_main_commit=root, constraints_proof=constraints_proof, stacking_proof=stacking, whir_proof=whir, shape=shape, _device=dev,
                      r=r, public_values=[a.public_values for a in airs], common_main_pcs=common,
                      log_heights=[a.common_main.height().bit_length() - 1 for a in airs])
 
