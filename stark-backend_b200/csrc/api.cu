@@ -144,6 +144,7 @@ int swirl_ctx_destroy(swirl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream || !ctx->owns_stream) cudaStreamSynchronize(ctx->stream);
     timing_clear(ctx);
+    swirl::program_cache_clear(ctx);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     arena_trim(ctx);
     for (auto& kv : ctx->arena_live) cudaFreeAsync(kv.first, ctx->stream);  // blocks the caller never released

@@ -673,6 +673,19 @@ struct TraceState {
     uint32_t norm = bb::R1;  // 1 / 2^max(l_skip - log_height, 0)
 };
 
+struct ProgramCache {
+    struct Entry {
+        TraceState::Chunk whole[2];
+        std::vector<TraceState::Chunk> chunks;
+    };
+    std::map<std::string, Entry> entries;
+    std::vector<void*> buffers;  // device code of all entries
+};
+ProgramCache* program_cache(swirl_ctx* ctx) {
+    if (!ctx->program_cache) ctx->program_cache = new ProgramCache();
+    return (ProgramCache*)ctx->program_cache;
+}
+
 int n_logup_of(int l_skip, uint64_t total) {
     if (!total) return 0;
     int bits = 0;
@@ -711,6 +724,17 @@ std::vector<Ext> poly_mul(const std::vector<Ext>& a, const std::vector<Ext>& b, 
 }
 
 }  // namespace
+
+namespace swirl {
+void program_cache_clear(swirl_ctx* ctx) {
+    ProgramCache* c = (ProgramCache*)ctx->program_cache;
+    if (!c) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : c->buffers) cudaFree(p);
+    delete c;
+    ctx->program_cache = nullptr;
+}
+}  // namespace swirl
 
 extern "C" size_t swirl_batch_constraints_proof_words(int l_skip, int max_constraint_degree, const swirl_air_ctx* airs,
                                                       size_t n_airs) {
@@ -821,6 +845,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     }
 
     mark("grind+setup");
+    if (program_cache(ctx)->entries.size() >= 1024) program_cache_clear(ctx);  // bound the cache; nothing of it is in use here
     // ---- per trace: selector matrix, base parts, programs ---------------------------------------------
     for (size_t t = 0; t < n_airs; t++) {
         TraceState& s = T[t];
@@ -848,9 +873,30 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             roots.push_back(Root{it.count_node, 1, w++});
             for (uint32_t j = 0; j < it.msg_len; j++) roots.push_back(Root{a.msg_nodes[it.msg_offset + j], 2, w++});
         }
-        SWIRL_TRY(compile_program(a, s.L, roots, &s.prog, BC_PREFETCH_VARS));
-        SWIRL_TRY(upload(s.prog.code.data(), s.prog.code.size() * sizeof(Instr), (void**)&s.d_code));
+        // Compiled programs are cached in the context, keyed by everything they depend on (DAG, roots, public values,
+        // part layout, chunk budget): a prover proves the same AIRs again and again, and the reference builds its rules
+        // once per proving key (cuda-backend/src/logup_zerocheck/rules/mod.rs:27-130).
+        std::string key;
         {
+            auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
+            const uint64_t hdr[6] = {a.n_nodes, a.n_constraints, a.n_interactions, a.n_public_values, (uint64_t)a.need_rot,
+                                     std::max<size_t>(2, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs))};
+            put(hdr, sizeof(hdr));
+            put(a.nodes, a.n_nodes * sizeof(swirl_dag_node));
+            put(a.constraint_idx, a.n_constraints * 4);
+            put(a.interactions, a.n_interactions * sizeof(swirl_interaction));
+            for (uint64_t i = 0; i < a.n_interactions; i++)
+                put(a.msg_nodes + a.interactions[i].msg_offset, a.interactions[i].msg_len * 4);
+            put(a.public_values, a.n_public_values * 4);
+            put(s.L.part_width.data(), s.L.part_width.size() * 4);
+        }
+        ProgramCache* cache = program_cache(ctx);
+        auto hit = cache->entries.find(key);
+        if (hit != cache->entries.end()) {
+            s.whole[0] = hit->second.whole[0];
+            s.whole[1] = hit->second.whole[1];
+            s.chunks = hit->second.chunks;
+        } else {
             // sub-programs never mix constraint and interaction roots: the zerocheck part of round 0 is needed on one
             // coset fewer than the LogUp part (cpu.rs:338-361 vs :405-409)
             const size_t nc = a.n_constraints;
@@ -861,7 +907,12 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 c->n_slots = pr.n_slots;
                 c->zerocheck_only = zc;
                 c->d_code = nullptr;  // an empty program is never dereferenced
-                if (!pr.code.empty()) SWIRL_TRY(upload(pr.code.data(), pr.code.size() * sizeof(Instr), (void**)&c->d_code));
+                if (!pr.code.empty()) {  // owned by the cache, released with the context
+                    SWIRL_CUDA(cudaMalloc((void**)&c->d_code, pr.code.size() * sizeof(Instr)));
+                    cache->buffers.push_back(c->d_code);
+                    SWIRL_CUDA(cudaMemcpyAsync(c->d_code, pr.code.data(), pr.code.size() * sizeof(Instr), cudaMemcpyHostToDevice, ctx->stream));
+                    SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));  // pr.code is a temporary
+                }
                 return 0;
             };
             SWIRL_TRY(compile_range(0, nc, true, &s.whole[0]));
@@ -887,6 +938,11 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 SWIRL_TRY(compile_range(0, 0, false, &c));
                 s.chunks.push_back(c);
             }
+            ProgramCache::Entry e;
+            e.whole[0] = s.whole[0];
+            e.whole[1] = s.whole[1];
+            e.chunks = s.chunks;
+            cache->entries.emplace(std::move(key), std::move(e));
         }
     }
 

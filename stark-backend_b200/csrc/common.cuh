@@ -53,6 +53,7 @@ struct swirl_ctx {
     uint64_t sync_count = 0;
     double sync_ms = 0;
     // pinned staging area for device-to-host copies into caller (pageable) memory, see d2h_staged
+    void* program_cache = nullptr;  // compiled constraint programs (batch.cu: ProgramCache)
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
 };
@@ -97,6 +98,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 // SWIRL_STALL_DEBUG=<ms>: host calls (stream-ordered allocations, stream synchronisations) that take longer
 // than <ms> of wall time are reported on stderr with their call site (box / allocator stall hunting).
+void program_cache_clear(swirl_ctx* ctx);  // batch.cu
 double stall_debug_ms();
 void stall_report(const char* what, const char* file, int line, double ms, size_t bytes);
 inline cudaError_t stream_sync(swirl_ctx* ctx, const char* file, int line) {
