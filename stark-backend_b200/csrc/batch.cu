@@ -646,9 +646,7 @@ struct TraceState {
     int log_height = 0, n = 0, n_lift = 0;
     size_t height = 0, lifted = 0;
     AirLayout L;
-    Program prog;
-    Instr* d_code = nullptr;
-    // the same program split by roots into independent sub-programs (their accumulators add up): one thread
+    // the constraint program split by roots into independent sub-programs (their accumulators add up): one thread
     // walks ~16 roots instead of the whole DAG, which multiplies the loads in flight per SM and divides the
     // serial latency of the short tail rounds
     struct Chunk {
