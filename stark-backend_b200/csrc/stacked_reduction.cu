@@ -101,6 +101,90 @@ sr_round0_kernel(const R0View* __restrict__ views, const uint32_t* __restrict__ 
         partials[blk * (size_t)(N * 12) + o] = s;
     }
 }
+// The same sums for 2^l_skip >= 4 with four consecutive points of D per thread: one 16-byte load of the column per
+// hypercube point, and every group of threads walks a contiguous run of points so that eq[x - 1] is the value it already
+// holds (one eq load per point instead of two per cell).  Products are summed four at a time in 64 bits (bb::dot4 bound).
+__global__ void __launch_bounds__(SR_BLOCK)
+sr_round0_vec_kernel(const R0View* __restrict__ views, const uint32_t* __restrict__ eq, int n_lift, int l_skip, int xc,
+                     uint32_t* __restrict__ partials) {
+    __shared__ uint32_t sm[SR_BLOCK][32 + 1];
+    const R0View v = views[blockIdx.y];
+    const int N = 1 << l_skip, N4 = N >> 2;
+    const int i4 = threadIdx.x % N4, g = threadIdx.x / N4, G = SR_BLOCK / N4;
+    const size_t nx = size_t(1) << n_lift;
+    const size_t x0 = (size_t)blockIdx.x * xc, x1 = min(x0 + (size_t)xc, nx);
+    const size_t run = (size_t)xc / G;  // xc is a multiple of 4 G
+    const size_t xs = x0 + (size_t)g * run, xe = min(xs + run, x1);
+    uint32_t a1[4][4], b1[4][4];  // [cell][coefficient]
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) a1[c][k] = b1[c][k] = 0;
+    const uint64_t PP = (uint64_t)bb::P << 32;
+    if (xs < xe) {
+        Ext ep = ldg_ext(eq + 4 * (xs == 0 ? nx - 1 : xs - 1));
+        for (size_t xb = xs; xb < xe; xb += 4) {
+            uint64_t s1[4][4], s2[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) s1[c][k] = s2[c][k] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const size_t x = xb + j;
+                if (x < xe) {
+                    const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(v.q + (x << l_skip)) + i4);
+                    const Ext e = ldg_ext(eq + 4 * x);
+                    const uint32_t q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            s1[c][k] += (uint64_t)e.c[k] * q[c];
+                            s2[c][k] += (uint64_t)ep.c[k] * q[c];
+                        }
+                    ep = e;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    a1[c][k] = bb::add(a1[c][k], bb::reduce(s1[c][k] >= PP ? s1[c][k] - PP : s1[c][k]));
+                    b1[c][k] = bb::add(b1[c][k], bb::reduce(s2[c][k] >= PP ? s2[c][k] - PP : s2[c][k]));
+                }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            sm[threadIdx.x][c * 8 + k] = a1[c][k];
+            sm[threadIdx.x][c * 8 + 4 + k] = b1[c][k];
+        }
+    __syncthreads();
+    // point i = 4 i4 + c of D: sum over the G groups, then the three products with the batching coefficients
+    if ((int)threadIdx.x < N) {
+        const int i = threadIdx.x, ii4 = i >> 2, c = i & 3;
+        Ext sa = bb::ext_zero(), sb = bb::ext_zero();
+        for (int gg = 0; gg < G; gg++) {
+            const uint32_t* row = sm[gg * N4 + ii4] + c * 8;
+            sa = ext_add(sa, Ext{{row[0], row[1], row[2], row[3]}});
+            sb = ext_add(sb, Ext{{row[4], row[5], row[6], row[7]}});
+        }
+        const Ext le = Ext{{v.lam_eq[0], v.lam_eq[1], v.lam_eq[2], v.lam_eq[3]}};
+        const Ext lr = Ext{{v.lam_rot[0], v.lam_rot[1], v.lam_rot[2], v.lam_rot[3]}};
+        const Ext o0 = ext_mul(sa, le), o1 = ext_mul(sa, lr), o2 = ext_mul(ext_sub(sb, sa), lr);
+        const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        uint32_t* out = partials + blk * (size_t)(N * 12) + (size_t)i * 12;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            out[k] = o0.c[k];
+            out[4 + k] = o1.c[k];
+            out[8 + k] = o2.c[k];
+        }
+    }
+}
 // result[o] = sum_b partials[b * nv + o]
 __global__ void sr_reduce_kernel(const uint32_t* __restrict__ partials, size_t nblocks, int nv, uint32_t* __restrict__ result) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,8 +441,12 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
             const size_t nviews = win[wi + 1] - win[wi];
             const size_t chunks = (t.len + SR_X_PER_BLOCK - 1) / SR_X_PER_BLOCK;
             SWIRL_REQUIRE(nviews < 65536, "too many columns of one height");
-            sr_round0_kernel<<<dim3((unsigned)chunks, (unsigned)nviews), SR_BLOCK, 0, ctx->stream>>>(
-                dv + win[wi], t.eq[0], t.n_lift, l_skip, SR_X_PER_BLOCK, part);
+            if (l_skip >= 2 && l_skip <= 6)
+                sr_round0_vec_kernel<<<dim3((unsigned)chunks, (unsigned)nviews), SR_BLOCK, 0, ctx->stream>>>(
+                    dv + win[wi], t.eq[0], t.n_lift, l_skip, SR_X_PER_BLOCK, part);
+            else
+                sr_round0_kernel<<<dim3((unsigned)chunks, (unsigned)nviews), SR_BLOCK, 0, ctx->stream>>>(
+                    dv + win[wi], t.eq[0], t.n_lift, l_skip, SR_X_PER_BLOCK, part);
             SWIRL_LAUNCH_CHECK(ctx);
             sr_reduce_kernel<<<(nv + 255) / 256, 256, 0, ctx->stream>>>(part, chunks * nviews, nv, d_res + wi * (size_t)nv);
             SWIRL_LAUNCH_CHECK(ctx);
