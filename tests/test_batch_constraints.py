@@ -128,3 +128,17 @@ def test_gpu_batch_constraints_large_accepted_by_oracle_verifier(dev, oracle):
     proof, r = dev.prove_batch_constraints(ts, l_skip, D, pow_bits, to_device_airs(dev, airs))
     ok, rv = oracle.bc_verify(st, l_skip, D, pow_bits, A.flatten(airs), len(airs), n_max, proof)
     assert ok and np.array_equal(rv, r) and np.array_equal(st, ts.words())
+
+
+@pytest.mark.gpu
+def test_gpu_violated_constraint_proof_equals_oracle_and_is_rejected(dev, oracle):
+    """A trace that violates its AIR: the prover still runs (the reference's debug builder is a separate check,
+    backend-tests/src/lib.rs disable_debug_builder()), the CUDA proof equals the oracle's word for word, and the oracle's
+    verifier rejects it."""
+    l_skip, D, pow_bits, airs, n_max, st = setup(oracle, case_fib, seed=5)
+    airs[0].common_main[0][7] ^= 1  # break the trace
+    ts, stv = sb.Transcript(st), st.copy()
+    want, r = oracle.bc_prove(st, l_skip, D, pow_bits, A.flatten(airs), 1, n_max)
+    got, rg = dev.prove_batch_constraints(ts, l_skip, D, pow_bits, to_device_airs(dev, airs))
+    assert np.array_equal(got, want) and np.array_equal(rg, r)
+    assert not oracle.bc_verify(stv, l_skip, D, pow_bits, A.flatten(airs), 1, n_max, got)[0]
