@@ -12,6 +12,7 @@ from .backend import (  # noqa: F401
     PcsParams,
     StackedLayout,
     StackedPcsData,
+    TraceTransporter,
     P,
     to_mont,
     from_mont,

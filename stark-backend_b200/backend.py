@@ -220,6 +220,35 @@ class PcsTraceView:
         return self._ptr
 
 
+class TraceTransporter:
+    """Host -> device transport of trace matrices with pinned double buffering (reference: DeviceDataTransporter,
+    prover/hal.rs:141-207; pinned staging in cuda-common/src/pinned.rs): `submit` starts the copy of a
+    pinned host trace into one of `depth` device buffers on a dedicated copy stream and returns a ticket; `matrix`
+    makes the library's stream wait for that copy and returns the DeviceMatrix.  Submitting the next proof's trace
+    before proving the current one overlaps the PCIe transfer with the proof."""
+
+    def __init__(self, dev, height, width, depth=2):
+        self.dev, self.height, self.width = dev, int(height), int(width)
+        self.buffers = [dev.alloc(self.height * self.width) for _ in range(depth)]
+        self.stream = torch.cuda.Stream(device=dev.torch_device)
+        self.next = 0
+
+    def submit(self, host_tensor):
+        assert host_tensor.is_pinned() and host_tensor.numel() == self.height * self.width
+        buf = self.buffers[self.next]
+        self.next = (self.next + 1) % len(self.buffers)
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self.stream):
+            buf.copy_(host_tensor, non_blocking=True)
+            ev.record(self.stream)
+        return buf, ev
+
+    def matrix(self, ticket):
+        buf, ev = ticket
+        self.dev.torch_stream().wait_event(ev)  # ordered on the device; the host does not block
+        return DeviceMatrix(buf, self.height, self.width)
+
+
 class WhirConfig:
     """reference: WhirConfig / WhirRoundConfig (config.rs:172-197)."""
 
