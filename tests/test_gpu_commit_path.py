@@ -417,3 +417,25 @@ def test_scatter_rows_to_peers_layout(dev, oracle):
         got = bufs[r].cpu().view(width, rows // world)
         assert torch.equal(got[col0:col0 + cols], want[r].reshape(cols, -1))
         assert int(got[:col0].abs().sum()) == 0 and int(got[col0 + cols:].abs().sum()) == 0
+
+
+@pytest.mark.gpu
+def test_trace_transporter_double_buffering(dev, oracle):
+    """TraceTransporter: traces submitted from pinned host memory (two in flight, buffers reused round-robin) commit to the
+    same roots as the oracle."""
+    import torch
+
+    l_skip, n_stack, log_blowup, k, w = 2, 6, 1, 2, 5
+    H = 1 << (l_skip + n_stack)
+    params = sb.PcsParams(l_skip, n_stack, log_blowup, k)
+    tp = sb.TraceTransporter(dev, H, w)
+    rng = np.random.default_rng(21)
+    hosts = [oracle.random_field(rng, H * w) for _ in range(5)]
+    pinned = [torch.from_numpy(h.view(np.int32)).pin_memory() for h in hosts]
+    tickets = [tp.submit(pinned[0])]
+    for i in range(5):
+        if i + 1 < 5:
+            tickets.append(tp.submit(pinned[i + 1]))  # next trace in flight while this one is committed
+        root, pcs = dev.commit(params, [tp.matrix(tickets[i])])
+        assert np.array_equal(root, oracle.stacked_commit(l_skip, n_stack, log_blowup, k, [(hosts[i], H, w)], want_codeword=False)[0])
+        pcs.free()
