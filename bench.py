@@ -195,15 +195,35 @@ def cpu_prove_sample(oracle, log_rows):
                                f"workload; n_stack {n_stack}, WHIR queries {cfg['num_queries']}, same PoW bits)")
 
 
+def reference_sample_log_rows(t14_seconds, steps, budget_s=240.0):
+    """Largest sample (rows = 2^k, 14 <= k <= LOG_ROWS) whose `steps` proofs fit the budget; a proof's cost is linear in
+    the rows within ~15 % (profiles/r2_cpu_full_proof_*.jsonl: 2^16 -> 2^20 is 14.2x the time for 16x the rows)."""
+    k = 14
+    while k < LOG_ROWS and steps * t14_seconds * (1 << (k + 1 - 14)) <= budget_s:
+        k += 1
+    return k
+
+
+CPU_NOTE = ("C++ restatement of the reference col-major prover (oracle/; the reference is Rust and cannot be built in this image); "
+            "every phase (commit, LogUp-GKR, batch constraints, stacked reduction, WHIR, PoW searches) runs on all host threads")
+CPU_FULL_SIZE = ("a full-size 2^20 x 256 proof by the same code was timed once per host: profiles/r2_cpu_full_proof_*.jsonl "
+                 "(8 cores: 217.8 s = 1.23 M cells/s against 1.09 M cells/s extrapolated from its 2^16-row sample)")
+
+
 def run_reference(args):
+    """The reference arm: the CPU implementation of the same path (oracle port, all host threads) on a bounded sample of the
+    same workload: the same AIR and parameters at 2^k rows, k chosen so that the K steps end within a few minutes (2^16 or
+    more on a 16-core host for the driver's K)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     oracle = load_oracle()
     cores = os.cpu_count() or 1
-    log_rows = 12
-    for _ in range(args.warmup):
-        cpu_prove_sample(oracle, 11)
+    t14 = None
+    for _ in range(max(1, args.warmup)):
+        _, dt, _ = cpu_prove_sample(oracle, 14)
+        t14 = dt if t14 is None else min(t14, dt)
+    log_rows = reference_sample_log_rows(t14, max(1, args.steps))
     times = []
     for _ in range(max(1, args.steps)):
         v, dt, sample = cpu_prove_sample(oracle, log_rows)
@@ -214,9 +234,8 @@ def run_reference(args):
         "impl": "reference", "metric": "trace_cells_per_s", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 (BabyBear Montgomery)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C++ restatement of the reference col-major prover (oracle/); its commit phase and PoW searches use all host threads, its sumcheck phases run on one"},
+        "config": {"workload": WORKLOAD, "sample": sample, "warmup_sample": "the same at 2^14 rows", "full_size": CPU_FULL_SIZE},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -440,11 +459,10 @@ def run_swirl(args):
         }
         if world == 1 and not args.no_cpu:
             oracle = load_oracle()
-            cpu_prove_sample(oracle, 11)
-            v, dt, sample = cpu_prove_sample(oracle, 12)
+            cpu_prove_sample(oracle, 12)
+            v, dt, sample = cpu_prove_sample(oracle, 16)
             out["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample,
-                                   "seconds": dt,
-                                   "note": "C++ restatement of the reference col-major prover (oracle/); its commit phase and PoW searches use all host threads, its sumcheck phases run on one"}
+                                   "seconds": dt, "note": CPU_NOTE, "full_size": CPU_FULL_SIZE}
         emit_json(out)
     del trace_dev
     torch.cuda.synchronize()

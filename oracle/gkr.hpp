@@ -45,8 +45,12 @@ inline FracSumcheckProof fractional_sumcheck(DuplexSponge& ts, const std::vector
     const int total_rounds = log2_strict(evals.size());
     std::vector<Frac> tree(size_t(2) << total_rounds);
     for (size_t i = 0; i < evals.size(); i++) tree[(size_t(1) << total_rounds) + i] = evals[i];
-    for (size_t node = (size_t(1) << total_rounds) - 1; node >= 1; node--)
-        tree[node] = frac_add(tree[2 * node], tree[2 * node + 1]);
+    for (int level = total_rounds - 1; level >= 0; level--) {  // same nodes as `for node = 2^n - 1 .. 1`, level by level
+        const size_t first = size_t(1) << level;
+        parallel_for(first, [&](size_t b, size_t e) {
+            for (size_t node = first + b; node < first + e; node++) tree[node] = frac_add(tree[2 * node], tree[2 * node + 1]);
+        }, 1024);
+    }
     const Frac frac_sum = tree[1];
     if (assert_zero) {
         if (!ef_is_zero(frac_sum.p)) throw NonZeroRootSum();
@@ -77,12 +81,14 @@ inline FracSumcheckProof fractional_sumcheck(DuplexSponge& ts, const std::vector
         // columns p_j0, q_j0, p_j1, q_j1
         std::vector<EF> pq(4 * eval_size);
         const Frac* seg = &tree[2 * eval_size];
-        for (size_t x = 0; x < eval_size; x++) {
-            pq[x] = seg[2 * x].p;
-            pq[eval_size + x] = seg[2 * x].q;
-            pq[2 * eval_size + x] = seg[2 * x + 1].p;
-            pq[3 * eval_size + x] = seg[2 * x + 1].q;
-        }
+        parallel_for(eval_size, [&](size_t b, size_t e) {
+            for (size_t x = b; x < e; x++) {
+                pq[x] = seg[2 * x].p;
+                pq[eval_size + x] = seg[2 * x].q;
+                pq[2 * eval_size + x] = seg[2 * x + 1].p;
+                pq[3 * eval_size + x] = seg[2 * x + 1].q;
+            }
+        }, 4096);
         size_t pq_h = eval_size, eq_h = eval_size;
         std::vector<EF> eq_xis = evals_eq_hypercube(xi_prev);
         std::vector<std::array<EF, 3>> round_polys;
@@ -91,17 +97,25 @@ inline FracSumcheckProof fractional_sumcheck(DuplexSponge& ts, const std::vector
             // s(X) at X in {1,2,3} of eq * (p0 q1 + p1 q0 + lambda q0 q1), summed over y in H_{n-1}
             std::array<EF, 3> s{ef_zero(), ef_zero(), ef_zero()};
             const size_t ny = pq_h / 2;
-            for (size_t y = 0; y < ny; y++)
-                for (int X = 1; X <= 3; X++) {
-                    const F xf = from_canonical((uint64_t)X);
-                    auto at = [&](const std::vector<EF>& m, size_t h, size_t col) {
-                        const EF t0 = m[col * h + 2 * y], t1 = m[col * h + 2 * y + 1];
-                        return t0 + (t1 - t0) * xf;
-                    };
-                    const EF eq = at(eq_xis, eq_h, 0);
-                    const EF p0 = at(pq, pq_h, 0), q0 = at(pq, pq_h, 1), p1 = at(pq, pq_h, 2), q1 = at(pq, pq_h, 3);
-                    s[X - 1] += eq * ((p0 * q1 + p1 * q0) + lambda * (q0 * q1));
-                }
+            const unsigned workers = par_workers(ny, 512);
+            std::vector<std::array<EF, 3>> partial(workers, s);
+            parallel_for_tid(ny, workers, [&](unsigned wk, size_t y_begin, size_t y_end) {
+                std::array<EF, 3> acc{ef_zero(), ef_zero(), ef_zero()};
+                for (size_t y = y_begin; y < y_end; y++)
+                    for (int X = 1; X <= 3; X++) {
+                        const F xf = from_canonical((uint64_t)X);
+                        auto at = [&](const std::vector<EF>& m, size_t h, size_t col) {
+                            const EF t0 = m[col * h + 2 * y], t1 = m[col * h + 2 * y + 1];
+                            return t0 + (t1 - t0) * xf;
+                        };
+                        const EF eq = at(eq_xis, eq_h, 0);
+                        const EF p0 = at(pq, pq_h, 0), q0 = at(pq, pq_h, 1), p1 = at(pq, pq_h, 2), q1 = at(pq, pq_h, 3);
+                        acc[X - 1] += eq * ((p0 * q1 + p1 * q0) + lambda * (q0 * q1));
+                    }
+                partial[wk] = acc;
+            });
+            for (const auto& pa : partial)
+                for (int X = 0; X < 3; X++) s[X] += pa[X];
             for (const EF& e : s) ts.observe_ext(e);
             round_polys.push_back(s);
             const EF r = ts.sample_ext();

@@ -211,17 +211,19 @@ inline void prove_zerocheck_and_logup(DuplexSponge& ts, int l_skip, int max_cons
             const std::vector<MatPart> mats = a.view_mats();
             const size_t height = a.height();
             unstacked[t].resize(height);
-            for (size_t i = 0; i < height; i++) {
-                std::vector<std::vector<F>> row_parts;
-                row_parts.push_back({i == 0 ? f_one() : f_zero(), i != height - 1 ? f_one() : f_zero(),
-                                     i == height - 1 ? f_one() : f_zero()});
-                for (const MatPart& m : mats) {
-                    std::vector<F> row(m.width);
-                    for (size_t j = 0; j < m.width; j++) row[j] = m.at((i + (m.is_rot ? 1 : 0)) % height, j);
-                    row_parts.push_back(row);
+            parallel_for(height, [&](size_t i_begin, size_t i_end) {
+                for (size_t i = i_begin; i < i_end; i++) {
+                    std::vector<std::vector<F>> row_parts;
+                    row_parts.push_back({i == 0 ? f_one() : f_zero(), i != height - 1 ? f_one() : f_zero(),
+                                         i == height - 1 ? f_one() : f_zero()});
+                    for (const MatPart& m : mats) {
+                        std::vector<F> row(m.width);
+                        for (size_t j = 0; j < m.width; j++) row[j] = m.at((i + (m.is_rot ? 1 : 0)) % height, j);
+                        row_parts.push_back(row);
+                    }
+                    unstacked[t][i] = eval_interactions(a, row_parts, beta_pows);
                 }
-                unstacked[t][i] = eval_interactions(a, row_parts, beta_pows);
-            }
+            }, 16);
         }
         gkr_input.assign(size_t(1) << (l_skip + n_logup), Frac{ef_zero(), ef_zero()});
         for (const SortedCol& sc : ilayout.sorted_cols) {

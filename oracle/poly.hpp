@@ -182,11 +182,14 @@ inline void fold_mle_evals(std::vector<EF>& values, size_t& height, size_t width
     if (height <= 1) return;
     const size_t nh = height / 2;
     std::vector<EF> out(nh * width);
-    for (size_t c = 0; c < width; c++)
-        for (size_t y = 0; y < nh; y++) {
-            const EF t0 = values[c * height + 2 * y], t1 = values[c * height + 2 * y + 1];
-            out[c * nh + y] = t0 + (t1 - t0) * r;
+    const size_t h0 = height;
+    parallel_for(nh * width, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            const size_t c = i / nh, y = i % nh;
+            const EF t0 = values[c * h0 + 2 * y], t1 = values[c * h0 + 2 * y + 1];
+            out[i] = t0 + (t1 - t0) * r;
         }
+    }, 4096);
     values.swap(out);
     height = nh;
 }

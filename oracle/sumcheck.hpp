@@ -164,7 +164,13 @@ inline std::array<std::vector<EF>, WD> sumcheck_uni_round0_poly(
     }
     std::vector<std::array<EF, WD>> evals(N * d);
     for (auto& e : evals) e.fill(ef_zero());
-    for (size_t x = 0; x < (size_t(1) << n); x++) {
+    // the sum over x is split over host threads (per-worker partial sums; exact field additions commute)
+    const size_t n_x = size_t(1) << n;
+    const unsigned workers = par_workers(n_x, 4);
+    std::vector<std::vector<std::array<EF, WD>>> partial(workers, evals);
+    parallel_for_tid(n_x, workers, [&](unsigned wk, size_t x_begin, size_t x_end) {
+    std::vector<std::array<EF, WD>>& evals = partial[wk];
+    for (size_t x = x_begin; x < x_end; x++) {
         // mats_at_zs[m][col][coset * N + z_idx]
         std::vector<std::vector<std::vector<F>>> at(mats.size());
         for (size_t mi = 0; mi < mats.size(); mi++) {
@@ -196,6 +202,10 @@ inline std::array<std::vector<EF>, WD> sumcheck_uni_round0_poly(
             z *= omega_skip;
         }
     }
+    });
+    for (const auto& pe : partial)
+        for (size_t i = 0; i < N * d; i++)
+            for (size_t k = 0; k < WD; k++) evals[i][k] += pe[i][k];
     for (size_t k = 0; k < WD; k++) {
         std::vector<EF> vals(N * d);
         for (size_t i = 0; i < N * d; i++) vals[i] = evals[i][k];
@@ -227,12 +237,14 @@ inline std::vector<EF> fold_ple_evals(int l_skip, const MatPart& mat, EF r, size
     }
     const size_t off = mat.is_rot ? 1 : 0;
     std::vector<EF> out(new_height * mat.width);
-    for (size_t j = 0; j < mat.width; j++)
-        for (size_t x = 0; x < new_height; x++) {
+    parallel_for(mat.width * new_height, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            const size_t j = i / new_height, x = i % new_height;
             EF acc = ef_zero();
             for (size_t z = 0; z < N; z++) acc += L[z] * mat.at(((x << l_skip) + z + off) % mat.height, j);
-            out[j * new_height + x] = acc;
+            out[i] = acc;
         }
+    }, 1024);
     *new_height_out = new_height;
     return out;
 }
@@ -259,18 +271,27 @@ inline std::array<std::vector<EF>, WD> sumcheck_round_poly_evals(
         return out;
     }
     for (size_t k = 0; k < WD; k++) out[k].assign(d, ef_zero());
-    for (size_t y = 0; y < (size_t(1) << (n - 1)); y++)
-        for (int X = 1; X <= d; X++) {
-            const EF xe = ef_from_u64((uint64_t)X);
-            std::vector<std::vector<EF>> rows(mats.size());
-            for (size_t mi = 0; mi < mats.size(); mi++)
-                for (size_t c = 0; c < mats[mi].width; c++) {
-                    const EF t0 = mats[mi].at(2 * y, c), t1 = mats[mi].at(2 * y + 1, c);
-                    rows[mi].push_back(t0 + (t1 - t0) * xe);
-                }
-            const auto v = w(xe, y, rows);
-            for (size_t k = 0; k < WD; k++) out[k][X - 1] += v[k];
-        }
+    const size_t n_y = size_t(1) << (n - 1);
+    const unsigned workers = par_workers(n_y, 16);
+    std::vector<std::array<std::vector<EF>, WD>> partial(workers, out);
+    parallel_for_tid(n_y, workers, [&](unsigned wk, size_t y_begin, size_t y_end) {
+        std::array<std::vector<EF>, WD>& acc = partial[wk];
+        for (size_t y = y_begin; y < y_end; y++)
+            for (int X = 1; X <= d; X++) {
+                const EF xe = ef_from_u64((uint64_t)X);
+                std::vector<std::vector<EF>> rows(mats.size());
+                for (size_t mi = 0; mi < mats.size(); mi++)
+                    for (size_t c = 0; c < mats[mi].width; c++) {
+                        const EF t0 = mats[mi].at(2 * y, c), t1 = mats[mi].at(2 * y + 1, c);
+                        rows[mi].push_back(t0 + (t1 - t0) * xe);
+                    }
+                const auto v = w(xe, y, rows);
+                for (size_t k = 0; k < WD; k++) acc[k][X - 1] += v[k];
+            }
+    });
+    for (const auto& pa : partial)
+        for (size_t k = 0; k < WD; k++)
+            for (int X = 0; X < d; X++) out[k][X] += pa[k][X];
     return out;
 }
 

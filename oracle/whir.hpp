@@ -61,17 +61,28 @@ inline std::vector<uint32_t> prove_whir_opening(DuplexSponge& ts, int l_skip, in
     // f_evals = sum_j mu^j * hypercube evals of the MLE whose coefficients are the RS message of column j
     std::vector<EF> f_evals(height, ef_zero());
     {
-        EF mu_pow = ef_one();
+        // columns are split over host threads, each with its own partial sum (exact additions commute)
+        std::vector<const F*> cols;
         for (const StackedPcsData* d : commits) {
             if (d->matrix.height != height) throw std::invalid_argument("commit heights differ");
-            for (size_t c = 0; c < d->matrix.width; c++) {
-                std::vector<F> x(d->matrix.col(c), d->matrix.col(c) + height);
+            for (size_t c = 0; c < d->matrix.width; c++) cols.push_back(d->matrix.col(c));
+        }
+        std::vector<EF> mu_pows(cols.size(), ef_one());
+        for (size_t j = 1; j < cols.size(); j++) mu_pows[j] = mu_pows[j - 1] * mu;
+        const unsigned workers = par_workers(cols.size(), 1);
+        std::vector<std::vector<EF>> partial(workers);
+        parallel_for_tid(cols.size(), workers, [&](unsigned wk, size_t c_begin, size_t c_end) {
+            std::vector<EF>& acc = partial[wk];
+            acc.assign(height, ef_zero());
+            for (size_t j = c_begin; j < c_end; j++) {
+                std::vector<F> x(cols[j], cols[j] + height);
                 eval_to_coeff_rs_message_inplace(l_skip, x.data(), height);
                 mle_coeffs_to_evals_inplace(x.data(), height);
-                for (size_t i = 0; i < height; i++) f_evals[i] += mu_pow * x[i];
-                mu_pow = mu_pow * mu;
+                for (size_t i = 0; i < height; i++) acc[i] += mu_pows[j] * x[i];
             }
-        }
+        });
+        for (const auto& pa : partial)
+            for (size_t i = 0; i < height; i++) f_evals[i] += pa[i];
     }
     std::vector<EF> w_evals = evals_mobius_eq_hypercube(u);
 
@@ -86,12 +97,24 @@ inline std::vector<uint32_t> prove_whir_opening(DuplexSponge& ts, int l_skip, in
         for (int round = 0; round < k; round++) {
             EF s[2] = {ef_zero(), ef_zero()};
             const size_t ny = f_evals.size() / 2;
-            for (int X = 1; X <= 2; X++) {
-                const F xf = from_canonical((uint64_t)X);
-                for (size_t y = 0; y < ny; y++) {
-                    const EF f_x = f_evals[2 * y] + (f_evals[2 * y + 1] - f_evals[2 * y]) * xf;
-                    const EF w_x = w_evals[2 * y] + (w_evals[2 * y + 1] - w_evals[2 * y]) * xf;
-                    s[X - 1] += f_x * w_x;
+            {
+                const unsigned workers = par_workers(ny, 2048);
+                std::vector<std::array<EF, 2>> partial(workers, {ef_zero(), ef_zero()});
+                parallel_for_tid(ny, workers, [&](unsigned wk, size_t y_begin, size_t y_end) {
+                    for (int X = 1; X <= 2; X++) {
+                        const F xf = from_canonical((uint64_t)X);
+                        EF acc = ef_zero();
+                        for (size_t y = y_begin; y < y_end; y++) {
+                            const EF f_x = f_evals[2 * y] + (f_evals[2 * y + 1] - f_evals[2 * y]) * xf;
+                            const EF w_x = w_evals[2 * y] + (w_evals[2 * y + 1] - w_evals[2 * y]) * xf;
+                            acc += f_x * w_x;
+                        }
+                        partial[wk][X - 1] = acc;
+                    }
+                });
+                for (const auto& pa : partial) {
+                    s[0] += pa[0];
+                    s[1] += pa[1];
                 }
             }
             ts.observe_ext(s[0]);
@@ -100,12 +123,17 @@ inline std::vector<uint32_t> prove_whir_opening(DuplexSponge& ts, int l_skip, in
             push_ef(sec_polys, s[1]);
             sec_fold_pow.push_back(ts.grind(cfg.folding_pow_bits).v);
             const EF alpha = ts.sample_ext();
-            for (size_t y = 0; y < ny; y++) {
-                f_evals[y] = f_evals[2 * y] + alpha * (f_evals[2 * y + 1] - f_evals[2 * y]);
-                w_evals[y] = w_evals[2 * y] + alpha * (w_evals[2 * y + 1] - w_evals[2 * y]);
+            {
+                std::vector<EF> f2(ny), w2(ny);
+                parallel_for(ny, [&](size_t b, size_t e) {
+                    for (size_t y = b; y < e; y++) {
+                        f2[y] = f_evals[2 * y] + alpha * (f_evals[2 * y + 1] - f_evals[2 * y]);
+                        w2[y] = w_evals[2 * y] + alpha * (w_evals[2 * y + 1] - w_evals[2 * y]);
+                    }
+                }, 4096);
+                f_evals.swap(f2);
+                w_evals.swap(w2);
             }
-            f_evals.resize(ny);
-            w_evals.resize(ny);
         }
         std::vector<EF> g_coeffs = f_evals;
         mle_evals_to_coeffs_inplace(g_coeffs);
@@ -115,11 +143,13 @@ inline std::vector<uint32_t> prove_whir_opening(DuplexSponge& ts, int l_skip, in
             // RS codeword of g on the domain of size 2^(log_rs_domain_size - 1): component-wise DFT
             const size_t N = size_t(1) << (log_rs_domain_size - 1);
             ColMajor cw(N, 4);
-            for (int comp = 0; comp < 4; comp++) {
-                F* col = cw.col(comp);
-                for (size_t i = 0; i < g_coeffs.size(); i++) col[i] = g_coeffs[i].c[comp];
-                dft_inplace(col, N);
-            }
+            parallel_for(4, [&](size_t b, size_t e) {
+                for (size_t comp = b; comp < e; comp++) {
+                    F* col = cw.col(comp);
+                    for (size_t i = 0; i < g_coeffs.size(); i++) col[i] = g_coeffs[i].c[comp];
+                    dft_inplace(col, N);
+                }
+            });
             g_tree = merkle_tree_new(std::move(cw), size_t(1) << k);
             const Digest g_commit = g_tree.root();
             ts.observe_commit(g_commit);
