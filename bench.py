@@ -308,7 +308,8 @@ def run_swirl(args):
         # prefetched (`pending` is cleared before the region) and waits for its own copy.
         ticket = pending.pop() if pending else transporter.submit(host)
         pending.append(transporter.submit(host))
-        proof = prove(transporter.matrix(ticket).buffer)
+        proof = prove(transporter.matrix(ticket).buffer)  # frees the PCS data that aliases the buffer
+        transporter.retire(ticket)
         return proof
 
     def gather(root):
@@ -322,7 +323,10 @@ def run_swirl(args):
         t0 = time.time()
         a.record(stream)
         walls = []
+        proof = None
         for _ in range(steps):
+            if proof is not None:
+                proof.release()  # explicit: the host proof buffers go back to the pool (what a pooling allocator does)
             ts_ = time.perf_counter()
             proof = fn()
             walls.append(1e3 * (time.perf_counter() - ts_))
@@ -370,7 +374,7 @@ def run_swirl(args):
         for nm in ("commit", "commit_host", "prove_batch_constraints", "prove_openings"):
             wrap(nm)
     for _ in range(max(args.warmup, 3)):
-        step_device()
+        step_device().release()
     l0 = dev.launch_count()
     ms, roots, t0, t1, proof = timed(step_device, args.steps)
     launches = dev.launch_count() - l0
@@ -386,14 +390,18 @@ def run_swirl(args):
 
     # end to end through host buffers
     for _ in range(2):
-        step_host()
+        step_host().release()
+    for t_ in pending:
+        transporter.retire(t_)
     pending.clear()  # nothing transported before the timed region counts for it
     torch.cuda.synchronize()
     ms_e2e, roots_e2e, _, _, proof_e2e = timed(step_host, args.steps)
+    for t_ in pending:
+        transporter.retire(t_)
     pending.clear()
     e2e_value = world * CELLS / (ms_e2e / args.steps / 1e3)
     for _ in range(2):
-        step_host_latency()
+        step_host_latency().release()
     ms_lat, roots_lat, _, _, proof_lat = timed(step_host_latency, args.steps)
     assert np.array_equal(proof.words(), proof_lat.words()), "device and host paths produce different proofs"
     assert all(np.array_equal(a, b) for a, b in zip(roots, roots_e2e)), "device and host paths disagree"

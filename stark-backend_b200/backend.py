@@ -8,6 +8,7 @@ PyTorch is plumbing only: it owns device buffers and the CUDA context; every com
 through the C ABI of libswirl_b200.so.
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -162,6 +163,7 @@ class StackedPcsData:
 
     def __init__(self, device, handle, params, keepalive):
         self._dev, self._h, self.params, self._keep = device, handle, params, keepalive
+        device._live_pcs.add(self)  # B200Device.close() frees the handles that are still alive before the context goes
         lib = device.lib
         self.height = int(lib.swirl_pcs_stacked_height(handle))
         self.width = int(lib.swirl_pcs_stacked_width(handle))
@@ -232,21 +234,45 @@ class TraceTransporter:
         self.buffers = [dev.alloc(self.height * self.width) for _ in range(depth)]
         self.stream = torch.cuda.Stream(device=dev.torch_device)
         self.next = 0
+        # per buffer: event recorded on the library's stream after the last consumer of the buffer was enqueued
+        self.consumed = [None] * depth
+        self.outstanding = 0
 
     def submit(self, host_tensor):
+        """Starts the copy into the next buffer.  At most `depth` tickets may be outstanding (submitted and not yet
+        `retire`d); the copy waits, on the device, for the work that last read this buffer."""
         assert host_tensor.is_pinned() and host_tensor.numel() == self.height * self.width
-        buf = self.buffers[self.next]
+        if self.outstanding >= len(self.buffers):
+            raise RuntimeError(f"TraceTransporter: {self.outstanding} tickets outstanding with depth {len(self.buffers)}; "
+                               "retire() a ticket before submitting another trace")
+        slot = self.next
+        buf = self.buffers[slot]
         self.next = (self.next + 1) % len(self.buffers)
+        self.outstanding += 1
         ev = torch.cuda.Event()
         with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])  # earlier readers of this buffer on the library's stream
             buf.copy_(host_tensor, non_blocking=True)
             ev.record(self.stream)
-        return buf, ev
+        return buf, ev, slot
 
     def matrix(self, ticket):
-        buf, ev = ticket
-        self.dev.torch_stream().wait_event(ev)  # ordered on the device; the host does not block
+        """The DeviceMatrix of a ticket; the library's stream waits for the copy (the host does not block).  NOTE: a
+        commitment of a single full-size trace aliases this buffer as its stacked matrix (commit.cu), so the
+        StackedPcsData / Proof.common_main_pcs made from it must be freed (or the proof finished) before `retire`."""
+        buf, ev, _ = ticket
+        self.dev.torch_stream().wait_event(ev)
         return DeviceMatrix(buf, self.height, self.width)
+
+    def retire(self, ticket):
+        """Everything that reads the ticket's buffer has been enqueued on the library's stream: the buffer may be reused by a
+        later submit (which waits for that work on the device)."""
+        _, _, slot = ticket
+        ev = torch.cuda.Event()
+        ev.record(self.dev.torch_stream())
+        self.consumed[slot] = ev
+        self.outstanding -= 1
 
 
 class WhirConfig:
@@ -376,9 +402,12 @@ class B200Device:
         h = C.c_void_p()
         check(self.lib.swirl_ctx_create(self.device, C.byref(h)))
         self.ctx = h
+        self._live_pcs = weakref.WeakSet()
 
     def close(self):
         if self.ctx:
+            for pcs in list(self._live_pcs):  # PCS data must not outlive the context that owns its memory
+                pcs.free()
             self.lib.swirl_ctx_destroy(self.ctx)
             self.ctx = None
 
@@ -428,7 +457,7 @@ class B200Device:
 
     # -- host proof buffers -------------------------------------------------------------------------------------
     # Fresh multi-megabyte numpy buffers are fresh anonymous pages: the first write into each 4 KiB page faults, which costs
-    # ~1 ms for the 3.4 MB WHIR proof.  Buffers handed back by Proof.__del__ are reused (what a pooling allocator such as
+    # ~1 ms for the 3.4 MB WHIR proof.  Buffers handed back by Proof.release() are reused (what a pooling allocator such as
     # the reference's mimalloc does for the Rust Vecs).
     def host_buffer(self, n_words):
         pool = self.__dict__.setdefault("_host_pool", {})
@@ -438,13 +467,11 @@ class B200Device:
         return np.zeros(int(n_words), dtype=np.uint32)
 
     def recycle_host_buffer(self, buf):
-        import sys
-
-        if isinstance(buf, np.ndarray) and buf.base is None and buf.dtype == np.uint32 and buf.size >= (1 << 16) \
-                and sys.getrefcount(buf) <= 3:  # nobody else holds it: safe to hand out again
+        """Called by Proof.release() only (never from a finaliser): the caller has given the buffer up."""
+        if isinstance(buf, np.ndarray) and buf.base is None and buf.dtype == np.uint32 and buf.size >= (1 << 16):
             pool = self.__dict__.setdefault("_host_pool", {})
             lst = pool.setdefault(int(buf.size), [])
-            if len(lst) < 4:
+            if len(lst) < 4 and not any(b is buf for b in lst):
                 lst.append(buf)
 
     def trim(self):

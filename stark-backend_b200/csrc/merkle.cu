@@ -216,7 +216,8 @@ __global__ void query_proofs_kernel(const uint32_t* __restrict__ layers, size_t 
     const int l = (int)(g % depth);
     // layer l starts at digest offset 2S - (S >> (l-1)) for l >= 1
     const size_t off = l == 0 ? 0 : 2 * S - (S >> (l - 1));
-    const size_t idx = ((size_t)indices[q] >> l) ^ 1;
+    // indices are query indices < S (S a power of two): masking is the identity for valid input and keeps a bad one in bounds
+    const size_t idx = (((size_t)indices[q] & (S - 1)) >> l) ^ 1;
     uint32_t d[8];
     load_digest(d, layers + (off + idx) * 8);
     store_digest(out + g * 8, d);
@@ -231,7 +232,7 @@ __global__ void open_rows_kernel(const uint32_t* __restrict__ matrix, size_t hei
     if (g >= num_queries * per_q) return;
     const size_t q = g / per_q, rem = g % per_q;
     const size_t t = rem / width, c = rem % width;
-    const size_t row = t * S + indices[q];
+    const size_t row = t * S + ((size_t)indices[q] & (S - 1));
     out[g] = row < height ? __ldg(matrix + c * height + row) : 0u;
 }
 

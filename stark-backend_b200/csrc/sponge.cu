@@ -177,17 +177,20 @@ extern "C" int swirl_transcript_sample(swirl_transcript* ts, uint32_t* out, size
 extern "C" int swirl_transcript_sample_bits(swirl_transcript* ts, int bits, uint32_t* out) {
     SWIRL_REQUIRE(ts && out, "null argument");
     SWIRL_REQUIRE(bits >= 0 && bits < 31, "bits");
+    SWIRL_REQUIRE(ts->absorb_idx < 8 && ts->sample_idx <= 8, "sponge indices");
     *out = Transcript(ts).sample_bits(bits);
     return 0;
 }
 extern "C" int swirl_transcript_check_witness(swirl_transcript* ts, int bits, uint32_t witness, int* ok) {
     SWIRL_REQUIRE(ts && ok, "null argument");
     SWIRL_REQUIRE(bits >= 0 && bits < 31 && witness < bb::P, "bits / witness");
+    SWIRL_REQUIRE(ts->absorb_idx < 8 && ts->sample_idx <= 8, "sponge indices");
     *ok = Transcript(ts).check_witness(bits, bb::to_mont(witness)) ? 1 : 0;
     return 0;
 }
 extern "C" int swirl_transcript_grind(swirl_ctx* ctx, swirl_transcript* ts, int bits, uint32_t* witness) {
     SWIRL_REQUIRE(ctx && ts && witness, "null argument");
+    SWIRL_REQUIRE(ts->absorb_idx < 8 && ts->sample_idx <= 8, "sponge indices");
     uint32_t wm = 0;
     SWIRL_TRY(transcript_grind(ctx, ts, bits, &wm));
     *witness = bb::from_mont(wm);

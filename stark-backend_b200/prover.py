@@ -46,13 +46,23 @@ class Proof:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
-    def __del__(self):
+    def release(self):
+        """Hand the large host proof buffers back to the device's pool for the next proof (what a pooling allocator does for
+        the reference's Vecs).  EXPLICIT: the caller promises not to read this proof's sections afterwards; a proof that is
+        merely dropped keeps its buffers until the garbage collector frees them.  Also usable as a context manager."""
         dev = self.__dict__.pop("_device", None)
-        if dev is not None:  # large host buffers go back to the device's pool when nobody else references them
+        if dev is not None:
             for name in ("whir_proof", "stacking_proof", "constraints_proof"):
                 buf = self.__dict__.pop(name, None)
                 if buf is not None:
                     dev.recycle_host_buffer(buf)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+        return False
 
     def words(self):
         return np.concatenate([self.common_main_commit, self.constraints_proof, self.stacking_proof, self.whir_proof])

@@ -439,3 +439,10 @@ def test_trace_transporter_double_buffering(dev, oracle):
         root, pcs = dev.commit(params, [tp.matrix(tickets[i])])
         assert np.array_equal(root, oracle.stacked_commit(l_skip, n_stack, log_blowup, k, [(hosts[i], H, w)], want_codeword=False)[0])
         pcs.free()
+        tp.retire(tickets[i])  # its readers are enqueued: the buffer may be overwritten by the submit after next
+    # the depth is enforced: a third outstanding ticket is refused instead of overwriting a trace in use
+    a, b = tp.submit(pinned[0]), tp.submit(pinned[1])
+    with pytest.raises(RuntimeError):
+        tp.submit(pinned[2])
+    tp.retire(a)
+    tp.retire(b)
