@@ -240,14 +240,23 @@ def run_reference(args):
     })
 
 
-# kernel families of swirl_ctx_timing_read with the algorithmic bytes of one launch on this workload
-# dram__bytes_read.sum + dram__bytes_write.sum of the family's largest launch, from the committed ncu --set full capture
-NCU_TRAFFIC = {
-    "leaf": {"bytes": 2150351000 + 8435968,
-             "note": "commit launch (2^21 x 256 codeword): 2.1504 GB read + 8.4 MB written vs 2.1517 GB algorithmic; "
-                     "profiles/r1q_top_kernels_ncu.txt"},
-    "bc_round0": {"bytes": 1249211000 + 60525056, "note": "1.249 GB read + 61 MB written vs 1.086 GB algorithmic; profiles/r1q_top_kernels_ncu.txt"},
-}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the `ncu --set full` capture of
+    this workload that tools/ncu_traffic.py summarises into profiles/ncu_traffic.json (refreshed whenever a kernel changes;
+    the file names the capture and the commit it was taken at)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
+
+
+def int32_peak():
+    """Measured 32-bit integer issue rates of this pool's B200 (tools/int_roofline.cu -> profiles/int32_peaks.json); the
+    driver-written MEASURED_PEAKS.json has no integer figure."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "int32_peaks.json")))
+    except Exception:
+        return {"imad_tops": 17.96, "mixed_issue_tops": 24.1, "source": "fallback: profiles/r1_int_roofline.jsonl"}
 
 
 def run_swirl(args):
@@ -445,17 +454,7 @@ def run_swirl(args):
                                          "hashing by column groups inside swirl_commit_host"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {
-                "kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": pk_["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk_["hbm_gbs"], "peak_source": pk_kind,
-                "traffic": NCU_TRAFFIC.get(dom, {}).get("bytes"), "traffic_note": NCU_TRAFFIC.get(dom, {}).get("note"),
-                "ms_per_launch": dom_ms, "launches_per_step": fam[dom][1], "algorithmic_bytes_per_step": fam[dom][3],
-                "achieved_definition": "algorithmic bytes of all launches of the family in a step / their summed duration",
-                "timing": "CUDA events around every launch of the family, over a repeat of the K timed steps",
-                "note": "the dominant kernel is bound by the 32-bit integer multiplier pipe, not by HBM: ncu shows the fma-heavy pipe "
-                        "82 % busy and 1.2 % of peak DRAM throughput (profiles/r1q_top_kernels_ncu.txt); see int_pipe and DESIGN.md section 4",
-                "int_pipe": int_pipe_roofline(leaf_perms, fam["leaf"][2], clocks),
-            },
+            "roofline": roofline_block(names[dom], dom, fam, ach, pk_, pk_kind, leaf_perms, clocks),
             "phases_ms_per_step": {k: v[2] for k, v in fam.items()},
             "phases_note": "kernel families with CUDA-event spans only; GKR tree/leaves, stacked reduction, WHIR and host latency are the rest",
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
@@ -479,20 +478,36 @@ def run_swirl(args):
         dist.destroy_process_group()
 
 
-def int_pipe_roofline(perms, ms, clocks):
-    """Integer-multiplier roofline of the Poseidon2 leaf kernel.  Measured on B200 (tools/int_roofline.cu,
-    profiles/r1_p2_iterate_ncu.txt): 32-bit integer multiplies issue only on the fma-heavy pipe,
-    64 lanes/clk/SM, IMAD 1 pass, IMAD.WIDE / IMAD.HI 2 passes.  A Montgomery product needs
-    IMAD.WIDE + IMAD + IMAD.HI = 5 passes; one permutation has 564 S-box products and 91 IMADs of
-    the internal diagonal => 2911 passes minimum."""
+def roofline_block(kernel_name, dom, fam, hbm_ach, pk_, pk_kind, leaf_perms, clocks):
+    """The dominant kernel family against BOTH rooflines; `bound` names the binding one.  The Poseidon2 leaf kernel is bound by
+    32-bit integer issue, so `achieved`/`peak`/`frac` are its integer figures and the HBM figures sit beside
+    them as `hbm`; for an HBM-bound dominant kernel it is the other way round."""
+    ip = int32_peak()
+    tr = ncu_traffic().get(dom, {})
+    hbm = {"achieved": hbm_ach, "peak": pk_["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / pk_["hbm_gbs"], "peak_source": pk_kind + " (MEASURED_PEAKS.json)"}
+    common = {"kernel": kernel_name, "ms_per_launch": fam[dom][0], "launches_per_step": fam[dom][1],
+              "algorithmic_bytes_per_step": fam[dom][3], "traffic": tr.get("bytes_per_launch"), "traffic_note": tr.get("note"),
+              "achieved_definition": "algorithmic units of all launches of the family in a step / their summed duration",
+              "timing": "CUDA events around every launch of the family, over a repeat of the K timed steps"}
+    if dom != "leaf":
+        return {**common, "bound": "hbm", **hbm}
+    # one permutation = 564 S-box Montgomery products (IMAD.WIDE + IMAD + IMAD.HI = 5 multiplier-pipe passes) + 91 IMADs of
+    # the internal diagonal = 2911 passes of the fma-heavy pipe: the multiplier roofline is the measured IMAD rate / 2911
     passes = 564 * 5 + 91
-    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-    peak = 64 * 148 * mhz * 1e6 / passes / 1e9
-    ach = perms / (ms / 1e3) / 1e9 if ms else 0.0
-    return {"kernel": "leaf_tree_kernel", "perms_per_step": perms, "gperm_per_s": ach, "peak_gperm_per_s": peak, "frac": ach / peak,
-            "model": "fma-heavy pipe, 64 lanes/clk/SM x 148 SM x sm_max_mhz / 2911 multiplier passes per permutation",
-            "ncu": "sm__pipe_fmaheavy_cycles_active 81.8 % of elapsed (the pipe also carries ~850 IMAD.IADD per permutation that ptxas "
-                   "places there; moving them to the ALU pipe was measured slower, profiles/r1_p2_v3_experiment_ncu.txt)"}
+    ms = fam["leaf"][2]
+    ach = leaf_perms / (ms / 1e3) / 1e9 if ms else 0.0
+    peak = ip["imad_tops"] * 1e12 / passes / 1e9
+    return {**common, "bound": "int32", "achieved": ach, "peak": peak, "unit": "Gperm/s", "frac": ach / peak,
+            "peak_source": f"measured IMAD issue rate {ip['imad_tops']} Tops/s ({ip.get('source', 'profiles/int32_peaks.json')}) / {passes} "
+                           "multiplier passes per permutation",
+            "perms_per_step": leaf_perms,
+            "issue_bound": {"note": "the permutation is ~5800 thread instructions; the measured mixed IMAD+ALU issue rate of the chip "
+                                    "bounds it more tightly than the multiplier pipe alone",
+                            "peak_gperm_s": ip.get("mixed_issue_tops", 24.1) * 1e12 / 5800 / 1e9,
+                            "frac": ach / (ip.get("mixed_issue_tops", 24.1) * 1e12 / 5800 / 1e9)},
+            "hbm": hbm,
+            "reference_gpu": "the reference's own Poseidon2 kernels compiled for sm_100 reach 3.0 Gperm/s on the same box "
+                             "(profiles/r2a_reference_gpu_kernels_vs_swirl.jsonl)"}
 
 
 def main():

@@ -32,6 +32,8 @@ extern "C" {
     pub fn swirl_ctx_stream(ctx: *mut SwirlCtx) -> *mut c_void;
     pub fn swirl_ctx_launch_count(ctx: *mut SwirlCtx) -> u64;
     pub fn swirl_ctx_set_ntt_plan(ctx: *mut SwirlCtx, max_log_radix: c_int, scratch_bytes: usize) -> c_int;
+    pub fn swirl_ctx_set_cache_rs_code_matrix(ctx: *mut SwirlCtx, on: c_int) -> c_int;
+    pub fn swirl_ctx_mem_stats(ctx: *mut SwirlCtx, reset_peak: c_int, out: *mut u64) -> c_int;
     pub fn swirl_last_error() -> *const c_char;
     pub fn swirl_ctx_timing_enable(ctx: *mut SwirlCtx, on: c_int) -> c_int;
     pub fn swirl_ctx_timing_read(ctx: *mut SwirlCtx, slot: c_int, total_ms: *mut f64, count: *mut u64) -> c_int;
@@ -61,6 +63,7 @@ extern "C" {
     pub fn swirl_commit(ctx: *mut SwirlCtx, params: *const SwirlPcsParams, d_traces: *const SwirlMatrix, n_traces: usize, h_root: *mut u32, out: *mut *mut SwirlPcs) -> c_int;
     pub fn swirl_commit_host(ctx: *mut SwirlCtx, params: *const SwirlPcsParams, h_traces: *const SwirlMatrix, n_traces: usize, h_root: *mut u32, out: *mut *mut SwirlPcs) -> c_int;
     pub fn swirl_pcs_free(ctx: *mut SwirlCtx, pcs: *mut SwirlPcs) -> c_int;
+    pub fn swirl_pcs_open_rows(ctx: *mut SwirlCtx, pcs: *const SwirlPcs, d_indices: *const u32, num_queries: usize, d_out: *mut u32) -> c_int;
     pub fn swirl_pcs_stacked_height(pcs: *const SwirlPcs) -> u64;
     pub fn swirl_pcs_stacked_width(pcs: *const SwirlPcs) -> u64;
     pub fn swirl_pcs_codeword_height(pcs: *const SwirlPcs) -> u64;

@@ -55,6 +55,14 @@ uint64_t swirl_ctx_launch_count(swirl_ctx* ctx);   /* kernels launched through t
 /* Tuning / test knobs: largest single-pass NTT radix (log2, default 11, range 1..13) and the
  * bytes of inter-pass scratch kept per column group (default 48 MiB, meant to stay L2 resident). */
 int swirl_ctx_set_ntt_plan(swirl_ctx* ctx, int max_log_radix, size_t scratch_bytes);
+/* GpuProverConfig::cache_rs_code_matrix (reference cuda-backend/src/device.rs:102-121).  on (default here): commitments keep
+ * their RS codeword for the WHIR openings.  off (the reference's default): the codeword is streamed through a 32-column
+ * scratch at commit time and the opened rows are re-encoded by column groups in the openings -- the large-trace mode. */
+int swirl_ctx_set_cache_rs_code_matrix(swirl_ctx* ctx, int on);
+/* Device memory the context's scratch arena holds (blocks of 1 MiB and more; the caller's own buffers are not counted):
+ * out = { bytes handed out now, high-water mark of that, bytes held (idle + handed out), free bytes on the device }.
+ * reset_peak != 0 restarts the high-water mark.  Reference: MemTracker (cuda-common/src/memory_manager). */
+int swirl_ctx_mem_stats(swirl_ctx* ctx, int reset_peak, uint64_t out[4]);
 const char* swirl_last_error(void);
 /* Per-kernel-family device timing with CUDA events on the ctx stream (off by default).
  * enable(on) clears the recorded spans; read() synchronises and returns the summed duration and
@@ -193,6 +201,10 @@ int swirl_commit(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_mat
 int swirl_commit_host(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* h_traces,
                       size_t n_traces, uint32_t h_root[8], swirl_pcs** out);
 int swirl_pcs_free(swirl_ctx* ctx, swirl_pcs* pcs);
+/* Opened rows of the commitment's codeword for `num_queries` query indices (device u32, < query_stride):
+ * d_out[q][t][c], t < 2^k_whir strided rows, c < stacked width (reference: MerkleTreeGpu::batch_open_rows,
+ * cuda-backend/src/merkle_tree.rs:199-).  Works with and without a cached codeword (swirl_ctx_set_cache_rs_code_matrix). */
+int swirl_pcs_open_rows(swirl_ctx* ctx, const swirl_pcs* pcs, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out);
 
 /* PCS data accessors */
 uint64_t swirl_pcs_stacked_height(const swirl_pcs* pcs);

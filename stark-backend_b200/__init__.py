@@ -19,3 +19,4 @@ from .backend import (  # noqa: F401
 )
 from .prover import AirProvingKey, CommittedTraceData, Coordinator, Proof, SystemParams  # noqa: F401,E402
 from . import codec  # noqa: F401,E402
+from . import memory  # noqa: F401,E402

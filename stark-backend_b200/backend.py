@@ -192,6 +192,18 @@ class StackedPcsData:
     def commit(self):
         return self.tree.root()
 
+    def open_rows(self, indices):
+        """Opened rows of the commitment's codeword, (num_queries, rows_per_query, width): from the cached codeword or, with
+        cache_rs_code_matrix = false, re-encoded by column groups (what the WHIR opening does)."""
+        dev = self._dev
+        idx = dev.h2d(np.asarray(indices, dtype=np.uint32))
+        rpq = 1 << self.params.k_whir
+        out = dev.alloc(len(indices) * rpq * self.width)
+        dev._sync_torch()
+        check(dev.lib.swirl_pcs_open_rows(dev.ctx, self._h, idx.data_ptr(), len(indices), out.data_ptr()))
+        dev.synchronize()
+        return out.cpu().numpy().view(np.uint32).reshape(len(indices), rpq, self.width)
+
     def free(self):
         if self._h:
             check(self._dev.lib.swirl_pcs_free(self._dev.ctx, self._h))
@@ -429,6 +441,16 @@ class B200Device:
 
     def launch_count(self):
         return int(self.lib.swirl_ctx_launch_count(self.ctx))
+
+    def set_cache_rs_code_matrix(self, on):
+        """reference: GpuDevice::set_cache_rs_code_matrix (cuda-backend/src/device.rs:108-110)."""
+        check(self.lib.swirl_ctx_set_cache_rs_code_matrix(self.ctx, 1 if on else 0))
+
+    def mem_stats(self, reset_peak=False):
+        """{live, peak, held, device_free} bytes of the context's scratch arena (traces handed in by the caller not counted)."""
+        out = (C.c_uint64 * 4)()
+        check(self.lib.swirl_ctx_mem_stats(self.ctx, 1 if reset_peak else 0, out))
+        return {"live": int(out[0]), "peak": int(out[1]), "held": int(out[2]), "device_free": int(out[3])}
 
     def set_ntt_plan(self, max_log_radix, scratch_bytes=0):
         check(self.lib.swirl_ctx_set_ntt_plan(self.ctx, max_log_radix, scratch_bytes))

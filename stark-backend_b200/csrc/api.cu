@@ -42,6 +42,8 @@ cudaError_t arena_alloc(swirl_ctx* ctx, void** p, size_t bytes) {
     if (it != ctx->arena_free.end() && it->first <= bytes + bytes / 4) {
         *p = it->second;
         ctx->arena_live[*p] = it->first;
+        ctx->arena_live_bytes += it->first;
+        ctx->arena_live_peak = std::max(ctx->arena_live_peak, ctx->arena_live_bytes);
         ctx->arena_free.erase(it);
         return cudaSuccess;
     }
@@ -55,6 +57,8 @@ cudaError_t arena_alloc(swirl_ctx* ctx, void** p, size_t bytes) {
     if (e == cudaSuccess) {
         ctx->arena_live[*p] = bytes;
         ctx->arena_bytes += bytes;
+        ctx->arena_live_bytes += bytes;
+        ctx->arena_live_peak = std::max(ctx->arena_live_peak, ctx->arena_live_bytes);
     }
     return e;
 }
@@ -66,6 +70,7 @@ void arena_free_block(swirl_ctx* ctx, void* p) {
         return;
     }
     ctx->arena_free.emplace(it->second, p);
+    ctx->arena_live_bytes -= it->second;
     ctx->arena_live.erase(it);
 }
 
@@ -175,6 +180,25 @@ int swirl_ctx_set_ntt_plan(swirl_ctx* ctx, int max_log_radix, size_t scratch_byt
     SWIRL_REQUIRE(max_log_radix >= 1 && max_log_radix <= 13, "max_log_radix must be in [1, 13]");
     ctx->ntt_max_log_radix = max_log_radix;
     if (scratch_bytes) ctx->ntt_scratch_bytes = scratch_bytes;
+    return 0;
+}
+
+int swirl_ctx_set_cache_rs_code_matrix(swirl_ctx* ctx, int on) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    ctx->cache_codeword = on != 0;
+    return 0;
+}
+
+int swirl_ctx_mem_stats(swirl_ctx* ctx, int reset_peak, uint64_t out[4]) {
+    SWIRL_REQUIRE(ctx && out, "null argument");
+    size_t free_b = 0, total_b = 0;
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    SWIRL_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    out[0] = ctx->arena_live_bytes;
+    out[1] = ctx->arena_live_peak;
+    out[2] = ctx->arena_bytes;
+    out[3] = free_b;
+    if (reset_peak) ctx->arena_live_peak = ctx->arena_live_bytes;
     return 0;
 }
 

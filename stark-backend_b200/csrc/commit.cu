@@ -65,6 +65,9 @@ __global__ void expand_strided_kernel(const uint32_t* __restrict__ src, uint32_t
 
 using namespace swirl;
 
+// columns per group when the codeword is streamed instead of cached (a multiple of the sponge rate)
+static constexpr uint64_t STREAM_GROUP = 32;
+
 static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* traces, size_t n,
                        uint32_t h_root[8], swirl_pcs* pcs) {
     const int l_skip = params->l_skip, n_stack = params->n_stack;
@@ -127,14 +130,59 @@ static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swi
     SWIRL_REQUIRE((uint64_t(1) << params->k_whir) <= N, "MerkleTreeRowsPerQueryExceeded");
     pcs->codeword_height = N;
     pcs->query_stride = N >> params->k_whir;
-    SWIRL_CUDA(dev_alloc(ctx, &pcs->codeword, N * W));
     SWIRL_CUDA(dev_alloc(ctx, &pcs->layers, (2 * pcs->query_stride - 1) * 8 + 8));
-    SWIRL_TRY(rs_encode(ctx, pcs->stacked, H, H, W, l_skip, params->log_blowup, pcs->codeword));
-    SWIRL_TRY(merkle_commit(ctx, pcs->codeword, N, W, params->k_whir, pcs->layers));
+    // streaming needs whole sponge blocks per group and the fused leaf kernel's per-row state hand-off
+    const bool stream_codeword = !ctx->cache_codeword && W > STREAM_GROUP && (uint64_t(1) << params->k_whir) <= 256;
+    if (!stream_codeword) {
+        SWIRL_CUDA(dev_alloc(ctx, &pcs->codeword, N * W));
+        SWIRL_TRY(rs_encode(ctx, pcs->stacked, H, H, W, l_skip, params->log_blowup, pcs->codeword));
+        SWIRL_TRY(merkle_commit(ctx, pcs->codeword, N, W, params->k_whir, pcs->layers));
+        if (!ctx->cache_codeword) {  // small matrix: encoded in one piece, still not kept
+            dev_free(ctx, pcs->codeword);
+            pcs->codeword = nullptr;
+        }
+    } else {
+        // cache_rs_code_matrix = false: the codeword exists only one column group at a time; the per-row sponge states wait in
+        // HBM between groups (64 B per codeword row) and the last group finishes the tree
+        uint32_t *tmp = nullptr, *state = nullptr;
+        SWIRL_CUDA(dev_alloc(ctx, &tmp, N * STREAM_GROUP));
+        SWIRL_CUDA(dev_alloc(ctx, &state, N * 16));
+        int rc = 0;
+        for (uint64_t c0 = 0; c0 < W && rc == 0; c0 += STREAM_GROUP) {
+            const uint64_t nc = std::min<uint64_t>(STREAM_GROUP, W - c0);
+            rc = rs_encode(ctx, pcs->stacked + c0 * H, H, H, nc, l_skip, params->log_blowup, tmp);
+            if (rc == 0) rc = merkle_commit_columns(ctx, tmp, N, nc, params->k_whir, pcs->layers, state, c0 == 0, c0 + nc >= W);
+        }
+        dev_free(ctx, tmp);
+        dev_free(ctx, state);
+        SWIRL_TRY(rc);
+    }
     SWIRL_CUDA(cudaMemcpyAsync(h_root, pcs->layers + (2 * pcs->query_stride - 2) * 8, 32, cudaMemcpyDeviceToHost,
                                ctx->stream));
     SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
     return 0;
+}
+
+// Opened rows (out[q][t][c], t < 2^log_rpq strided rows per query) of the commitment's codeword.
+int swirl::pcs_open_rows(swirl_ctx* ctx, const swirl_pcs* pcs, int log_rpq, const uint32_t* d_indices, size_t num_queries,
+                         uint32_t* d_out) {
+    const uint64_t H = pcs->layout.height, W = pcs->layout.width, N = pcs->codeword_height;
+    if (pcs->codeword)
+        return matrix_open_rows(ctx, pcs->codeword, N, W, pcs->query_stride, log_rpq, d_indices, num_queries, d_out);
+    // not cached (reference default, cuda-backend/src/device.rs:113-121): encode again, one column group at a time
+    SWIRL_REQUIRE(pcs->stacked, "commitment keeps neither its codeword nor its stacked matrix");
+    const uint64_t group = std::min<uint64_t>(W, STREAM_GROUP);
+    uint32_t* tmp = nullptr;
+    SWIRL_CUDA(dev_alloc(ctx, &tmp, N * group));
+    int rc = 0;
+    for (uint64_t c0 = 0; c0 < W && rc == 0; c0 += group) {
+        const uint64_t nc = std::min(group, W - c0);
+        rc = rs_encode(ctx, pcs->stacked + c0 * H, H, H, nc, pcs->params.l_skip, pcs->params.log_blowup, tmp);
+        if (rc == 0)
+            rc = matrix_open_rows_window(ctx, tmp, N, nc, pcs->query_stride, log_rpq, d_indices, num_queries, d_out, W, c0);
+    }
+    dev_free(ctx, tmp);
+    return rc;
 }
 
 static void pcs_release(swirl_ctx* ctx, swirl_pcs* pcs) {
@@ -261,6 +309,12 @@ int swirl_commit_host(swirl_ctx* ctx, const swirl_pcs_params* params, const swir
     }
     *out = pcs;
     return 0;
+}
+
+int swirl_pcs_open_rows(swirl_ctx* ctx, const swirl_pcs* pcs, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out) {
+    SWIRL_REQUIRE(ctx && pcs && (num_queries == 0 || (d_indices && d_out)), "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    return pcs_open_rows(ctx, pcs, pcs->params.k_whir, d_indices, num_queries, d_out);
 }
 
 int swirl_pcs_free(swirl_ctx* ctx, swirl_pcs* pcs) {

@@ -36,6 +36,10 @@ struct swirl_ctx {
     void* round_scratch = nullptr;  // swirl::RoundScratch (ext.cuh), created on first use
     uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
     int ntt_max_log_radix = 11;               // largest single-pass radix (log2)
+    // GpuProverConfig::cache_rs_code_matrix (reference cuda-backend/src/device.rs:102-121): keep the RS codeword of a
+    // commitment for the WHIR openings (true: 2x the trace in HBM) or stream it through a column-group scratch at commit
+    // time and recompute the opened rows' columns in the openings (false: the large-trace mode, BASELINE configs[3])
+    bool cache_codeword = true;
     size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)
     // optional per-kernel-family CUDA-event timing (bench.py's roofline numbers)
     bool timing = false;
@@ -49,6 +53,7 @@ struct swirl_ctx {
     std::multimap<size_t, void*> arena_free;        // size -> idle block
     std::unordered_map<void*, size_t> arena_live;   // block handed out -> size
     size_t arena_bytes = 0;                         // idle + live
+    size_t arena_live_bytes = 0, arena_live_peak = 0;  // handed out now / high-water mark (swirl_ctx_mem_stats)
     // host-side synchronisation statistics (swirl_ctx_sync_stats): how much of a proof is spent waiting on the stream
     uint64_t sync_count = 0;
     double sync_ms = 0;

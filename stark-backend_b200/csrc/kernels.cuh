@@ -21,6 +21,14 @@ int matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, si
                      size_t query_stride, int log_rpq, const uint32_t* d_indices, size_t num_queries,
                      uint32_t* d_out);
 
+int matrix_open_rows_window(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, size_t query_stride,
+                            int log_rpq, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out, size_t out_width,
+                            size_t col0);
+// Opened rows of a commitment's codeword: from the cached codeword, or (cache_rs_code_matrix = false) by re-encoding the
+// stacked matrix one column group at a time (commit.cu).
+int pcs_open_rows(swirl_ctx* ctx, const struct ::swirl_pcs* pcs, int log_rpq, const uint32_t* d_indices, size_t num_queries,
+                  uint32_t* d_out);
+
 // ---- sponge.cu ---------------------------------------------------------------------------
 void round_scratch_free(swirl_ctx* ctx);
 

@@ -223,17 +223,18 @@ __global__ void query_proofs_kernel(const uint32_t* __restrict__ layers, size_t 
     store_digest(out + g * 8, d);
 }
 
-// out[q][t][c] = matrix[c*height + t*S + idx_q]   (zero past `height`)
+// out[q][t][col0 + c] = matrix[c*height + t*S + idx_q]   (zero past `height`), c < width; rows of `out_width` words
 __global__ void open_rows_kernel(const uint32_t* __restrict__ matrix, size_t height, uint32_t width, size_t S,
                                  int log_rpq, const uint32_t* __restrict__ indices, size_t num_queries,
-                                 uint32_t* __restrict__ out) {
+                                 uint32_t* __restrict__ out, uint32_t out_width, uint32_t col0) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t per_q = (size_t)width << log_rpq;
     if (g >= num_queries * per_q) return;
     const size_t q = g / per_q, rem = g % per_q;
     const size_t t = rem / width, c = rem % width;
+    // indices are query indices < S (S a power of two): masking is the identity for valid input and keeps a bad one in bounds
     const size_t row = t * S + ((size_t)indices[q] & (S - 1));
-    out[g] = row < height ? __ldg(matrix + c * height + row) : 0u;
+    out[((q << log_rpq) + t) * out_width + col0 + c] = row < height ? __ldg(matrix + c * height + row) : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -349,10 +350,18 @@ int merkle_query_proofs(swirl_ctx* ctx, const uint32_t* d_layers, size_t query_s
 
 int matrix_open_rows(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, size_t query_stride,
                      int log_rpq, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out) {
+    return matrix_open_rows_window(ctx, d_matrix, height, width, query_stride, log_rpq, d_indices, num_queries, d_out, width, 0);
+}
+
+// The same for `width` columns that are columns [col0, col0 + width) of a matrix whose opened rows have `out_width` words
+// (the codeword recomputed one column group at a time).
+int matrix_open_rows_window(swirl_ctx* ctx, const uint32_t* d_matrix, size_t height, size_t width, size_t query_stride,
+                            int log_rpq, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out, size_t out_width,
+                            size_t col0) {
     const size_t total = num_queries * (width << log_rpq);
     if (total == 0) return 0;
     open_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-        d_matrix, height, (uint32_t)width, query_stride, log_rpq, d_indices, num_queries, d_out);
+        d_matrix, height, (uint32_t)width, query_stride, log_rpq, d_indices, num_queries, d_out, (uint32_t)out_width, (uint32_t)col0);
     SWIRL_LAUNCH_CHECK(ctx);
     return 0;
 }

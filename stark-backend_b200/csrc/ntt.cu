@@ -279,11 +279,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_strided_pass_kernel(PassAr
     uint32_t* dst = a.dst + col * a.dst_col_stride + base;
 
     if (a.chunk_l >= 0) {
-        // TW == 16: a thread owns one row = 16 consecutive evaluations = whole chunks
-        for (int r = threadIdx.x; r < R; r += NTT_THREADS) {
+        // TW >= 16: a thread owns 16 consecutive evaluations of a row = whole chunks
+        const int log_parts = log_tw - 4;
+        for (int idx = threadIdx.x; idx < (R << log_parts); idx += NTT_THREADS) {
+            const int r = idx >> log_parts, part = idx & ((1 << log_parts) - 1);
             uint32_t x[16];
             if ((uint32_t)r < a.n_valid) {
-                const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)r << a.log_s));
+                const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)r << a.log_s) + (part << 4));
                 const uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
                 x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
                 x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_strided_pass_kernel(PassAr
                 for (int i = 0; i < 16; i++) x[i] = 0;
             }
 #pragma unroll
-            for (int i = 0; i < 16; i++) sm[r * pitch + i] = x[i];
+            for (int i = 0; i < 16; i++) sm[r * pitch + (part << 4) + i] = x[i];
         }
     } else {
         for (int idx = threadIdx.x; idx < (R << log_tw); idx += NTT_THREADS) {
@@ -485,7 +487,9 @@ static int make_plan(const swirl_ctx* ctx, int log_n, int min_r1, NttPlan* plan)
 
 static int tile_log_tw(int log_r, int log_limit) {
     int log_tw = ilog2(NTT_TILE_ELEMS) - log_r;
-    if (log_tw > 4) log_tw = 4;
+    // small radices (the passes of a three-pass plan, 2^24 and up) take wider tiles: the same 16 K elements per CTA as a
+    // radix-2^10 pass, 128-256 B segments per row
+    if (log_tw > 6) log_tw = 6;
     if (log_tw > log_limit) log_tw = log_limit;
     if (log_tw < 0) log_tw = 0;
     return log_tw;
@@ -499,6 +503,10 @@ static int ensure_smem_attr() {
     SWIRL_CUDA(cudaFuncSetAttribute(ntt_strided_pass_kernel<LR, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
     SWIRL_CUDA(cudaFuncSetAttribute(ntt_final_pass_kernel<LR, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         SWIRL_NTT_ATTR(0, 0)
+        SWIRL_NTT_ATTR(6, 6)
+        SWIRL_NTT_ATTR(7, 6)
+        SWIRL_NTT_ATTR(8, 6)
+        SWIRL_NTT_ATTR(9, 5)
         SWIRL_NTT_ATTR(7, 4)
         SWIRL_NTT_ATTR(8, 4)
         SWIRL_NTT_ATTR(9, 4)
@@ -558,6 +566,7 @@ static int run_ntt(swirl_ctx* ctx, const NttPlan& plan, const uint32_t* src, siz
     if (a.log_r == LR && a.log_tw == LT)                                                        \
         ntt_strided_pass_kernel<LR, LT><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(a); \
     else
+            SWIRL_NTT_CASE(6, 6) SWIRL_NTT_CASE(7, 6) SWIRL_NTT_CASE(8, 6) SWIRL_NTT_CASE(9, 5)
             SWIRL_NTT_CASE(7, 4) SWIRL_NTT_CASE(8, 4) SWIRL_NTT_CASE(9, 4) SWIRL_NTT_CASE(10, 4) SWIRL_NTT_CASE(11, 3)
                 ntt_strided_pass_kernel<0, 0><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(a);
 #undef SWIRL_NTT_CASE
@@ -596,6 +605,7 @@ static int run_ntt(swirl_ctx* ctx, const NttPlan& plan, const uint32_t* src, siz
     if (a.log_r == LR && a.log_tw == LT)                                                      \
         ntt_final_pass_kernel<LR, LT><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(a); \
     else
+        SWIRL_NTT_CASE(6, 6) SWIRL_NTT_CASE(7, 6) SWIRL_NTT_CASE(8, 6) SWIRL_NTT_CASE(9, 5)
         SWIRL_NTT_CASE(7, 4) SWIRL_NTT_CASE(8, 4) SWIRL_NTT_CASE(9, 4) SWIRL_NTT_CASE(10, 4) SWIRL_NTT_CASE(11, 3)
             ntt_final_pass_kernel<0, 0><<<(unsigned)grid, NTT_THREADS, smem, ctx->stream>>>(a);
 #undef SWIRL_NTT_CASE

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "swirl_ctx_sync_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
     "swirl_ctx_timing_bytes": (_i, [_vp, _i, C.POINTER(_u64)]),
     "swirl_ctx_set_ntt_plan": (_i, [_vp, _i, _sz]),
+    "swirl_ctx_set_cache_rs_code_matrix": (_i, [_vp, _i]),
+    "swirl_ctx_mem_stats": (_i, [_vp, _i, C.POINTER(_u64)]),
     "swirl_last_error": (C.c_char_p, []),
     "swirl_ctx_timing_enable": (_i, [_vp, _i]),
     "swirl_ctx_timing_read": (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_u64)]),
@@ -99,6 +101,7 @@ PROTOTYPES = {
     "swirl_commit": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_commit_host": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_pcs_free": (_i, [_vp, _vp]),
+    "swirl_pcs_open_rows": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "swirl_pcs_stacked_height": (_u64, [_vp]),
     "swirl_pcs_stacked_width": (_u64, [_vp]),
     "swirl_pcs_codeword_height": (_u64, [_vp]),

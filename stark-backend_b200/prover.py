@@ -77,9 +77,28 @@ class Proof:
 
 
 class Coordinator:
-    def __init__(self, device, params, transcript=None):
+    def __init__(self, device, params, transcript=None, plan_memory=False):
+        """plan_memory: before committing, model the proof's device memory (memory.py, after the reference's
+        memory_metering.rs) and switch the device to cache_rs_code_matrix = false when keeping the codeword would not
+        fit the free HBM (the reference's default for its GPU prover, cuda-backend/src/device.rs:113-121)."""
         self.device, self.params = device, params
         self.transcript = transcript if transcript is not None else Transcript()
+        self.plan_memory = plan_memory
+        self.memory_estimate = None
+
+    def _plan(self, airs):
+        from . import memory as M
+
+        dev, P = self.device, self.params
+        counts = M.ProvingMemoryCounts.from_airs(airs, P.l_skip)
+        H = 1 << (P.l_skip + P.n_stack)
+        alias = len(airs) == 1 and airs[0].common_main.height() == H
+        cfg = M.ProvingMemoryConfig(P.l_skip, P.l_skip + P.n_stack, P.log_blowup, P.whir.k, True, alias)
+        st = dev.mem_stats()
+        free = st["device_free"] + (st["held"] - st["live"])  # idle arena blocks are reusable
+        cache, est = M.choose_cache_rs_code_matrix(cfg, counts, free)
+        dev.set_cache_rs_code_matrix(cache)
+        self.memory_estimate = {"cache_rs_code_matrix": cache, "free_bytes": free, **est.__dict__}
 
     def prove_host(self, vk_pre_hash, per_air_pk, air, host_trace, height, width):
         """Single-AIR proof with the common main trace in HOST memory: the H2D transport runs inside
@@ -112,6 +131,8 @@ class Coordinator:
 
         ts.observe(vk_pre_hash)
         per_trace = sorted(per_trace, key=lambda t: (-t[1].common_main.height(), t[0]))
+        if self.plan_memory and precommitted is None:
+            self._plan([t[1] for t in per_trace])
         if precommitted is None:
             root, common = dev.commit(P.pcs(), [t[1].common_main for t in per_trace])
         else:

@@ -48,7 +48,18 @@ def bench_commit(dev, rk, log_h, width, l_skip=4, lb=1, k=4, reps=5):
     trace = torch.randint(0, P, (H * width,), dtype=torch.int32, device="cuda")
     cw = torch.empty((H << lb) * width, dtype=torch.int32, device="cuda")
     cur = torch.cuda.current_stream()
-    ref_lde = time_ms(lambda: rk.rs_code_matrix(trace, H, width, l_skip, lb, out=cw), cur, reps)
+    # the reference's mle_interpolate_fused_2d_kernel indexes the buffer with 32 bits (`uint32_t base_idx = col * padded_height
+    # + physical_idx`, cuda/src/mle_interpolate.cu:89): a codeword of 2^32 elements or more (C4: 2^34) wraps around and the
+    # root comes out wrong, so the reference is run on column groups below 2^32 elements
+    cwh = H << lb
+    grp = width if cwh * width < (1 << 32) else max(1, ((1 << 32) - 1) // cwh // 2)
+
+    def ref_rs():
+        for c0 in range(0, width, grp):
+            nc = min(grp, width - c0)
+            rk.rs_code_matrix(trace[c0 * H:(c0 + nc) * H], H, nc, l_skip, lb, out=cw[c0 * cwh:(c0 + nc) * cwh])
+
+    ref_lde = time_ms(ref_rs, cur, reps)
     ref_tree = time_ms(lambda: rk.merkle_tree(cw, H << lb, width, 1 << k), cur, reps)
     ref_root = rk.d2h(rk.merkle_tree(cw, H << lb, width, 1 << k)[-1]).tolist()
     m = sb.DeviceMatrix(trace, H, width)
@@ -66,7 +77,7 @@ def bench_commit(dev, rk, log_h, width, l_skip=4, lb=1, k=4, reps=5):
          swirl_ms=dict(rs_encode=our_lde, merkle_tree=our_tree, total=our_lde + our_tree),
          speedup=dict(lde=ref_lde / our_lde, merkle=ref_tree / our_tree, total=(ref_lde + ref_tree) / (our_lde + our_tree)),
          reference_gcells_s=cells / (ref_lde + ref_tree) / 1e6, swirl_gcells_s=cells / (our_lde + our_tree) / 1e6,
-         roots_equal=bool(ref_root == our_root))
+         reference_column_groups=-(-width // grp), roots_equal=bool(ref_root == our_root))
     del trace, cw
 
 

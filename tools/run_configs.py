@@ -29,7 +29,7 @@ def whir_cfg(log_blowup, log_h, k, lfp, qpow, fpow, mpow, sec, list_from=None, m
         rate += k - 1
     return dict(k=k, num_queries=nq, mu_pow_bits=mpow, query_phase_pow_bits=qpow, folding_pow_bits=fpow)
 
-def prove_and_verify(name, airs, traces, l_skip, n_stack, log_blowup, D, logup_pow, whir, reps=3):
+def prove_and_verify(name, airs, traces, l_skip, n_stack, log_blowup, D, logup_pow, whir, reps=3, cache=None, plan_memory=False):
     """airs: A.Air with shape-only common_main; traces: CUDA int32 tensors."""
     params = sb.SystemParams(l_skip, n_stack, log_blowup, sb.WhirConfig(**whir), logup_pow, D)
     vk = np.arange(8, dtype=np.uint32)
@@ -39,10 +39,14 @@ def prove_and_verify(name, airs, traces, l_skip, n_stack, log_blowup, D, logup_p
                  for i, (a, t) in enumerate(zip(airs, traces))]
     cells = sum(a.common_main[1] * a.common_main[2] for a in airs)
     best = None
+    if cache is not None:
+        dev.set_cache_rs_code_matrix(cache)
+    dev.trim()
+    dev.mem_stats(reset_peak=True)
     for _ in range(reps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        coord = sb.Coordinator(dev, params)
+        coord = sb.Coordinator(dev, params, plan_memory=plan_memory)
         proof = coord.prove(vk, pk, per_trace)
         dev.synchronize()
         dt = time.perf_counter() - t0
@@ -55,7 +59,10 @@ def prove_and_verify(name, airs, traces, l_skip, n_stack, log_blowup, D, logup_p
                                     proof.stacking_proof, proof.whir_proof)
     tv = time.perf_counter() - t0
     proof.common_main_pcs.free()
-    emit(config=name, prove_ms=best * 1e3, trace_cells=cells, cells_per_s=cells / best, proof_bytes=int(proof.words().size * 4),
+    mem = dev.mem_stats()
+    dev.set_cache_rs_code_matrix(True)
+    emit(config=name, arena_peak_gib=mem["peak"] / 2**30, cache_rs_code_matrix=cache, memory_plan=coord.memory_estimate,
+         prove_ms=best * 1e3, trace_cells=cells, cells_per_s=cells / best, proof_bytes=int(proof.words().size * 4),
          phase_ms=coord.phase_ms, oracle_verifier_accepts=bool(ok is True), failed_stage=None if ok is True else where, verify_s=tv, whir=whir,
          params=dict(l_skip=l_skip, n_stack=n_stack, log_blowup=log_blowup, max_constraint_degree=D, logup_pow_bits=logup_pow))
 
@@ -74,6 +81,30 @@ if "c2" in which:
     t = torch.randint(0, 2, ((1 << 20) * 256,), dtype=torch.int32, device="cuda", generator=g) * R1
     prove_and_verify("C2 BenchmarkAir 2^20 x 256 (app params, stacked height 2^20)", [air], [t], 4, 16, 1, 3, 18,
                      whir_cfg(1, 20, 4, 10, 20, 5, 15, 100))
+    del t
+if "c2h24" in which:
+    # uniform_runner's own defaults for configs[1]: --log-stacked-height 24 (H = 2^24, W = 16 stacked columns; the 256 trace
+    # columns of 2^20 rows are stacked 16 to a column) and the all-zero trace (benchmarks/synthetic/src/bin/uniform_runner.rs:72,250-267)
+    air = shape_only(A.benchmark(3, 256, 256, 32, np.random.default_rng(0)), 1 << 20, 256)
+    t = torch.zeros((1 << 20) * 256, dtype=torch.int32, device="cuda")
+    prove_and_verify("C2 BenchmarkAir 2^20 x 256, all-zero trace, stacked height 2^24 (uniform_runner defaults)", [air], [t], 4, 20, 1, 3, 18,
+                     whir_cfg(1, 24, 4, 10, 20, 5, 15, 100))
+    prove_and_verify("C2 BenchmarkAir 2^20 x 256, all-zero trace, stacked height 2^20", [air], [t], 4, 16, 1, 3, 18,
+                     whir_cfg(1, 20, 4, 10, 20, 5, 15, 100))
+    del t
+if "c4p" in which:
+    # BASELINE configs[3] as a FULL proof: 2^24 x 512 (32 GiB trace, 64 GiB codeword), 512 boolean constraints, 3 send/receive
+    # pairs = 6 x 2^24 LogUp leaves, the most that fits the 2^27-leaf GKR layout here (the uniform_runner default of 0.25 interactions per column would need 64 GiB of LogUp leaves and as much again
+    # for the fraction tree at this height -- more than the device next to the trace; reported as out of memory, not shrunk silently)
+    h, w = 1 << 24, 512
+    air = shape_only(A.benchmark(3, w, w, 3, np.random.default_rng(0)), h, w)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    t = torch.randint(0, 2, (h * w,), dtype=torch.int32, device="cuda", generator=g) * R1
+    for cache in (False, True):
+        prove_and_verify(f"C4 BenchmarkAir 2^24 x 512 full proof (app params, stacked height 2^24), cache_rs_code_matrix={cache}", [air], [t],
+                         4, 20, 1, 3, 18, whir_cfg(1, 24, 4, 10, 20, 5, 15, 100), reps=2, cache=cache)
+    prove_and_verify("C4 full proof, planner decides (Coordinator plan_memory)", [air], [t], 4, 20, 1, 3, 18,
+                     whir_cfg(1, 24, 4, 10, 20, 5, 15, 100), reps=1, plan_memory=True)
     del t
 if "c3" in which:
     airs, traces = [], []
