@@ -16,6 +16,18 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] #[derive(Clone, Copy)] pub struct SwirlWhirConfig { pub k: i32, pub num_rounds: i32, pub num_queries: [i32; 32],
     pub mu_pow_bits: i32, pub query_phase_pow_bits: i32, pub folding_pow_bits: i32 }
 /// SymbolicExpressionNode (air_builders/symbolic/dag.rs:17-45) in the boundary encoding
+/// SWIRL_NODE_* of include/swirl_b200.h
+pub const SWIRL_NODE_VAR_PREP: u32 = 0;
+pub const SWIRL_NODE_VAR_MAIN: u32 = 1;
+pub const SWIRL_NODE_VAR_PUBLIC: u32 = 2;
+pub const SWIRL_NODE_IS_FIRST: u32 = 3;
+pub const SWIRL_NODE_IS_LAST: u32 = 4;
+pub const SWIRL_NODE_IS_TRANSITION: u32 = 5;
+pub const SWIRL_NODE_CONST: u32 = 6;
+pub const SWIRL_NODE_ADD: u32 = 7;
+pub const SWIRL_NODE_SUB: u32 = 8;
+pub const SWIRL_NODE_NEG: u32 = 9;
+pub const SWIRL_NODE_MUL: u32 = 10;
 #[repr(C)] #[derive(Clone, Copy)] pub struct SwirlDagNode { pub op: u32, pub a: u32, pub b: u32, pub c: u32 }
 #[repr(C)] #[derive(Clone, Copy)] pub struct SwirlInteraction { pub count_node: u32, pub bus_index: u32, pub msg_offset: u32, pub msg_len: u32 }
 #[repr(C)] pub struct SwirlAirCtx { pub nodes: *const SwirlDagNode, pub n_nodes: u64, pub constraint_idx: *const u32, pub n_constraints: u64,

@@ -95,6 +95,12 @@ class _Cursor:
             raise ValueError(f"flat proof section has {len(self.w) - self.pos} trailing words")
 
 
+def _claims_flat_to_wire(words):
+    """Per layer: EF elements (0, 1, 2, 3) -> (0, 2, 1, 3)."""
+    a = np.asarray(words).reshape(-1, 4, 4)
+    return a[:, [0, 2, 1, 3], :].reshape(-1)
+
+
 def encode_gkr_and_batch_constraints(w, shape, bc_words):
     """GkrProof then BatchConstraintProof (proof.rs:259-304) from the flat section of
     swirl_prove_batch_constraints."""
@@ -103,7 +109,9 @@ def encode_gkr_and_batch_constraints(w, shape, bc_words):
     w.raw(c.take(1))                       # logup_pow_witness
     w.raw(c.take(4))                       # q0_claim
     w.u32(L)                               # Vec<GkrLayerClaims>
-    w.raw(c.take(16 * L))
+    # the flat section holds a layer's claims in transcript order p(xi,0), q(xi,0), p(xi,1), q(xi,1)
+    # (fractional_sumcheck_gkr.rs:185-193); GkrLayerClaims::encode writes p_xi_0, p_xi_1, q_xi_0, q_xi_1 (proof.rs:211-218)
+    w.raw(_claims_flat_to_wire(c.take(16 * L)))
     w.raw(c.take(12 * (L * (L - 1) // 2)))  # sumcheck_polys: no prefixes (proof.rs:264-270)
     w.u32(n)                               # numerator_term_per_air (slice)
     w.raw(c.take(4 * n))
@@ -262,7 +270,7 @@ def decode_proof(data):
     # GkrProof
     bc = [r.field(1), r.field(4)]
     L = r.u32()
-    bc.append(r.field(16 * L))
+    bc.append(_claims_flat_to_wire(r.field(16 * L)))  # the permutation (p0, q0, p1, q1) <-> (p0, p1, q0, q1) is an involution
     bc.append(r.field(12 * (L * (L - 1) // 2)))
     # BatchConstraintProof
     n = r.u32()

@@ -254,12 +254,12 @@ struct WorkItem {
 };
 
 __global__ void __launch_bounds__(SR_BLOCK)
-sr_mle_round_kernel(const MleView* __restrict__ views, const WorkItem* __restrict__ items, uint32_t* partials,
-                    unsigned int* ticket, uint32_t* result) {
+sr_mle_round_kernel(const MleView* __restrict__ views, const WorkItem* __restrict__ items, size_t y_per_block,
+                    uint32_t* partials, unsigned int* ticket, uint32_t* result) {
     const WorkItem it = items[blockIdx.x];
     const MleView v = views[it.view];
     const size_t ny = size_t(1) << v.log_ny;
-    const size_t y0 = (size_t)it.chunk * SR_Y_PER_BLOCK, y1 = min(y0 + (size_t)SR_Y_PER_BLOCK, ny);
+    const size_t y0 = (size_t)it.chunk * y_per_block, y1 = min(y0 + y_per_block, ny);
     Ext e1 = bb::ext_zero(), e2 = bb::ext_zero(), k1 = bb::ext_zero(), k2 = bb::ext_zero();
     for (size_t y = y0 + threadIdx.x; y < y1; y += SR_BLOCK) {
         const Ext q0 = ldg_ext(v.q + 8 * y), q1 = ldg_ext(v.q + 8 * y + 4);
@@ -557,13 +557,19 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
     SWIRL_CUDA(dev_alloc(ctx, &d_ex, views.size()));
     to_free.push_back(d_views);
     to_free.push_back(d_ex);
-    size_t max_items = 0;
-    for (const View& v : views) {
-        const int n_lift = std::max(v.log_height - l_skip, 0);
-        const size_t ny = n_lift >= 1 ? size_t(1) << (n_lift - 1) : 1;
-        max_items += (ny + SR_Y_PER_BLOCK - 1) / SR_Y_PER_BLOCK;
+    // hypercube points per block: SR_Y_PER_BLOCK, doubled until the work items of the first (largest) round fit the
+    // reduction scratch (BASELINE configs[3]: 512 views of 2^19 points each)
+    size_t y_per_block = SR_Y_PER_BLOCK, max_items = 0;
+    for (;; y_per_block *= 2) {
+        max_items = 0;
+        for (const View& v : views) {
+            const int n_lift = std::max(v.log_height - l_skip, 0);
+            const size_t ny = n_lift >= 1 ? size_t(1) << (n_lift - 1) : 1;
+            max_items += (ny + y_per_block - 1) / y_per_block;
+        }
+        if (max_items <= (size_t)rs->max_blocks) break;
+        SWIRL_REQUIRE(y_per_block < (size_t(1) << 30), "too many views for the reduction scratch");
     }
-    SWIRL_REQUIRE(max_items <= (size_t)rs->max_blocks, "too many work items for the reduction scratch");
     SWIRL_CUDA(dev_alloc(ctx, &d_items, max_items + 1));
     to_free.push_back(d_items);
     int qcur = 0;
@@ -596,7 +602,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
                 hex.push_back(mv);
             } else {
                 const size_t ny = size_t(1) << hd;
-                for (size_t c = 0; c < (ny + SR_Y_PER_BLOCK - 1) / SR_Y_PER_BLOCK; c++)
+                for (size_t c = 0; c < (ny + y_per_block - 1) / y_per_block; c++)
                     items.push_back(WorkItem{(uint32_t)hviews.size(), (uint32_t)c});
                 hviews.push_back(mv);
             }
@@ -606,8 +612,8 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
         if (!items.empty()) {
             SWIRL_CUDA(cudaMemcpyAsync(d_views, hviews.data(), hviews.size() * sizeof(MleView), cudaMemcpyHostToDevice, ctx->stream));
             SWIRL_CUDA(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
-            sr_mle_round_kernel<<<(unsigned)items.size(), SR_BLOCK, 0, ctx->stream>>>(d_views, d_items, rs->d_partials, rs->d_ticket,
-                                                                                   rs->d_result);
+            sr_mle_round_kernel<<<(unsigned)items.size(), SR_BLOCK, 0, ctx->stream>>>(d_views, d_items, y_per_block, rs->d_partials,
+                                                                                   rs->d_ticket, rs->d_result);
             SWIRL_LAUNCH_CHECK(ctx);
         }
         if (!hex.empty()) {

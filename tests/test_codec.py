@@ -30,7 +30,8 @@ def nested_proof(shape, root, bc, st, wh):
     L, n, D = shape.gkr_layers, len(shape.airs), shape.max_constraint_degree
     it = iter(canon(bc))
     gkr = dict(logup_pow_witness=next(it), q0_claim=ef(it),
-               claims_per_layer=[[ef(it) for _ in range(4)] for _ in range(L)],
+               # flat order = transcript order (fractional_sumcheck_gkr.rs:185-193)
+               claims_per_layer=[dict(zip(("p_xi_0", "q_xi_0", "p_xi_1", "q_xi_1"), [ef(it) for _ in range(4)])) for _ in range(L)],
                sumcheck_polys=[[[ef(it) for _ in range(3)] for _ in range(j)] for j in range(1, L)])
     bcp = dict(numerator_term_per_air=[ef(it) for _ in range(n)], denominator_term_per_air=[ef(it) for _ in range(n)],
                univariate_round_coeffs=[ef(it) for _ in range((D + 1) * ((1 << shape.l_skip) - 1) + 1)],
@@ -84,8 +85,8 @@ def serialise_nested(p):
     g = p["gkr_proof"]
     f(g["logup_pow_witness"]); ef(g["q0_claim"])
     u32(len(g["claims_per_layer"]))
-    for c in g["claims_per_layer"]:
-        [ef(e) for e in c]
+    for c in g["claims_per_layer"]:  # GkrLayerClaims::encode, proof.rs:211-218
+        ef(c["p_xi_0"]); ef(c["p_xi_1"]); ef(c["q_xi_0"]); ef(c["q_xi_1"])
     for rnd in g["sumcheck_polys"]:
         for arr in rnd:
             [ef(e) for e in arr]
