@@ -336,6 +336,16 @@ int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* ts, int l_sk
                                   int logup_pow_bits, const swirl_air_ctx* airs, size_t n_airs, uint32_t* h_proof,
                                   size_t proof_words, uint32_t* h_r);
 
+/* Per-AIR run-time compiled constraint kernels: for traces of 2^17 rows and more the round-0 program of
+ * an AIR is emitted as straight-line CUDA C++, compiled with NVRTC for sm_100a at first use and cached in the context
+ * (SWIRL_JIT=0, or a missing libnvrtc, selects the interpreter kernels instead; both are GPU paths and produce the same
+ * words).  This returns that source for inspection (which = 0: constraint roots, 1: interaction roots); host only, the
+ * matrices of `air` need only their shapes.  Returns the source length; copies at most cap - 1 characters into out.
+ * Reference counterpart: the rule compiler + interpreter, cuda-backend/src/logup_zerocheck/rules/mod.rs:27-130. */
+/* 0 = interpreter only, 1 = compile the programs of tall traces (default), 2 = compile every program (tests). */
+int swirl_ctx_set_jit(swirl_ctx* ctx, int mode);
+size_t swirl_jit_round0_source(const swirl_air_ctx* air, int which, char* out, size_t cap);
+
 /* ---- phase level: OpeningProver::prove_openings (hal.rs:118-138; cpu_backend.rs:139-220) =
  *      swirl_stacked_reduction, u_cube = (u_0^(2^i))_{i<l_skip} ++ u[1..], swirl_whir_open.
  *      Buffers as in those two calls. -------------------------------------------------------------- */

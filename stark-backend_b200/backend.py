@@ -446,6 +446,10 @@ class B200Device:
         """reference: GpuDevice::set_cache_rs_code_matrix (cuda-backend/src/device.rs:108-110)."""
         check(self.lib.swirl_ctx_set_cache_rs_code_matrix(self.ctx, 1 if on else 0))
 
+    def set_jit(self, mode):
+        """Run-time compiled per-AIR constraint kernels: 0 = interpreter only, 1 = tall traces (default), 2 = always."""
+        check(self.lib.swirl_ctx_set_jit(self.ctx, int(mode)))
+
     def mem_stats(self, reset_peak=False):
         """{live, peak, held, device_free} bytes of the context's scratch arena (traces handed in by the caller not counted)."""
         out = (C.c_uint64 * 4)()

@@ -189,6 +189,12 @@ int swirl_ctx_set_cache_rs_code_matrix(swirl_ctx* ctx, int on) {
     return 0;
 }
 
+int swirl_ctx_set_jit(swirl_ctx* ctx, int mode) {
+    SWIRL_REQUIRE(ctx && mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    ctx->jit_mode = mode;
+    return 0;
+}
+
 int swirl_ctx_mem_stats(swirl_ctx* ctx, int reset_peak, uint64_t out[4]) {
     SWIRL_REQUIRE(ctx && out, "null argument");
     size_t free_b = 0, total_b = 0;

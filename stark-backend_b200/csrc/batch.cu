@@ -19,15 +19,18 @@
 // at a single row (the tail terms of the front-loaded batching).  The constant zerofier /
 // normalisation factors and all polynomial bookkeeping stay on the host with the transcript.
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <type_traits>
 #include <vector>
 
 #include "ext.cuh"
 #include "hostpoly.hpp"
+#include "jit.hpp"
 #include "kernels.cuh"
 #include "pcs.cuh"
 #include "transcript.hpp"
@@ -635,6 +638,145 @@ static void launch_mle(int D, const MleArgs* descs, const uint16_t* block_air, i
         else { CALL(256); }               \
     } while (0)
 
+// ---- host: program -> straight-line CUDA C++ (jit.hpp) -----------------------------------------------------
+// One statement per instruction; value slot s lane l is the register variable s<s>_<l>.  The statements are the
+// macros of csrc/jit_prelude.cuh (LD = column load at the thread's coset point, PF = prefetch, ACC = weighted
+// accumulation into one of the three EF accumulators).
+// Programs of real AIRs repeat: the same few instructions applied to consecutive columns / weights (BenchmarkAir:
+// assert_bool on every column; range checks, byte decompositions and bus messages in production chips).  A run of r >= 4
+// repetitions of a period of p instructions whose column / weight operands advance by constant steps is emitted as ONE loop
+// (`it` = repetition), which keeps the generated kernel small enough to compile in seconds and to live in the instruction
+// cache; everything else is emitted statement by statement.
+struct JitRun {
+    size_t start, period, reps;
+    std::vector<std::array<int64_t, 3>> delta;  // per instruction of the period: step of (a, b, c)
+};
+static bool jit_delta_ok(const Instr& x, const Instr& y, std::array<int64_t, 3>* d) {
+    if (x.op_dst != y.op_dst) return false;
+    (*d)[0] = (int64_t)y.a - (int64_t)x.a;
+    (*d)[1] = (int64_t)y.b - (int64_t)x.b;
+    (*d)[2] = (int64_t)y.c - (int64_t)x.c;
+    switch (x.op_dst & 0xff) {
+        case I_VAR:
+        case I_PREF: return (*d)[0] == 0;                   // part fixed; column (b) and global column (c) may step
+        case I_ACC: return (*d)[0] == 0 && (*d)[2] == 0;     // accumulator and slot fixed; weight (b) may step
+        case I_MULACC: return (*d)[0] == 0 && (*d)[1] == 0;  // operand slots fixed; weight (c) may step
+        default: return (*d)[0] == 0 && (*d)[1] == 0 && (*d)[2] == 0;
+    }
+}
+static std::vector<JitRun> jit_find_runs(const std::vector<Instr>& code) {
+    std::vector<JitRun> runs;
+    const size_t n = code.size();
+    size_t i = 0;
+    while (i < n) {
+        JitRun best{i, 0, 0, {}};
+        for (size_t p = 1; p <= 48 && i + 2 * p <= n; p++) {
+            std::vector<std::array<int64_t, 3>> d(p);
+            bool ok = true;
+            for (size_t j = 0; j < p && ok; j++) ok = jit_delta_ok(code[i + j], code[i + p + j], &d[j]);
+            if (!ok) continue;
+            size_t r = 2;
+            for (;; r++) {
+                if (i + (r + 1) * p > n) break;
+                bool same = true;
+                for (size_t j = 0; j < p && same; j++) {
+                    std::array<int64_t, 3> e;
+                    same = jit_delta_ok(code[i + (r - 1) * p + j], code[i + r * p + j], &e) && e == d[j];
+                }
+                if (!same) break;
+            }
+            if (r >= 4 && r * p > best.reps * best.period) best = JitRun{i, p, r, d};
+        }
+        if (best.reps) {
+            runs.push_back(best);
+            i += best.period * best.reps;
+        } else {
+            i++;
+        }
+    }
+    return runs;
+}
+
+// One statement per instruction; value slot s lane l is the register variable s<s>_<l>.  The statements are the
+// macros of csrc/jit_prelude.cuh (LD = column load at the thread's coset point, PF = prefetch, ACC = weighted
+// accumulation into one of the three EF accumulators).  Returns "" when the program is too irregular to be worth
+// compiling (more than JIT_MAX_STATEMENTS statements after loop detection): NVRTC's time grows much faster than
+// linearly with the size of a basic block (measured: 768 statements with inlined loads = 13 minutes).
+constexpr size_t JIT_MAX_STATEMENTS = 320;
+static std::string generate_round0_source(const std::vector<Instr>& code, int n_slots, const char* name) {
+    const std::vector<JitRun> runs = jit_find_runs(code);
+    size_t statements = code.size(), loads = 0;
+    for (const JitRun& r : runs) statements -= r.period * (r.reps - 1);
+    if (statements > JIT_MAX_STATEMENTS) return std::string();
+    {
+        size_t ri = 0;
+        for (size_t i = 0; i < code.size();) {
+            const bool in_run = ri < runs.size() && runs[ri].start == i;
+            const size_t len = in_run ? runs[ri].period : 1;
+            for (size_t j = 0; j < len; j++) loads += (code[i + j].op_dst & 0xff) == I_VAR;
+            i += in_run ? runs[ri].period * runs[ri].reps : 1;
+            ri += in_run;
+        }
+    }
+    std::string s;
+    s.reserve(statements * 128 + 16384);
+    // the column load (4 x 16-byte loads + a 16-term dot product) is inlined while the kernel stays small
+    s += loads <= 24 ? "#define SW_LOAD_ATTR __device__ __forceinline__\n" : "#define SW_LOAD_ATTR __device__ __noinline__\n";
+    s += "#define SW_MIN_BLOCKS 2\n";
+    s += jit_prelude();
+    s += "\nSW_R0_SIGNATURE(";
+    s += name;
+    s += ") {\nSW_R0_PROLOGUE\n";
+    for (int i = 0; i < n_slots; i++) s += "uint32_t s" + std::to_string(i) + "_0 = 0, s" + std::to_string(i) + "_1 = 0;\n";
+    auto v = [](uint32_t slot, int lane) { return "s" + std::to_string(slot) + "_" + std::to_string(lane); };
+    // operand `val` (+ it * step inside a loop)
+    auto opnd = [](uint32_t val, int64_t step) {
+        if (step == 0) return std::to_string(val);
+        return "(" + std::to_string(val) + " + it * (" + std::to_string(step) + "))";
+    };
+    auto emit = [&](const Instr& in, const std::array<int64_t, 3>& d) {
+        const uint32_t op = in.op_dst & 0xff, dst = in.op_dst >> 8;
+        auto bin = [&](const char* fn) {
+            for (int l = 0; l < 2; l++) s += v(dst, l) + " = " + fn + "(" + v(in.a, l) + ", " + v(in.b, l) + "); ";
+            s += "\n";
+        };
+        switch (op) {
+            case I_VAR: s += "LD(" + std::to_string(in.a) + ", " + opnd(in.b, d[1]) + ", " + v(dst, 0) + ", " + v(dst, 1) + ")\n"; break;
+            case I_PREF: s += "PF(" + std::to_string(in.a) + ", " + opnd(in.b, d[1]) + ")\n"; break;
+            case I_CONST: s += v(dst, 0) + " = " + v(dst, 1) + " = " + std::to_string(in.a) + "u;\n"; break;
+            case I_ADD: bin("f_add"); break;
+            case I_SUB: bin("f_sub"); break;
+            case I_MUL: bin("f_mul"); break;
+            case I_NEG:
+                for (int l = 0; l < 2; l++) s += v(dst, l) + " = f_neg(" + v(in.a, l) + "); ";
+                s += "\n";
+                break;
+            case I_MULACC:
+                s += "ACC(" + std::to_string(dst) + ", " + opnd(in.c, d[2]) + ", f_mul(" + v(in.a, 0) + ", " + v(in.b, 0) + "), f_mul(" +
+                     v(in.a, 1) + ", " + v(in.b, 1) + "))\n";
+                break;
+            default:  // I_ACC: a = accumulator, b = weight index, c = slot
+                s += "ACC(" + std::to_string(in.a) + ", " + opnd(in.b, d[1]) + ", " + v(in.c, 0) + ", " + v(in.c, 1) + ")\n";
+        }
+    };
+    const std::array<int64_t, 3> zero{0, 0, 0};
+    size_t ri = 0;
+    for (size_t i = 0; i < code.size();) {
+        if (ri < runs.size() && runs[ri].start == i) {
+            const JitRun& r = runs[ri++];
+            s += "#pragma unroll 1\nfor (int it = 0; it < " + std::to_string(r.reps) + "; it++) {\n";
+            for (size_t j = 0; j < r.period; j++) emit(code[i + j], r.delta[j]);
+            s += "}\n";
+            i += r.period * r.reps;
+        } else {
+            emit(code[i], zero);
+            i++;
+        }
+    }
+    s += "SW_R0_EPILOGUE\n}\n";
+    return s;
+}
+
 }  // namespace swirl
 
 using namespace swirl;
@@ -649,11 +791,19 @@ struct TraceState {
     // the constraint program split by roots into independent sub-programs (their accumulators add up): one thread
     // walks ~16 roots instead of the whole DAG, which multiplies the loads in flight per SM and divides the
     // serial latency of the short tail rounds
+    struct Jit {  // the program as a run-time compiled kernel (jit.hpp); built at first use by a tall trace
+        std::vector<Instr> h_code;
+        int n_slots = 0;
+        int state = 0;  // 0 = not tried, 1 = ready, -1 = unavailable (interpreter is used)
+        JitKernel kernel;
+        ~Jit() { jit_release(&kernel); }
+    };
     struct Chunk {
         Instr* d_code = nullptr;
         uint32_t n_instr = 0;
         int n_slots = 0;
         bool zerocheck_only = false;  // only constraint roots: round 0 needs it on d - 1 cosets, not d
+        std::shared_ptr<Jit> jit;     // whole programs only
     };
     std::vector<Chunk> chunks;
     Chunk whole[2];  // the constraint roots / the interaction roots as one program each (round 0 of tall traces)
@@ -898,12 +1048,17 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             // sub-programs never mix constraint and interaction roots: the zerocheck part of round 0 is needed on one
             // coset fewer than the LogUp part (cpu.rs:338-361 vs :405-409)
             const size_t nc = a.n_constraints;
-            auto compile_range = [&](size_t r0, size_t r1, bool zc, TraceState::Chunk* c) -> int {
+            auto compile_range = [&](size_t r0, size_t r1, bool zc, TraceState::Chunk* c, bool keep_host = false) -> int {
                 Program pr;
                 SWIRL_TRY(compile_program(a, s.L, std::vector<Root>(roots.begin() + r0, roots.begin() + r1), &pr, BC_PREFETCH_VARS));
                 c->n_instr = (uint32_t)pr.code.size();
                 c->n_slots = pr.n_slots;
                 c->zerocheck_only = zc;
+                if (keep_host) {
+                    c->jit = std::make_shared<TraceState::Jit>();
+                    c->jit->h_code = pr.code;
+                    c->jit->n_slots = pr.n_slots;
+                }
                 c->d_code = nullptr;  // an empty program is never dereferenced
                 if (!pr.code.empty()) {  // owned by the cache, released with the context
                     SWIRL_CUDA(cudaMalloc((void**)&c->d_code, pr.code.size() * sizeof(Instr)));
@@ -913,8 +1068,8 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 }
                 return 0;
             };
-            SWIRL_TRY(compile_range(0, nc, true, &s.whole[0]));
-            SWIRL_TRY(compile_range(nc, roots.size(), false, &s.whole[1]));
+            SWIRL_TRY(compile_range(0, nc, true, &s.whole[0], true));
+            SWIRL_TRY(compile_range(nc, roots.size(), false, &s.whole[1], true));
             const size_t k_max = std::max<size_t>(2, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
             const size_t K = std::max<size_t>(1, std::min(k_max, (roots.size() + BC_CHUNK_ROOTS - 1) / BC_CHUNK_ROOTS));
             // K chunks shared between the two classes in proportion to their roots, at least one per non-empty class
@@ -1126,8 +1281,10 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     std::vector<R0Block> r0_desc_air;
     {
         std::vector<R0Args> descs;
+        std::vector<void*> desc_kernel;  // run-time compiled kernel of the desc's program, or nullptr = interpreter
         std::vector<uint16_t> block_air;
         size_t part_words = 0;
+        const bool use_jit = l_skip == 4 && ctx->jit_mode != 0 && jit_available();
         for (size_t t = 0; t < n_airs; t++) {
             TraceState& s = T[t];
             const int cd = (int)airs[t].constraint_degree;
@@ -1135,12 +1292,32 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             // enough hypercube points to fill the machine: one walk of the whole constraint / interaction program per
             // point (the per-point set-up is paid once); short traces take the sub-programs for their parallelism
             std::vector<TraceState::Chunk> whole{s.whole[0], s.whole[1]};
-            const bool split = (size_t(1) << s.n_lift) < BC_R0_SPLIT_BELOW;
+            const bool split = (size_t(1) << s.n_lift) < BC_R0_SPLIT_BELOW && !(use_jit && ctx->jit_mode == 2);
             for (const auto& ch : split ? s.chunks : whole) {
                 // zerocheck: the quotient lives on d - 1 cosets; LogUp numerators / denominators need d
                 const int cosets = ch.zerocheck_only ? cd - 1 : cd;
                 if (cosets == 0 || ch.n_instr == 0) continue;
-                max_slots_r0 = std::max(max_slots_r0, ch.n_slots);
+                void* jk = nullptr;
+                if (use_jit && !split && ch.jit && ch.jit->state >= 0) {
+                    TraceState::Jit& j = *ch.jit;
+                    if (j.state == 0) {  // first tall trace with this program: compile it (seconds, once per context)
+                        const auto tj = std::chrono::steady_clock::now();
+                        const std::string src = generate_round0_source(j.h_code, j.n_slots, "swirl_r0_jit");
+                        const int jrc = src.empty() ? -1 : jit_compile(ctx, src, "swirl_r0_jit", &j.kernel);
+                        j.state = jrc == 0 ? 1 : -1;
+                        if (src.empty()) {
+                            if (trace_on) fprintf(stderr, "[swirl jit] program of %zu instructions is too irregular to compile quickly: interpreter\n", j.h_code.size());
+                        } else if (trace_on || jrc != 0)
+                            fprintf(stderr, "[swirl jit] round-0 kernel for a program of %zu instructions: %s (%.0f ms)%s%s\n", j.h_code.size(),
+                                    jrc == 0 ? "compiled" : "FAILED, using the interpreter",
+                                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tj).count(),
+                                    jrc == 0 ? "" : ": ", jrc == 0 ? "" : swirl_last_error());
+                        j.h_code.clear();
+                        j.h_code.shrink_to_fit();
+                    }
+                    if (j.state == 1) jk = j.kernel.kernel;
+                }
+                if (!jk) max_slots_r0 = std::max(max_slots_r0, ch.n_slots);
                 R0Args ra{};
                 ra.code = ch.d_code;
                 ra.n_instr = ch.n_instr;
@@ -1165,6 +1342,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 SWIRL_REQUIRE(descs.size() < 65535, "too many AIRs");
                 block_air.insert(block_air.end(), ra.n_blocks, (uint16_t)descs.size());
                 descs.push_back(ra);
+                desc_kernel.push_back(jk);
             }
         }
         SWIRL_CUDA(dev_alloc(ctx, &d_r0, r0_words + 4));
@@ -1177,11 +1355,25 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 d.partials = part + (size_t)(uintptr_t)d.partials;
                 d.result = d_r0 + (size_t)(uintptr_t)d.result;
             }
-            R0Args* d_descs = nullptr;
-            uint16_t* d_ba = nullptr;
-            SWIRL_TRY(upload(descs.data(), descs.size() * sizeof(R0Args), (void**)&d_descs));
-            SWIRL_TRY(upload(block_air.data(), block_air.size() * sizeof(uint16_t), (void**)&d_ba));
-            const unsigned blocks = (unsigned)block_air.size();
+            // one launch per kernel: the interpreter takes every desc without a compiled program, each compiled program
+            // takes its own descs (AIRs that share a DAG share the kernel)
+            std::map<void*, std::vector<size_t>> groups;
+            for (size_t i = 0; i < descs.size(); i++) groups[desc_kernel[i]].push_back(i);
+            bool first_group = true;
+            for (const auto& grp : groups) {
+                std::vector<R0Args> gd;
+                std::vector<uint16_t> gba;
+                for (size_t i : grp.second) {
+                    R0Args d = descs[i];
+                    d.first_block = (uint32_t)gba.size();
+                    gba.insert(gba.end(), d.n_blocks, (uint16_t)gd.size());
+                    gd.push_back(d);
+                }
+                R0Args* d_descs = nullptr;
+                uint16_t* d_ba = nullptr;
+                SWIRL_TRY(upload(gd.data(), gd.size() * sizeof(R0Args), (void**)&d_descs));
+                SWIRL_TRY(upload(gba.data(), gba.size() * sizeof(uint16_t), (void**)&d_ba));
+                const unsigned blocks = (unsigned)gba.size();
 #define BC_R0(NS)                                                                                                     \
     do {                                                                                                              \
         const size_t smem = (size_t)BC_BLOCK * (13 + ((NS) <= 64 ? (NS) * 2 : 0)) * 4;                               \
@@ -1193,15 +1385,23 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             batch_round0_kernel<NS, 0><<<blocks, BC_BLOCK, smem, ctx->stream>>>(d_descs, d_ba);                      \
         }                                                                                                             \
     } while (0)
-            {
-                SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0, r0_alg_bytes);
-                BC_DISPATCH_NS(max_slots_r0, BC_R0);
-            }
+                {
+                    // the family's algorithmic bytes are accounted once (with its first launch)
+                    SwirlTimed timed(ctx, SWIRL_T_BC_ROUND0, first_group ? r0_alg_bytes : 0);
+                    if (grp.first) {
+                        void* kargs[2] = {(void*)&d_descs, (void*)&d_ba};
+                        SWIRL_CUDA(cudaLaunchKernel((const void*)grp.first, dim3(blocks), dim3(BC_BLOCK), kargs, 0, ctx->stream));
+                    } else {
+                        BC_DISPATCH_NS(max_slots_r0, BC_R0);
+                    }
+                }
 #undef BC_R0
-            SWIRL_LAUNCH_CHECK(ctx);
-            const int max_nv = D * (int)N * 12;
-            bc_reduce_multi_kernel<<<dim3((max_nv + 255) / 256, (unsigned)descs.size()), 256, 0, ctx->stream>>>(d_descs);
-            SWIRL_LAUNCH_CHECK(ctx);
+                SWIRL_LAUNCH_CHECK(ctx);
+                first_group = false;
+                const int max_nv = D * (int)N * 12;
+                bc_reduce_multi_kernel<<<dim3((max_nv + 255) / 256, (unsigned)gd.size()), 256, 0, ctx->stream>>>(d_descs);
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
         }
     }
     std::vector<uint32_t> h_r0c(r0_words + 4), h_r0(r0_off[n_airs] + 4, 0);
@@ -1606,4 +1806,33 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     for (size_t i = 0; i < r.size(); i++) memcpy(h_r + 4 * i, r[i].c, 16);
     mark("openings");
     return 0;
+}
+
+// Debugging aid / documentation: the CUDA C++ the library would compile at run time for one AIR's round-0 program
+// (which = 0: the constraint roots, 1: the interaction roots).  Host only, no device needed; matrices of `air` need
+// only their shapes.  Returns the source length (excluding the terminator); copies at most cap - 1 characters.
+extern "C" size_t swirl_jit_round0_source(const swirl_air_ctx* air, int which, char* out, size_t cap) {
+    if (!air) return 0;
+    AirLayout L;
+    if (air_layout(*air, &L) != 0) return 0;
+    std::vector<Root> roots;
+    if (which == 0) {
+        for (uint64_t k = 0; k < air->n_constraints; k++) roots.push_back(Root{air->constraint_idx[k], 0, (uint32_t)k});
+    } else {
+        uint32_t w = (uint32_t)air->n_constraints;
+        for (uint64_t i = 0; i < air->n_interactions; i++) {
+            const swirl_interaction& it = air->interactions[i];
+            roots.push_back(Root{it.count_node, 1, w++});
+            for (uint32_t j = 0; j < it.msg_len; j++) roots.push_back(Root{air->msg_nodes[it.msg_offset + j], 2, w++});
+        }
+    }
+    Program pr;
+    if (compile_program(*air, L, roots, &pr, BC_PREFETCH_VARS) != 0) return 0;
+    const std::string src = generate_round0_source(pr.code, pr.n_slots, "swirl_r0_jit");
+    if (out && cap) {
+        const size_t n = std::min(src.size(), cap - 1);
+        memcpy(out, src.data(), n);
+        out[n] = 0;
+    }
+    return src.size();
 }

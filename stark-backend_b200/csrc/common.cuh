@@ -40,6 +40,7 @@ struct swirl_ctx {
     // commitment for the WHIR openings (true: 2x the trace in HBM) or stream it through a column-group scratch at commit
     // time and recompute the opened rows' columns in the openings (false: the large-trace mode, BASELINE configs[3])
     bool cache_codeword = true;
+    int jit_mode = 1;  // run-time compiled constraint kernels: 0 = never, 1 = traces of 2^17 rows and more, 2 = always (tests)
     size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)
     // optional per-kernel-family CUDA-event timing (bench.py's roofline numbers)
     bool timing = false;

@@ -117,6 +117,8 @@ PROTOTYPES = {
     "swirl_batch_constraints_proof_words": (_sz, [_i, _i, _vp, _sz]),
     "swirl_prove_batch_constraints": (_i, [_vp, C.POINTER(TranscriptC), _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "swirl_prove_openings": (_i, [_vp, C.POINTER(TranscriptC), C.POINTER(WhirConfigC), _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "swirl_ctx_set_jit": (_i, [_vp, _i]),
+    "swirl_jit_round0_source": (_sz, [_vp, _i, C.c_char_p, _sz]),
     "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
 }
 
