@@ -277,6 +277,9 @@ def run_swirl(args):
     params = sb.SystemParams(L_SKIP, LOG_ROWS - L_SKIP, LOG_BLOWUP, whir, LOGUP_POW, MAX_CONSTRAINT_DEGREE)
     air = benchmark_air_dag(COLS)
     rng = np.random.default_rng(42 + rank)
+    # one process per GPU: run on, and pin host memory from, the CPUs local to this rank's GPU (N > 1: 8 x 1 GiB per step
+    # would otherwise cross the sockets; round 1 measured e2e efficiency 0.84 at N = 8 without it)
+    numa_cpus = multi.bind_to_gpu_numa_node(local) if world > 1 else None
     host = torch.from_numpy((rng.integers(0, 2, size=CELLS, dtype=np.uint64) * R1).astype(np.uint32).view(np.int32)).pin_memory()
     trace_dev = host.to(dev.torch_device)
     stream = dev.torch_stream()
@@ -425,6 +428,16 @@ def run_swirl(args):
         except Exception as e:  # the replica measurement above stands on its own
             sharded = {"error": f"{type(e).__name__}: {e}"}
 
+    # ... and ONE PROOF over the N GPUs (multi.ShardedProver: commitment sharded over the ranks, sumcheck phases on rank 0,
+    # WHIR openings gathered from the ranks that hold the queried rows), for BASELINE configs[1] and configs[2]; the proof
+    # bytes must equal the single-GPU proof's
+    sharded_proofs = None
+    if world > 1:
+        try:
+            sharded_proofs = [sharded_proof_benchmark(dev, world, rank, which) for which in ("c2", "c3")]
+        except Exception as e:
+            sharded_proofs = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         pk_, pk_kind = peaks()
         # per family: avg ms per launch, launches per step, ms per step, algorithmic bytes per step (accounted by the
@@ -447,6 +460,8 @@ def run_swirl(args):
                        "parallelism": f"{world} independent proofs (one per GPU), commitments all-gathered" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": 4 * CELLS, "d2h_bytes_per_step": int(proof.words().size * 4),
+                    "host_affinity": (f"rank bound to the {len(numa_cpus)} CPUs local to its GPU before pinning the trace" if numa_cpus
+                                      else "default"),
                     "path": "TraceTransporter (pinned double buffering: the next step's trace is copied while this step proves; the "
                             "first step waits for its own copy) + Coordinator.prove; K + 1 copies of 1 GiB in the K timed steps",
                     "single_proof_ms": ms_lat / args.steps,
@@ -460,6 +475,7 @@ def run_swirl(args):
             "lde": {"ms_per_step": lde_ms, "algorithmic_gb_s": lde_bytes / (lde_ms / 1e3) / 1e9 if lde_ms else 0.0,
                     "frac_of_hbm": (lde_bytes / (lde_ms / 1e3) / 1e9) / pk_["hbm_gbs"] if lde_ms else 0.0},
             "sharded_commit": sharded,
+            "sharded_proof": sharded_proofs,
             "proof_bytes": len(proof.encode()),  # Proof::encode_to_vec() wire format (stark-backend_b200/codec.py)
             "host_step_ms": stalls.pop("step_ms"),
             "remeasured_after_host_stall": stalls or None,
@@ -476,6 +492,67 @@ def run_swirl(args):
     dev.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_proof_benchmark(dev, world, rank, which):
+    """One proof over all ranks (strong scaling of a single proof): returns, on rank 0, ms per proof (wall clock around the
+    collective call, best of 3 after a warm-up; the ranks enter together) beside the same proof on one GPU."""
+    import torch
+    import torch.distributed as dist
+
+    import airs as A
+    import stark_backend_b200 as sb
+    from stark_backend_b200 import multi
+
+    if which == "c2":
+        name, log_stack = "BASELINE configs[1]: BenchmarkAir 2^20 x 256", 20
+        specs = [(benchmark_air_dag(COLS), 1 << LOG_ROWS, COLS)]
+    else:
+        name, log_stack = "BASELINE configs[2]: 32 BenchmarkAirs 2^17 x 20 with LogUp (2^22 rows), stacked height 2^24", 24
+        specs = [(A.benchmark(3, 20, 20, 3, np.random.default_rng(i)), 1 << 17, 20) for i in range(32)]
+    params = sb.SystemParams(L_SKIP, log_stack - L_SKIP, LOG_BLOWUP, sb.WhirConfig(K_WHIR, whir_queries(log_stack), MU_POW, QUERY_POW, FOLD_POW),
+                             LOGUP_POW, MAX_CONSTRAINT_DEGREE)
+    g = torch.Generator(device=dev.torch_device).manual_seed(4242)  # the same traces on every rank
+    per_trace = []
+    for i, (air, h, w) in enumerate(specs):
+        t = torch.randint(0, 2, (h * w,), dtype=torch.int32, device=dev.torch_device, generator=g) * R1
+        per_trace.append((i, sb.AirProvingContext(air.nodes, air.constraint_idx, air.interactions, 2, False, sb.DeviceMatrix(t, h, w)), []))
+    pk = [sb.AirProvingKey(True, None) for _ in specs]
+    vk = np.arange(8, dtype=np.uint32)
+    sp = multi.ShardedProver(dev, params, world, rank)
+    best, words = None, None
+    for rep in range(4):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        proof = sp.prove(vk, pk, per_trace)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if rep:
+            best = dt if best is None else min(best, dt)
+        if proof is not None:
+            words = proof.words()
+            proof.common_main_pcs.free()
+            proof.release()
+    out = None
+    if rank == 0:
+        single = []
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref = sb.Coordinator(dev, params).prove(vk, pk, per_trace)
+            dev.synchronize()
+            single.append(time.perf_counter() - t0)
+            same = bool(np.array_equal(ref.words(), words))
+            ref.common_main_pcs.free()
+            ref.release()
+        cells = sum(h * w for _, h, w in specs)
+        out = {"workload": name, "n_gpus": world, "ms_per_proof": best * 1e3, "single_gpu_ms_per_proof": min(single[1:]) * 1e3,
+               "speedup": min(single[1:]) / best, "cells_per_s": cells / best, "proof_identical_to_single_gpu": same,
+               "sharded_commit_ms": sp.timings.get("sharded_commit_ms"), "rank0_rest_ms": sp.timings.get("rank0_rest_ms"),
+               "scaling": "strong", "sharded": "commitment (RS encode by columns, leaf hashing by query ranges); sumcheck phases on rank 0"}
+    dist.barrier()
+    return out
 
 
 def roofline_block(kernel_name, dom, fam, hbm_ach, pk_, pk_kind, leaf_perms, clocks):

@@ -16,6 +16,8 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] #[derive(Clone, Copy)] pub struct SwirlWhirConfig { pub k: i32, pub num_rounds: i32, pub num_queries: [i32; 32],
     pub mu_pow_bits: i32, pub query_phase_pow_bits: i32, pub folding_pow_bits: i32 }
 /// SymbolicExpressionNode (air_builders/symbolic/dag.rs:17-45) in the boundary encoding
+/// swirl_open_fn of include/swirl_b200.h
+pub type SwirlOpenFn = unsafe extern "C" fn(user: *mut c_void, h_indices: *const u32, num_queries: usize, d_rows: *mut u32, d_paths: *mut u32) -> c_int;
 /// SWIRL_NODE_* of include/swirl_b200.h
 pub const SWIRL_NODE_VAR_PREP: u32 = 0;
 pub const SWIRL_NODE_VAR_MAIN: u32 = 1;
@@ -74,6 +76,8 @@ extern "C" {
     pub fn swirl_gkr_fractional_sumcheck_padded(ctx: *mut SwirlCtx, ts: *mut SwirlTranscript, d_leaves: *const u32, n_stored: u64, pad_q: *const u32, log_n: c_int, assert_zero: c_int, h_frac_sum: *mut u32, h_claims: *mut u32, h_polys: *mut u32, h_xi: *mut u32) -> c_int;
     pub fn swirl_commit(ctx: *mut SwirlCtx, params: *const SwirlPcsParams, d_traces: *const SwirlMatrix, n_traces: usize, h_root: *mut u32, out: *mut *mut SwirlPcs) -> c_int;
     pub fn swirl_commit_host(ctx: *mut SwirlCtx, params: *const SwirlPcsParams, h_traces: *const SwirlMatrix, n_traces: usize, h_root: *mut u32, out: *mut *mut SwirlPcs) -> c_int;
+    pub fn swirl_stack(ctx: *mut SwirlCtx, params: *const SwirlPcsParams, d_traces: *const SwirlMatrix, n_traces: usize, out: *mut *mut SwirlPcs) -> c_int;
+    pub fn swirl_pcs_attach_external(pcs: *mut SwirlPcs, root: *const u32, f: SwirlOpenFn, user: *mut c_void) -> c_int;
     pub fn swirl_pcs_free(ctx: *mut SwirlCtx, pcs: *mut SwirlPcs) -> c_int;
     pub fn swirl_pcs_open_rows(ctx: *mut SwirlCtx, pcs: *const SwirlPcs, d_indices: *const u32, num_queries: usize, d_out: *mut u32) -> c_int;
     pub fn swirl_pcs_stacked_height(pcs: *const SwirlPcs) -> u64;

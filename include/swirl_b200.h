@@ -206,6 +206,19 @@ int swirl_pcs_free(swirl_ctx* ctx, swirl_pcs* pcs);
  * cuda-backend/src/merkle_tree.rs:199-).  Works with and without a cached codeword (swirl_ctx_set_cache_rs_code_matrix). */
 int swirl_pcs_open_rows(swirl_ctx* ctx, const swirl_pcs* pcs, const uint32_t* d_indices, size_t num_queries, uint32_t* d_out);
 
+/* ---- commitments whose codeword and Merkle tree live outside this context (a commitment sharded over several GPUs) ----
+ * swirl_stack: layout + stacked matrix only (the first half of TraceCommitter::commit; reference
+ * stack_traces_into_expanded, cuda-backend/src/stacked_pcs.rs:143-220): every rank of a sharded commitment takes its
+ * column slice from swirl_pcs_stacked_matrix.  swirl_pcs_attach_external: gives the handle the commitment's root and a
+ * callback that the WHIR opening calls instead of reading a local codeword / digest layers:
+ *   fn(user, h_indices[nq] (host), nq, d_rows (device, [nq][2^k_whir][stacked width] words),
+ *      d_paths (device, [nq][log2(query_stride)][8] words))  ->  0, with both buffers complete on return.
+ * The stream of the context is idle when the callback runs.  No reference counterpart (the reference commits on one GPU);
+ * the opened rows and paths must be the ones MerkleTreeGpu would return (merkle_tree.rs:199-, stacked_pcs.rs:388-405). */
+typedef int (*swirl_open_fn)(void* user, const uint32_t* h_indices, size_t num_queries, uint32_t* d_rows, uint32_t* d_paths);
+int swirl_stack(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* d_traces, size_t n_traces, swirl_pcs** out);
+int swirl_pcs_attach_external(swirl_pcs* pcs, const uint32_t root[8], swirl_open_fn fn, void* user);
+
 /* PCS data accessors */
 uint64_t swirl_pcs_stacked_height(const swirl_pcs* pcs);
 uint64_t swirl_pcs_stacked_width(const swirl_pcs* pcs);

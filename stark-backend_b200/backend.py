@@ -190,7 +190,35 @@ class StackedPcsData:
         return self._dev._d2h(self._dev.lib.swirl_pcs_stacked_matrix(self._h), self.height * self.width)
 
     def commit(self):
-        return self.tree.root()
+        return self.external_root if getattr(self, "external_root", None) is not None else self.tree.root()
+
+    def stacked_ptr(self):
+        """Device pointer of the stacked matrix (height x width, column-major)."""
+        return self._dev.lib.swirl_pcs_stacked_matrix(self._h)
+
+    def attach_external(self, root, open_fn):
+        """The commitment's codeword and tree live elsewhere (other ranks of a sharded commitment): `open_fn(indices) ->
+        (rows (nq, 2^k, width) uint32, paths (nq, depth, 8) uint32)` supplies what the WHIR opening asks for."""
+        dev, width, rpq = self._dev, self.width, 1 << self.params.k_whir
+        depth = int(dev.lib.swirl_pcs_query_stride(self._h)).bit_length() - 1
+
+        def thunk(_user, h_idx, nq, d_rows, d_paths):
+            try:
+                rows, paths = open_fn([int(h_idx[i]) for i in range(nq)])
+                rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(nq, rpq, width)
+                paths = np.ascontiguousarray(paths, dtype=np.uint32).reshape(nq, depth, 8)
+                check(dev.lib.swirl_memcpy_h2d(dev.ctx, d_rows, rows.ctypes.data, rows.nbytes))
+                check(dev.lib.swirl_memcpy_h2d(dev.ctx, d_paths, paths.ctypes.data, paths.nbytes))
+                dev.synchronize()
+                return 0
+            except Exception as e:  # noqa: BLE001 -- an exception must not unwind through the C frames
+                self._callback_error = e
+                return 10001
+
+        self._open_cb = _lib.OPEN_FN(thunk)  # kept alive as long as the handle
+        root = np.ascontiguousarray(root, dtype=np.uint32)
+        check(dev.lib.swirl_pcs_attach_external(self._h, root.ctypes.data, self._open_cb, None))
+        self.external_root = root.copy()
 
     def open_rows(self, indices):
         """Opened rows of the commitment's codeword, (num_queries, rows_per_query, width): from the cached codeword or, with
@@ -701,6 +729,19 @@ class B200Device:
         check(self.lib.swirl_whir_open(self.ctx, C.byref(ts.c), C.byref(cc), handles, len(pcs_list), u.ctypes.data,
                                        proof.ctypes.data, n))
         return proof
+
+    def stack(self, params, traces):
+        """Layout + stacked matrix only (first half of commit): the handle has no codeword or tree until
+        `attach_external` (sharded commitments, multi.py)."""
+        n = len(traces)
+        arr = (MatrixC * max(n, 1))()
+        for i, t in enumerate(traces):
+            arr[i] = MatrixC(t.ptr(), t.height(), t.width())
+        h = C.c_void_p()
+        pc = params.c()
+        self._sync_torch()
+        check(self.lib.swirl_stack(self.ctx, C.byref(pc), arr, n, C.byref(h)))
+        return StackedPcsData(self, h, params, list(traces))
 
     # -- TraceCommitter::commit ---------------------------------------------------------------
     def commit(self, params, traces):

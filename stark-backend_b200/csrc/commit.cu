@@ -68,8 +68,8 @@ using namespace swirl;
 // columns per group when the codeword is streamed instead of cached (a multiple of the sponge rate)
 static constexpr uint64_t STREAM_GROUP = 32;
 
-static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* traces, size_t n,
-                       uint32_t h_root[8], swirl_pcs* pcs) {
+// layout + stacked matrix (the part of the commitment that involves no encoding or hashing)
+static int stack_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* traces, size_t n, swirl_pcs* pcs) {
     const int l_skip = params->l_skip, n_stack = params->n_stack;
     SWIRL_REQUIRE(l_skip >= 0 && n_stack >= 0 && l_skip + n_stack <= 27, "l_skip / n_stack");
     SWIRL_REQUIRE(params->log_blowup >= 0 && params->k_whir >= 0, "log_blowup / k_whir");
@@ -124,12 +124,19 @@ static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swi
         }
         if (off < W * H) SWIRL_CUDA(cudaMemsetAsync(q + off, 0, (W * H - off) * 4, ctx->stream));
     }
-
-    // ---- codeword + tree ----
     const uint64_t N = H << params->log_blowup;
     SWIRL_REQUIRE((uint64_t(1) << params->k_whir) <= N, "MerkleTreeRowsPerQueryExceeded");
     pcs->codeword_height = N;
     pcs->query_stride = N >> params->k_whir;
+    return 0;
+}
+
+static int commit_impl(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* traces, size_t n,
+                       uint32_t h_root[8], swirl_pcs* pcs) {
+    SWIRL_TRY(stack_impl(ctx, params, traces, n, pcs));
+    const int l_skip = params->l_skip;
+    const uint64_t H = pcs->layout.height, W = pcs->layout.width, N = pcs->codeword_height;
+    // ---- codeword + tree ----
     SWIRL_CUDA(dev_alloc(ctx, &pcs->layers, (2 * pcs->query_stride - 1) * 8 + 8));
     // streaming needs whole sponge blocks per group and the fused leaf kernel's per-row state hand-off
     const bool stream_codeword = !ctx->cache_codeword && W > STREAM_GROUP && (uint64_t(1) << params->k_whir) <= 256;
@@ -308,6 +315,29 @@ int swirl_commit_host(swirl_ctx* ctx, const swirl_pcs_params* params, const swir
         return rc;
     }
     *out = pcs;
+    return 0;
+}
+
+int swirl_stack(swirl_ctx* ctx, const swirl_pcs_params* params, const swirl_matrix* d_traces, size_t n_traces, swirl_pcs** out) {
+    SWIRL_REQUIRE(ctx && params && d_traces && out, "null argument");
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    swirl_pcs* pcs = new swirl_pcs();
+    const int rc = stack_impl(ctx, params, d_traces, n_traces, pcs);
+    if (rc != 0) {
+        pcs_release(ctx, pcs);
+        *out = nullptr;
+        return rc;
+    }
+    *out = pcs;
+    return 0;
+}
+
+int swirl_pcs_attach_external(swirl_pcs* pcs, const uint32_t root[8], swirl_open_fn fn, void* user) {
+    SWIRL_REQUIRE(pcs && root && fn, "null argument");
+    SWIRL_REQUIRE(!pcs->codeword && !pcs->layers, "the commitment already has a local tree");
+    memcpy(pcs->ext_root, root, 32);
+    pcs->open_fn = fn;
+    pcs->open_user = user;
     return 0;
 }
 

@@ -35,5 +35,10 @@ struct swirl_pcs {
     uint32_t* codeword = nullptr;  // device, owned
     uint32_t* layers = nullptr;    // device, owned
     std::vector<uint32_t*> owned_traces;  // device copies made by swirl_commit_host
+    // external tree (swirl_pcs_attach_external): codeword and digest layers live elsewhere (other GPUs of a sharded
+    // commitment); the WHIR opening asks the callback for the opened rows and Merkle paths of its query indices
+    swirl_open_fn open_fn = nullptr;
+    void* open_user = nullptr;
+    uint32_t ext_root[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 

@@ -14,6 +14,7 @@
 // the first window that contains a hit.
 #include "kernels.cuh"
 #include "poseidon2.cuh"
+#include "poseidon2_v2.cuh"
 
 namespace swirl {
 
@@ -26,6 +27,8 @@ __global__ void __launch_bounds__(256)
 grind_kernel(GrindState st, uint32_t mask, uint32_t w0, uint32_t w_end, uint32_t* __restrict__ result) {
     const uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= w_end) return;
+    // blocks are scheduled in ascending order: once a smaller witness is known, the rest of the window is skipped
+    if (__ldcg(result) < w0 + blockIdx.x * blockDim.x) return;
     uint32_t s[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = st.s[i];
@@ -33,7 +36,7 @@ grind_kernel(GrindState st, uint32_t mask, uint32_t w0, uint32_t w_end, uint32_t
 #pragma unroll
     for (int i = 0; i < 8; i++)
         if ((uint32_t)i == st.slot) s[i] = wm;
-    p2::permute(s);
+    p2v2::permute(s);
     if ((bb::from_mont(s[7]) & mask) == 0) atomicMin(result, w);
 }
 

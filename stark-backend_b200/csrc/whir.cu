@@ -432,8 +432,18 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             if (wr == 0) {
                 for (size_t ci = 0; ci < n_commits; ci++) {
                     const size_t row_words = (size_t)nq * (widths[ci] << k), path_words = (size_t)nq * depth * 8;
-                    SWIRL_TRY(pcs_open_rows(ctx, pcs[ci], k, d_idx, nq, d_open));  // cached codeword, or re-encoded by column groups
-                    SWIRL_TRY(merkle_query_proofs(ctx, pcs[ci]->layers, pcs[ci]->query_stride, d_idx, nq, d_open + row_words));
+                    if (pcs[ci]->open_fn) {
+                        // the tree lives elsewhere (sharded commitment): the owner of each query supplies rows and path
+                        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+                        const int orc = pcs[ci]->open_fn(pcs[ci]->open_user, h_idx.data(), (size_t)nq, d_open, d_open + row_words);
+                        if (orc != 0) {
+                            set_error("external opening callback failed");
+                            return orc;
+                        }
+                    } else {
+                        SWIRL_TRY(pcs_open_rows(ctx, pcs[ci], k, d_idx, nq, d_open));  // cached codeword, or re-encoded by column groups
+                        SWIRL_TRY(merkle_query_proofs(ctx, pcs[ci]->layers, pcs[ci]->query_stride, d_idx, nq, d_open + row_words));
+                    }
                     swirl::trace_mark(ctx, "whir", "  open kernels", &t_prev);
                     SWIRL_CUDA(swirl::d2h_staged(ctx, sec_rows0[ci], d_open, row_words * 4));
                     SWIRL_CUDA(swirl::d2h_staged(ctx, sec_proofs0[ci], d_open + row_words, path_words * 4));

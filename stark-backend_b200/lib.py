@@ -59,6 +59,8 @@ class AirCtxC(C.Structure):
 
 
 _vp, _sz, _i, _u32, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64
+# swirl_open_fn(user, h_indices, num_queries, d_rows, d_paths) -> int
+OPEN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.c_size_t, C.c_void_p, C.c_void_p)
 
 # name -> (restype, argtypes); every prototype of include/swirl_b200.h
 PROTOTYPES = {
@@ -100,6 +102,8 @@ PROTOTYPES = {
     "swirl_gkr_fractional_sumcheck_padded": (_i, [_vp, C.POINTER(TranscriptC), _vp, _u64, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "swirl_commit": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
     "swirl_commit_host": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, _vp, C.POINTER(_vp)]),
+    "swirl_stack": (_i, [_vp, C.POINTER(PcsParamsC), C.POINTER(MatrixC), _sz, C.POINTER(_vp)]),
+    "swirl_pcs_attach_external": (_i, [_vp, _vp, _vp, _vp]),
     "swirl_pcs_free": (_i, [_vp, _vp]),
     "swirl_pcs_open_rows": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "swirl_pcs_stacked_height": (_u64, [_vp]),

@@ -7,6 +7,37 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins the calling process to the CPUs that are local to GPU `local_rank` (NVML: nvmlDeviceGetCpuAffinity), so that
+    pinned host buffers allocated afterwards are first-touched on the GPU's own NUMA node and the prover thread runs next to
+    it.  With one process per GPU this removes the cross-socket hop from every trace transport (8 ranks x 1 GiB per step
+    otherwise share the inter-socket links).  Returns the CPU list, or None when NVML / the affinity call is unavailable
+    (reference: per-device pinned staging, cuda-common/src/pinned.rs)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def assign_proofs(n_proofs, world, rank):
     """Round-robin assignment of independent proofs (segments / AIR groups) to ranks."""
     return [i for i in range(n_proofs) if i % world == rank]
@@ -218,3 +249,137 @@ def sharded_commit_benchmark(dev, log_rows, cols, l_skip, log_blowup, log_rpq, w
             pcs.free()
         out.update(single_gpu_ms=min(single), speedup=min(single) / ms, roots_equal=bool(np.array_equal(root, res["root"])))
     return out
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# One proof over several GPUs: the common-main commitment -- the leaf hashing is the largest phase of
+# every BASELINE config -- is sharded over the ranks (column-sharded RS encode, one row exchange over NVLink, local
+# fused leaf hash + subtree, 32-byte sub-roots all-gathered); rank 0 then runs the sumcheck phases on its own copy of the
+# traces, and when the WHIR opening samples its query indices every rank opens the queries whose rows it holds (each
+# query lives on exactly one rank) and the rows / local Merkle paths are reduced to rank 0, which appends the top
+# log2(world) siblings.  The transcript is rank 0's, the proof is the one a single GPU produces, byte for byte.
+# Communication per proof: the row exchange (4 N (G-1)/G^2 bytes per rank), G sub-roots, the query indices (< 1 KB) and
+# the opened rows (a few MB).  The sumcheck tables are not sharded (DESIGN.md section 7 explains what that would take).
+# -------------------------------------------------------------------------------------------------------------------
+class ShardedProver:
+    def __init__(self, dev, params, world, rank, use_peer_memory=True):
+        self.dev, self.params, self.world, self.rank = dev, params, world, rank
+        self.backend = DeviceCommitBackend(dev)
+        self.use_peer_memory = use_peer_memory and world > 1 and dev is not None
+        self._px = None
+        self.timings = {}
+
+    # ---- the commitment, sharded ---------------------------------------------------------------------------------
+    def _commit(self, stacked):
+        P = self.params
+        H, W = stacked.height, stacked.width
+        c0, c1 = column_slice(W, self.world, self.rank)
+        full = _tensor_view(self.dev, stacked.stacked_ptr(), H * W)
+        mine = full[c0 * H:c1 * H]
+        rows = H << P.log_blowup
+        if self.use_peer_memory:
+            if self._px is None or (self._px.width, self._px.rows) != (W, rows):
+                self._px = PeerExchange(self.dev, W, rows, self.world, self.rank)
+        res = sharded_commit(self.backend, mine, H, W, P.l_skip, P.log_blowup, P.whir.k, self.world, self.rank,
+                             peer_exchange=self._px if self.use_peer_memory else None)
+        # every level of the top log2(world) levels, for the upper part of the Merkle paths
+        levels = [torch.from_numpy(res["sub_roots"].view(np.int32)).to(self.dev.torch_device).view(self.world, 8)]
+        while levels[-1].shape[0] > 1:
+            levels.append(self.backend.compress_level(levels[-1]))
+        res["top_levels"] = [l.cpu().numpy().view(np.uint32).reshape(-1, 8) for l in levels]
+        return res
+
+    # ---- openings: every rank answers for the queries it owns ----------------------------------------------------------
+    def _open_local(self, res, indices, stacked):
+        """rows (nq, 2^k, W) and local paths (nq, local_depth, 8) as int32 device tensors, zero for queries of other ranks."""
+        P, dev = self.params, self.dev
+        k = P.whir.k
+        W = stacked.width
+        S = (stacked.height << P.log_blowup) >> k
+        s_local = S // self.world
+        depth_local = s_local.bit_length() - 1
+        nq = len(indices)
+        rows = torch.zeros(nq * (W << k), dtype=torch.int32, device=dev.torch_device)
+        paths = torch.zeros(nq * max(depth_local, 1) * 8, dtype=torch.int32, device=dev.torch_device)
+        mine = [j for j, i in enumerate(indices) if i // s_local == self.rank]
+        if mine:
+            local = [indices[j] % s_local for j in mine]
+            shard = res["shard"]
+            r = dev.matrix_open_rows(shard.data_ptr(), shard.shape[1], W, s_local, k, local)  # (n, 2^k, W) numpy
+            sel = torch.tensor(mine, device=dev.torch_device)
+            rows.view(nq, -1)[sel] = torch.from_numpy(r.reshape(len(mine), -1).view(np.int32)).to(dev.torch_device)
+            if depth_local:
+                p = dev.merkle_query_proofs(res["layers"].data_ptr(), s_local, local)
+                paths.view(nq, -1)[sel] = torch.from_numpy(p.reshape(len(mine), -1).view(np.int32)).to(dev.torch_device)
+        return rows, paths, depth_local
+
+    def _exchange_openings(self, res, stacked, indices):
+        """Collective: rank 0 passes the indices, the others pass None.  Returns (rows, paths) on rank 0."""
+        dev = self.dev
+        n = torch.tensor([len(indices) if indices is not None else 0], dtype=torch.int64, device=dev.torch_device)
+        if self.world > 1:
+            dist.broadcast(n, 0)
+        idx = torch.tensor(indices if indices is not None else [0] * int(n.item()), dtype=torch.int64, device=dev.torch_device)
+        if self.world > 1:
+            dist.broadcast(idx, 0)
+        indices = [int(x) for x in idx.cpu().tolist()]
+        rows, paths, depth_local = self._open_local(res, indices, stacked)
+        if self.world > 1:  # every query has exactly one owner: a sum over ranks places each row (values < p < 2^31)
+            dist.reduce(rows, 0)
+            dist.reduce(paths, 0)
+        if self.rank != 0:
+            return None
+        nq, W, k = len(indices), stacked.width, self.params.whir.k
+        s_local = ((stacked.height << self.params.log_blowup) >> k) // self.world
+        top = res["top_levels"]
+        full_paths = np.zeros((nq, depth_local + len(top) - 1, 8), dtype=np.uint32)
+        full_paths[:, :depth_local] = paths.cpu().numpy().view(np.uint32).reshape(nq, max(depth_local, 1), 8)[:, :depth_local]
+        for j, i in enumerate(indices):
+            node = i // s_local
+            for lvl in range(len(top) - 1):
+                full_paths[j, depth_local + lvl] = top[lvl][node ^ 1]
+                node >>= 1
+        return rows.cpu().numpy().view(np.uint32).reshape(nq, 1 << k, W), full_paths
+
+    # ---- the proof -----------------------------------------------------------------------------------------------------
+    def prove(self, vk_pre_hash, per_air_pk, per_trace):
+        """Every rank passes the same arguments (the traces are resident on every rank; a rank reads only its column slice
+        of the stacked matrix for the commitment, rank 0 reads everything for the sumchecks).  Returns the Proof on rank 0,
+        None elsewhere.  `self.timings`: milliseconds of the sharded commitment (max over ranks) and, on rank 0, the rest."""
+        from .prover import Coordinator
+
+        dev, P = self.dev, self.params
+        per_trace = sorted(per_trace, key=lambda t: (-t[1].common_main.height(), t[0]))
+        stream = dev.torch_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stacked = dev.stack(P.pcs(), [t[1].common_main for t in per_trace])
+        res = self._commit(stacked)
+        e1.record(stream)
+        dev.synchronize()
+        self.timings["sharded_commit_ms"] = max_over_ranks(e0.elapsed_time(e1), dev.torch_device)
+        if self.rank != 0:
+            self._exchange_openings(res, stacked, None)  # serve rank 0's single request
+            stacked.free()
+            return None
+        stacked.attach_external(res["root"], lambda idx: self._exchange_openings(res, stacked, idx))
+        import time
+
+        t0 = time.perf_counter()
+        proof = Coordinator(dev, P).prove(vk_pre_hash, per_air_pk, per_trace, precommitted=(res["root"], stacked))
+        dev.synchronize()
+        self.timings["rank0_rest_ms"] = 1e3 * (time.perf_counter() - t0)
+        err = getattr(stacked, "_callback_error", None)
+        if err is not None:
+            raise err
+        return proof
+
+
+def _tensor_view(dev, ptr, n_words):
+    """int32 torch view of `n_words` device words at `ptr` (no copy; the owner must outlive the view)."""
+    class _Iface:
+        pass
+
+    o = _Iface()
+    o.__cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(o, device=dev.torch_device)

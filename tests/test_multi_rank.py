@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -123,3 +124,34 @@ def test_sharded_commit_world_size_2_gloo(tmp_path, oracle):
 
 def test_sharded_commit_ragged_columns_world_size_2_gloo(tmp_path, oracle):
     _run_sharded(tmp_path, oracle, 5)
+
+
+@pytest.mark.gpu
+def test_sharded_prover_single_rank_matches_plain_proof(oracle):
+    """multi.ShardedProver with one rank: the commitment goes through the sharded path (stack -> column slice -> shard
+    tree), the WHIR opening through the external-tree callback; the proof must equal Coordinator.prove's word for word
+    (the N > 1 runs of tools/sharded_proof.py check the same on 2-8 GPUs)."""
+    import test_prove as tp
+    import stark_backend_b200 as sb
+    from stark_backend_b200 import multi
+
+    airs = [a for a in tp.fixture_airs(2)[0] if a.preprocessed is None and not a.cached]
+    dev = sb.B200Device(0)
+    try:
+        sp = sb.SystemParams(tp.L_SKIP, tp.N_STACK, tp.LOG_BLOWUP, sb.WhirConfig(**tp.WHIR), tp.LOGUP_POW, tp.D)
+        dm = lambda m: sb.DeviceMatrix(dev.h2d(m[0]), m[1], m[2])
+        pks = [sb.AirProvingKey(True, None) for _ in airs]
+        mk = lambda: [(i, sb.AirProvingContext(a.nodes, a.constraint_idx, a.interactions, a.constraint_degree, a.need_rot,
+                                               dm(a.common_main), a.public_values), []) for i, a in enumerate(airs)]
+        vk = oracle.to_mont(np.arange(100, 108))
+        try:
+            plain = sb.Coordinator(dev, sp).prove(vk, pks, mk())
+        except sb.SwirlError as e:  # the subset of AIRs may not balance its buses: then the sharded path must fail the same way
+            with pytest.raises(sb.SwirlError):
+                multi.ShardedProver(dev, sp, 1, 0).prove(vk, pks, mk())
+            assert e.code == 10005
+            return
+        sharded = multi.ShardedProver(dev, sp, 1, 0).prove(vk, pks, mk())
+        assert np.array_equal(plain.words(), sharded.words())
+    finally:
+        dev.close()
