@@ -50,13 +50,26 @@ __host__ __device__ __forceinline__ uint32_t sqr(uint32_t a) { return mul(a, a);
 
 // Signed Montgomery product a*b*2^-32 (mod p) for ANY int32 inputs: x = a*b, q = lo(x)*p^-1,
 // r = hi(x) - hi(q*p); |r| <= |a||b|/2^32 + p/2, so it is closed on int32 and needs no correction
-// between chained products.  IMAD.WIDE + IMAD + IMAD.HI + IADD: 5 fma-heavy passes, 1 alu op.
+// between chained products.  On the device x - q*p (a multiple of 2^32) is formed inside the third
+// multiply: IMAD.WIDE + IMAD + IMAD.HI with the 64-bit x as addend = 5 fma-heavy passes and NO alu
+// op.  ptxas only emits that form when (i) the first product is an explicit mul.wide.s32 (a C++
+// int64 product of a value that came out of `>> 32` is expanded into unsigned pieces plus sign
+// fix-ups) and (ii) -p is not a visible immediate (knowing q*p == lo(x) it "simplifies" the sum
+// into IMAD.HI + a carry chain of three adds), hence the constant-bank operand.
+#ifdef __CUDACC__
+static __device__ __constant__ int32_t SMUL_NEG_P = -(int32_t)P;
+#endif
 __host__ __device__ __forceinline__ int32_t smul(int32_t a, int32_t b) {
+#ifdef __CUDA_ARCH__
+    int64_t x;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(x) : "r"(a), "r"(b));
+    const int32_t q = (int32_t)((uint32_t)x * PINV);
+    int64_t y;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(y) : "r"(q), "r"(SMUL_NEG_P));
+    return (int32_t)((x + y) >> 32);
+#else
     const int64_t x = (int64_t)a * b;
     const int32_t q = (int32_t)((uint32_t)x * PINV);
-#ifdef __CUDA_ARCH__
-    return (int32_t)(x >> 32) - __mulhi(q, (int32_t)P);
-#else
     return (int32_t)(x >> 32) - (int32_t)(((int64_t)q * (int32_t)P) >> 32);
 #endif
 }

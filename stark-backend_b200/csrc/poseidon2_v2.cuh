@@ -55,6 +55,46 @@ static const int32_t H_EXT_TERM[80] = {P2_EXT_TERM_VALUES Z16};
 using bb::canon;
 using bb::smul;
 
+// ---- pipe placement of the plain additions ----------------------------------------------------------
+// ptxas splits two-input adds between the ALU pipe (IADD3) and the fma-heavy pipe (IMAD.IADD) by
+// instruction COUNT; it does not know that IMAD.WIDE / IMAD.HI occupy the heavy pipe for two passes,
+// so its split leaves the multiplier pipe ~25 % busier than the ALU pipe.  An add with a third
+// operand that is zero at run time (constant bank) can only be an IADD3, which pins it to the ALU.
+// POL is a bit mask of the groups of additions that are pinned (tools/p2_bench.cu sweeps it).
+constexpr int PIN_M4 = 1, PIN_COLSUM = 2, PIN_EXT_OUT = 4, PIN_INT_SUM = 8, PIN_INT_OUT = 16, PIN_EXT_RC = 32;
+#ifndef P2V2_PIN_POLICY
+#define P2V2_PIN_POLICY 0
+#endif
+#ifdef __CUDACC__
+static __device__ __constant__ uint32_t PIN_ZERO = 0;
+#endif
+template <bool PIN>
+__host__ __device__ __forceinline__ uint32_t radd(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    if (PIN) return a + b + PIN_ZERO;
+#endif
+    return a + b;
+}
+template <bool PIN>
+__host__ __device__ __forceinline__ uint32_t rsub(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    if (PIN) return a - b + PIN_ZERO;
+#endif
+    return a - b;
+}
+template <bool PIN>
+__host__ __device__ __forceinline__ uint32_t padd(uint32_t a, uint32_t b) {
+    const uint32_t s = radd<PIN>(a, b), t = s - bb::P;
+    return s < t ? s : t;
+}
+template <bool PIN>
+__host__ __device__ __forceinline__ uint32_t psub(uint32_t a, uint32_t b) {
+    const uint32_t d = rsub<PIN>(a, b), t = d + bb::P;
+    return d < t ? d : t;
+}
+template <bool PIN>
+__host__ __device__ __forceinline__ uint32_t pdbl(uint32_t a) { return padd<PIN>(a, a); }
+
 // s in [-p, p) (state word plus signed round constant) -> s^7 canonical
 __host__ __device__ __forceinline__ uint32_t sbox7(int32_t s) {
     const int32_t x2 = smul(s, s);    // |.| < 0.97 p
@@ -64,28 +104,32 @@ __host__ __device__ __forceinline__ uint32_t sbox7(int32_t s) {
 }
 
 // y = M4 x, M4 = [[2,3,1,1],[1,2,3,1],[1,1,2,3],[3,1,1,2]]; 11 canonical additions
+template <int POL>
 __host__ __device__ __forceinline__ void m4(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
-    const uint32_t t01 = bb::add(x0, x1), t23 = bb::add(x2, x3);
-    const uint32_t t0123 = bb::add(t01, t23);
-    const uint32_t t01123 = bb::add(t0123, x1), t01233 = bb::add(t0123, x3);
-    const uint32_t y3 = bb::add(t01233, bb::dbl(x0));
-    const uint32_t y1 = bb::add(t01123, bb::dbl(x2));
-    x0 = bb::add(t01123, t01);
-    x2 = bb::add(t01233, t23);
+    constexpr bool Q = (POL & PIN_M4) != 0;
+    const uint32_t t01 = padd<Q>(x0, x1), t23 = padd<Q>(x2, x3);
+    const uint32_t t0123 = padd<Q>(t01, t23);
+    const uint32_t t01123 = padd<Q>(t0123, x1), t01233 = padd<Q>(t0123, x3);
+    const uint32_t y3 = padd<Q>(t01233, pdbl<Q>(x0));
+    const uint32_t y1 = padd<Q>(t01123, pdbl<Q>(x2));
+    x0 = padd<Q>(t01123, t01);
+    x2 = padd<Q>(t01233, t23);
     x1 = y1;
     x3 = y3;
 }
 
 // External linear layer fused with the next round's constants: the outputs are
 // state + (rc - p) in [-p, p), ready for the S-box (one IADD3 per word).
+template <int POL>
 __host__ __device__ __forceinline__ void external_linear_rc(uint32_t s[16], const int32_t* rc) {
+    constexpr bool QC = (POL & PIN_COLSUM) != 0, QO = (POL & PIN_EXT_OUT) != 0;
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) m4(s[i], s[i + 1], s[i + 2], s[i + 3]);
+    for (int i = 0; i < 16; i += 4) m4<POL>(s[i], s[i + 1], s[i + 2], s[i + 3]);
     uint32_t t[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) t[j] = bb::add(bb::add(s[j], s[4 + j]), bb::add(s[8 + j], s[12 + j]));
+    for (int j = 0; j < 4; j++) t[j] = padd<QC>(padd<QC>(s[j], s[4 + j]), padd<QC>(s[8 + j], s[12 + j]));
 #pragma unroll
-    for (int i = 0; i < 16; i++) s[i] = bb::add(s[i], t[i & 3]) + (uint32_t)rc[i];  // [0,p) + [-p,0)
+    for (int i = 0; i < 16; i++) s[i] = radd<(POL & PIN_EXT_RC) != 0>(padd<QO>(s[i], t[i & 3]), (uint32_t)rc[i]);  // [0,p) + [-p,0)
 }
 
 // x * 2^-k for canonical x, 1 <= k <= 27:  (x >> k) - 15 * 2^(27-k) * (x mod 2^k), in (-p, 2^30]
@@ -106,35 +150,35 @@ __host__ __device__ __forceinline__ uint32_t mul_neg_2exp_neg(uint32_t x) {
 }
 
 // s <- (J + diag(d)) s, d = (-2, 1, 2, 1/2, 3, 4, -1/2, -3, -4, 2^-8, 1/4, 1/8, 2^-27, -2^-8, -1/16, -2^-27)
+template <int POL>
 __host__ __device__ __forceinline__ void internal_linear(uint32_t s[16]) {
-    using bb::add;
-    using bb::sub;
-    const uint32_t r1 = add(add(add(s[1], s[2]), add(s[3], s[4])), add(add(s[5], s[6]), add(s[7], s[8])));
-    const uint32_t r2 = add(add(add(s[9], s[10]), add(s[11], s[12])), add(add(s[13], s[14]), s[15]));
-    const uint32_t rest = add(r1, r2);
-    const uint32_t sum = add(rest, s[0]);
-    s[0] = sub(rest, s[0]);
-    s[1] = add(sum, s[1]);
-    s[2] = add(add(sum, s[2]), s[2]);
-    s[3] = add(sum, bb::halve(s[3]));
-    s[4] = add(add(sum, s[4]), bb::dbl(s[4]));
+    constexpr bool QS = (POL & PIN_INT_SUM) != 0, Q = (POL & PIN_INT_OUT) != 0;
+    const uint32_t r1 = padd<QS>(padd<QS>(padd<QS>(s[1], s[2]), padd<QS>(s[3], s[4])), padd<QS>(padd<QS>(s[5], s[6]), padd<QS>(s[7], s[8])));
+    const uint32_t r2 = padd<QS>(padd<QS>(padd<QS>(s[9], s[10]), padd<QS>(s[11], s[12])), padd<QS>(padd<QS>(s[13], s[14]), s[15]));
+    const uint32_t rest = padd<QS>(r1, r2);
+    const uint32_t sum = padd<QS>(rest, s[0]);
+    s[0] = psub<Q>(rest, s[0]);
+    s[1] = padd<Q>(sum, s[1]);
+    s[2] = padd<Q>(padd<Q>(sum, s[2]), s[2]);
+    s[3] = padd<Q>(sum, bb::halve(s[3]));
+    s[4] = padd<Q>(padd<Q>(sum, s[4]), pdbl<Q>(s[4]));
     {
-        const uint32_t d = bb::dbl(s[5]);
-        s[5] = add(add(sum, d), d);
+        const uint32_t d = pdbl<Q>(s[5]);
+        s[5] = padd<Q>(padd<Q>(sum, d), d);
     }
-    s[6] = sub(sum, bb::halve(s[6]));
-    s[7] = sub(sub(sum, s[7]), bb::dbl(s[7]));
+    s[6] = psub<Q>(sum, bb::halve(s[6]));
+    s[7] = psub<Q>(psub<Q>(sum, s[7]), pdbl<Q>(s[7]));
     {
-        const uint32_t d = bb::dbl(s[8]);
-        s[8] = sub(sub(sum, d), d);
+        const uint32_t d = pdbl<Q>(s[8]);
+        s[8] = psub<Q>(psub<Q>(sum, d), d);
     }
-    s[9] = add(sum, mul_2exp_neg<8>(s[9]));
-    s[10] = add(sum, mul_2exp_neg<2>(s[10]));
-    s[11] = add(sum, mul_2exp_neg<3>(s[11]));
-    s[12] = add(sum, mul_2exp_neg<27>(s[12]));
-    s[13] = add(sum, mul_neg_2exp_neg<8>(s[13]));
-    s[14] = add(sum, mul_neg_2exp_neg<4>(s[14]));
-    s[15] = add(sum, mul_neg_2exp_neg<27>(s[15]));
+    s[9] = padd<Q>(sum, mul_2exp_neg<8>(s[9]));
+    s[10] = padd<Q>(sum, mul_2exp_neg<2>(s[10]));
+    s[11] = padd<Q>(sum, mul_2exp_neg<3>(s[11]));
+    s[12] = padd<Q>(sum, mul_2exp_neg<27>(s[12]));
+    s[13] = padd<Q>(sum, mul_neg_2exp_neg<8>(s[13]));
+    s[14] = padd<Q>(sum, mul_neg_2exp_neg<4>(s[14]));
+    s[15] = padd<Q>(sum, mul_neg_2exp_neg<27>(s[15]));
 }
 
 #ifdef P2V2_UNROLL_ROUNDS
@@ -143,20 +187,21 @@ __host__ __device__ __forceinline__ void internal_linear(uint32_t s[16]) {
 #define P2V2_ROUND_LOOP _Pragma("unroll 1")
 #endif
 
-__host__ __device__ __forceinline__ void permute(uint32_t s[16]) {
-    external_linear_rc(s, &P2V2_RC_INIT(0));
+template <int POL>
+__host__ __device__ __forceinline__ void permute_pol(uint32_t s[16]) {
+    external_linear_rc<POL>(s, &P2V2_RC_INIT(0));
     P2V2_ROUND_LOOP
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox7((int32_t)s[i]);
-        external_linear_rc(s, &P2V2_RC_INIT((r + 1) * 16));
+        external_linear_rc<POL>(s, &P2V2_RC_INIT((r + 1) * 16));
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = canon((int32_t)s[i]);
     P2V2_ROUND_LOOP
     for (int r = 0; r < 13; r++) {
         s[0] = sbox7((int32_t)s[0] + P2V2_RC_INT(r));
-        internal_linear(s);
+        internal_linear<POL>(s);
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = (uint32_t)((int32_t)s[i] + P2V2_RC_TERM(i));
@@ -164,10 +209,12 @@ __host__ __device__ __forceinline__ void permute(uint32_t s[16]) {
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < 16; i++) s[i] = sbox7((int32_t)s[i]);
-        external_linear_rc(s, &P2V2_RC_TERM((r + 1) * 16));
+        external_linear_rc<POL>(s, &P2V2_RC_TERM((r + 1) * 16));
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) s[i] = canon((int32_t)s[i]);
 }
+
+__host__ __device__ __forceinline__ void permute(uint32_t s[16]) { permute_pol<P2V2_PIN_POLICY>(s); }
 
 }  // namespace p2v2

@@ -12,6 +12,7 @@ template <int V>
 __device__ __forceinline__ void perm(uint32_t s[16]) {
     if (V == 0) p2::permute_v1(s);
     if (V == 1) p2v2::permute(s);
+    if (V >= 100) p2v2::permute_pol<V - 100>(s);  // pin-policy sweep
 }
 
 // every thread iterates the permutation `iters` times on its own state (issue-bound measurement)
@@ -81,6 +82,17 @@ int main() {
         size_t bad = 0;
         for (size_t i = 0; i < o0.size(); i++) bad += o0[i] != o1[i];
         printf("{\"check\": \"p2v2 == p2\", \"mismatches\": %zu}\n", bad);
+        if (tps == 2048) {
+            std::vector<uint32_t> o2;
+#define POLRUN(P)                                                                     \
+    {                                                                                 \
+        run<100 + P>("p2v2 pin policy " #P, init, o2, tps, sms, iters);               \
+        size_t b2 = 0;                                                                \
+        for (size_t i = 0; i < o0.size(); i++) b2 += o0[i] != o2[i];                  \
+        printf("{\"check\": \"policy " #P " == p2\", \"mismatches\": %zu}\n", b2); \
+    }
+            POLRUN(0) POLRUN(1) POLRUN(8) POLRUN(16) POLRUN(7) POLRUN(24) POLRUN(29) POLRUN(31) POLRUN(23) POLRUN(15) POLRUN(63) POLRUN(61) POLRUN(55) POLRUN(47) POLRUN(39) POLRUN(56)
+        }
     }
     return 0;
 }
