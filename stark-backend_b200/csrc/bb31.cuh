@@ -45,6 +45,13 @@ __host__ __device__ __forceinline__ uint32_t reduce(uint64_t x) {
     uint32_t u = r - P;
     return r < u ? r : u;
 }
+// x < 2 * p * 2^32 -> x / 2^32 mod p, canonical.  p*2^32 has a zero low word, so the conditional
+// subtraction that brings x below p*2^32 only touches the high word and is one unsigned min there
+// (VIADDMNMX) instead of a 64-bit compare + select + subtract (6 instructions).
+__host__ __device__ __forceinline__ uint32_t reduce_lazy(uint64_t x) {
+    const uint32_t hi = (uint32_t)(x >> 32), hm = hi - P;
+    return reduce(((uint64_t)(hi < hm ? hi : hm) << 32) | (uint32_t)x);
+}
 __host__ __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) { return reduce((uint64_t)a * b); }
 __host__ __device__ __forceinline__ uint32_t sqr(uint32_t a) { return mul(a, a); }
 
@@ -141,10 +148,8 @@ __host__ __device__ __forceinline__ Ext ext_mul_base(Ext a, uint32_t s) {
 // `reduce` requires (4 p^2 - p 2^32 < p 2^32).
 __host__ __device__ __forceinline__ uint32_t dot4(uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1,
                                                   uint32_t a2, uint32_t b2, uint32_t a3, uint32_t b3) {
-    const uint64_t PP = (uint64_t)P << 32;
-    uint64_t s = ((uint64_t)a0 * b0 + (uint64_t)a1 * b1) + ((uint64_t)a2 * b2 + (uint64_t)a3 * b3);
-    s = s >= PP ? s - PP : s;
-    return reduce(s);
+    const uint64_t s = ((uint64_t)a0 * b0 + (uint64_t)a1 * b1) + ((uint64_t)a2 * b2 + (uint64_t)a3 * b3);
+    return reduce_lazy(s);
 }
 
 __host__ __device__ __forceinline__ Ext ext_mul(Ext a, Ext b) {

@@ -30,10 +30,9 @@ __device__ __forceinline__ uint32_t f_reduce(uint64_t x) {  // x < p * 2^32 -> x
 __device__ __forceinline__ uint32_t f_mul(uint32_t a, uint32_t b) { return f_reduce((uint64_t)a * b); }
 __device__ __forceinline__ uint32_t f_dot4(uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, uint32_t a3,
                                            uint32_t b3) {
-    const uint64_t PP = (uint64_t)SW_P << 32;
     uint64_t s = ((uint64_t)a0 * b0 + (uint64_t)a1 * b1) + ((uint64_t)a2 * b2 + (uint64_t)a3 * b3);
-    s = s >= PP ? s - PP : s;
-    return f_reduce(s);
+    const uint32_t hi = (uint32_t)(s >> 32), hm = hi - SW_P;  // conditional - p*2^32: one unsigned min on the high word
+    return f_reduce(((uint64_t)(hi < hm ? hi : hm) << 32) | (uint32_t)s);
 }
 
 struct Ext {

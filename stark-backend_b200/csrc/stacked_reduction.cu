@@ -59,7 +59,6 @@ sr_round0_kernel(const R0View* __restrict__ views, const uint32_t* __restrict__ 
     // a1 = sum_x eq[x] q[x], b = sum_x eq[x-1] q[x] (a2 = b - a1): EF x base products summed four at a time in 64 bits
     // (4 p^2 < 2^64) with one Montgomery reduction per coefficient per group instead of one per product
     Ext a1 = bb::ext_zero(), b1 = bb::ext_zero();
-    const uint64_t PP = (uint64_t)bb::P << 32;
     for (size_t xb = x0 + g; xb < x1; xb += 4 * (size_t)G) {
         uint64_t s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -78,8 +77,8 @@ sr_round0_kernel(const R0View* __restrict__ views, const uint32_t* __restrict__ 
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            a1.c[k] = bb::add(a1.c[k], bb::reduce(s1[k] >= PP ? s1[k] - PP : s1[k]));
-            b1.c[k] = bb::add(b1.c[k], bb::reduce(s2[k] >= PP ? s2[k] - PP : s2[k]));
+            a1.c[k] = bb::add(a1.c[k], bb::reduce_lazy(s1[k]));
+            b1.c[k] = bb::add(b1.c[k], bb::reduce_lazy(s2[k]));
         }
     }
     const Ext a2 = ext_sub(b1, a1);
@@ -120,7 +119,6 @@ sr_round0_vec_kernel(const R0View* __restrict__ views, const uint32_t* __restric
     for (int c = 0; c < 4; c++)
 #pragma unroll
         for (int k = 0; k < 4; k++) a1[c][k] = b1[c][k] = 0;
-    const uint64_t PP = (uint64_t)bb::P << 32;
     if (xs < xe) {
         Ext ep = ldg_ext(eq + 4 * (xs == 0 ? nx - 1 : xs - 1));
         for (size_t xb = xs; xb < xe; xb += 4) {
@@ -150,8 +148,8 @@ sr_round0_vec_kernel(const R0View* __restrict__ views, const uint32_t* __restric
             for (int c = 0; c < 4; c++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    a1[c][k] = bb::add(a1[c][k], bb::reduce(s1[c][k] >= PP ? s1[c][k] - PP : s1[c][k]));
-                    b1[c][k] = bb::add(b1[c][k], bb::reduce(s2[c][k] >= PP ? s2[c][k] - PP : s2[c][k]));
+                    a1[c][k] = bb::add(a1[c][k], bb::reduce_lazy(s1[c][k]));
+                    b1[c][k] = bb::add(b1[c][k], bb::reduce_lazy(s2[c][k]));
                 }
         }
     }

@@ -20,7 +20,8 @@ class SwirlError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libswirl_b200.so")
+    # SWIRL_B200_LIB: an alternative build of the same library (A/B measurements of kernel variants)
+    return os.environ.get("SWIRL_B200_LIB") or os.path.join(_HERE, "libswirl_b200.so")
 
 
 class PcsParamsC(C.Structure):
