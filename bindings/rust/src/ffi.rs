@@ -52,6 +52,8 @@ extern "C" {
     pub fn swirl_ctx_timing_enable(ctx: *mut SwirlCtx, on: c_int) -> c_int;
     pub fn swirl_ctx_timing_read(ctx: *mut SwirlCtx, slot: c_int, total_ms: *mut f64, count: *mut u64) -> c_int;
     pub fn swirl_ctx_sync_stats(ctx: *mut SwirlCtx, count: *mut u64, wait_ms: *mut f64) -> c_int;
+    pub fn swirl_ctx_set_round_link(ctx: *mut SwirlCtx, on: c_int) -> c_int;
+    pub fn swirl_ctx_link_stats(ctx: *mut SwirlCtx, count: *mut u64) -> c_int;
     pub fn swirl_ctx_timing_bytes(ctx: *mut SwirlCtx, slot: c_int, bytes: *mut u64) -> c_int;
     pub fn swirl_malloc(ctx: *mut SwirlCtx, bytes: usize, d_out: *mut *mut c_void) -> c_int;
     pub fn swirl_free(ctx: *mut SwirlCtx, d_ptr: *mut c_void) -> c_int;

@@ -74,6 +74,13 @@ int swirl_ctx_timing_enable(swirl_ctx* ctx, int on);
 int swirl_ctx_timing_read(swirl_ctx* ctx, int slot, double* total_ms, uint64_t* count);
 /* Stream synchronisations issued by the library on this context so far and the wall time spent inside them. */
 int swirl_ctx_sync_stats(swirl_ctx* ctx, uint64_t* count, double* wait_ms);
+/* Round link: the kernels of all rounds of a sumcheck are enqueued up front and exchange each round's
+ * result / next challenge with the host transcript through a mapped pinned mailbox, so neither a launch nor a stream
+ * synchronisation sits between two rounds (on = 1, the default; 0 = one launch + cudaStreamSynchronize per round, the
+ * reference's pattern: cuda-backend/src/logup_zerocheck/fractional.rs:649-, sponge.rs:267-300).  Same proof either way.
+ * swirl_ctx_link_stats: round results received through the mailbox so far. */
+int swirl_ctx_set_round_link(swirl_ctx* ctx, int on);
+int swirl_ctx_link_stats(swirl_ctx* ctx, uint64_t* count);
 /* Algorithmic bytes of the recorded launches of a family; 0 for families without accounting. */
 int swirl_ctx_timing_bytes(swirl_ctx* ctx, int slot, uint64_t* bytes);
 

@@ -496,6 +496,16 @@ class B200Device:
         check(self.lib.swirl_ctx_sync_stats(self.ctx, C.byref(n), C.byref(ms)))
         return int(n.value), ms.value
 
+    def set_round_link(self, on):
+        """Sumcheck rounds through the mapped mailbox (default) or one launch + stream synchronisation per round."""
+        check(self.lib.swirl_ctx_set_round_link(self.ctx, 1 if on else 0))
+
+    def link_stats(self):
+        """Round results received through the mailbox (no stream synchronisation) so far."""
+        n = C.c_uint64()
+        check(self.lib.swirl_ctx_link_stats(self.ctx, C.byref(n)))
+        return int(n.value)
+
     def timing_enable(self, on=True):
         check(self.lib.swirl_ctx_timing_enable(self.ctx, 1 if on else 0))
 

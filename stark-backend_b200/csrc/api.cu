@@ -109,6 +109,7 @@ static int ctx_init(int device, cudaStream_t stream, bool owns, swirl_ctx** out)
     ctx->device = device;
     ctx->stream = stream;
     ctx->owns_stream = owns;
+    if (const char* env = getenv("SWIRL_ROUND_LINK")) ctx->round_link = atoi(env) != 0;  // A/B knob, see swirl_ctx_set_round_link
     if (owns) {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -248,6 +249,18 @@ int swirl_ctx_sync_stats(swirl_ctx* ctx, uint64_t* count, double* wait_ms) {
     SWIRL_REQUIRE(ctx && count && wait_ms, "null argument");
     *count = ctx->sync_count;
     *wait_ms = ctx->sync_ms;
+    return 0;
+}
+
+int swirl_ctx_set_round_link(swirl_ctx* ctx, int on) {
+    SWIRL_REQUIRE(ctx, "null ctx");
+    ctx->round_link = on != 0;
+    return 0;
+}
+
+int swirl_ctx_link_stats(swirl_ctx* ctx, uint64_t* count) {
+    SWIRL_REQUIRE(ctx && count, "null argument");
+    *count = ctx->link_count;
     return 0;
 }
 

@@ -40,6 +40,7 @@ struct swirl_ctx {
     // commitment for the WHIR openings (true: 2x the trace in HBM) or stream it through a column-group scratch at commit
     // time and recompute the opened rows' columns in the openings (false: the large-trace mode, BASELINE configs[3])
     bool cache_codeword = true;
+    bool round_link = true;  // sumcheck rounds exchange results/challenges with the host through a mapped mailbox (ext.cuh: RoundLink)
     int jit_mode = 1;  // run-time compiled constraint kernels: 0 = never, 1 = traces of 2^17 rows and more, 2 = always (tests)
     size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)
     // optional per-kernel-family CUDA-event timing (bench.py's roofline numbers)
@@ -58,6 +59,7 @@ struct swirl_ctx {
     // host-side synchronisation statistics (swirl_ctx_sync_stats): how much of a proof is spent waiting on the stream
     uint64_t sync_count = 0;
     double sync_ms = 0;
+    uint64_t link_count = 0;  // round results received through the mapped mailbox instead of a stream synchronisation (ext.cuh: RoundLink)
     // pinned staging area for device-to-host copies into caller (pageable) memory, see d2h_staged
     void* program_cache = nullptr;  // compiled constraint programs (batch.cu: ProgramCache)
     void* h_stage = nullptr;

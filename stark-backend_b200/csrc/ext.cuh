@@ -57,15 +57,16 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t (&v)[NV]) {
 // reset for the next launch.  blockDim.x must be a multiple of 32, <= 1024, >= NV.
 // Group form: the blocks [0, nblocks) of one logical group (bidx = this block's index in the group)
 // reduce into `result`; several groups may share a launch, each with its own ticket and partials.
+// Returns true (block-uniform) in the block that wrote `result`.
 template <int NV>
-__device__ __forceinline__ void group_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
+__device__ __forceinline__ bool group_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
                                           unsigned int* __restrict__ ticket, uint32_t* __restrict__ result,
-                                          unsigned nblocks, unsigned bidx) {
+                                          unsigned nblocks, unsigned bidx, uint32_t tag = 0) {
     __shared__ bool sm_last;
     const uint32_t tot = block_sum<NV>(v);
     if (nblocks == 1) {
-        if (threadIdx.x < NV) result[threadIdx.x] = tot;
-        return;
+        if (threadIdx.x < NV) result[threadIdx.x] = tot | tag;
+        return true;
     }
     if (threadIdx.x < NV) partials[(size_t)bidx * NV + threadIdx.x] = tot;
     __threadfence();
@@ -82,14 +83,71 @@ __device__ __forceinline__ void group_sum(uint32_t (&v)[NV], uint32_t* __restric
             for (int i = 0; i < NV; i++) acc[i] = bb::add(acc[i], __ldcg(partials + (size_t)b * NV + i));
         }
         const uint32_t t2 = block_sum<NV>(acc);
-        if (threadIdx.x < NV) result[threadIdx.x] = t2;
+        if (threadIdx.x < NV) result[threadIdx.x] = t2 | tag;
         if (threadIdx.x == 0) *ticket = 0;
     }
+    return sm_last;
 }
 template <int NV>
-__device__ __forceinline__ void grid_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
-                                         unsigned int* __restrict__ ticket, uint32_t* __restrict__ result) {
-    group_sum<NV>(v, partials, ticket, result, gridDim.x, blockIdx.x);
+__device__ __forceinline__ bool grid_sum(uint32_t (&v)[NV], uint32_t* __restrict__ partials,
+                                         unsigned int* __restrict__ ticket, uint32_t* __restrict__ result, uint32_t tag = 0) {
+    return group_sum<NV>(v, partials, ticket, result, gridDim.x, blockIdx.x, tag);
+}
+
+// ---- round link: host <-> kernel mailbox through mapped pinned memory -----------------------------------------
+// A sumcheck round is "sweep a table, send a few field elements to the transcript, get a challenge back".  With one
+// launch + cudaStreamSynchronize per round that exchange costs ~10 us (tools/latency_bench.cu); a device-resident
+// sponge is no way out, because a lone Poseidon2 permutation takes 4.2 us on the GPU (0.86 us on the host).  So the
+// transcript stays on the host and the *launches and stream synchronisations* leave the critical path instead: the
+// kernels of all rounds of a sumcheck are enqueued up front; each one waits (block 0 polls the mapped mailbox, the
+// other blocks poll block 0's relay in device memory) for the challenge the host derives from the previous round,
+// and the host polls the round's result words in mapped memory.
+// Every access that crosses PCIe is a full round trip (~1.5 us), so each direction is ONE transaction and carries its
+// own "ready" mark instead of a separate flag + fence: field words are < 2^31, their top bits are free.
+//  * host -> device: the challenge is one aligned 16-byte store; the top bits of its four words spell seq % 15
+//    (15 = abort), the kernel polls with one 16-byte volatile load until they spell its own sequence number;
+//  * device -> host: the result words carry (seq & 1) in their top bit; the host waits until all of them do.
+// Sequence numbers are consecutive inside one sumcheck, so the previous content never looks ready.
+struct RoundLink {
+    const uint32_t* mail;  // mapped pinned, written by the host: 4 tagged challenge words (16-byte aligned)
+    uint32_t* gate;        // device: block 0's relay of the mailbox, same format
+    uint32_t seq;          // this launch (0 = no link: plain stream-ordered kernel)
+    uint32_t wait;         // the launch needs a challenge before it starts
+};
+__host__ __device__ __forceinline__ uint32_t link_mail_tag(uint32_t seq) { return seq % 15u; }
+__host__ __device__ __forceinline__ uint32_t link_result_tag(uint32_t seq) { return (seq & 1u) << 31; }  // 0 when seq == 0
+
+__device__ __forceinline__ uint4 link_poll(const uint32_t* p, uint32_t want) {
+    uint4 v;
+    const long long t0 = clock64();
+    for (unsigned it = 1;; it++) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        const uint32_t tag = (v.x >> 31) | ((v.y >> 31) << 1) | ((v.z >> 31) << 2) | ((v.w >> 31) << 3);
+        if (tag == want || tag == 15u) break;
+        if ((it & 255u) == 0 && clock64() - t0 > 4000000000ll) break;  // ~2 s: a dead host must not hang the GPU
+    }
+    return v;
+}
+// All threads of every block call this first; returns the challenge (garbage after an abort or a time-out: the host
+// ignores the results then).
+__device__ __forceinline__ Ext link_wait(const RoundLink& l) {
+    __shared__ uint4 sm_link;
+    if (l.seq == 0 || !l.wait) return bb::ext_zero();
+    if (threadIdx.x == 0) {
+        const uint32_t want = link_mail_tag(l.seq);
+        uint4 v;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            v = link_poll(l.mail, want);
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(l.gate), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                         : "memory");  // one 16-byte store: the relay is consistent as well
+        } else {
+            v = link_poll(l.gate, want);
+        }
+        sm_link = v;
+    }
+    __syncthreads();
+    const uint4 v = sm_link;
+    return Ext{{v.x & 0x7fffffffu, v.y & 0x7fffffffu, v.z & 0x7fffffffu, v.w & 0x7fffffffu}};
 }
 
 // Scratch every sumcheck-type phase needs: block partials, the ticket, and a mapped pinned result
@@ -100,7 +158,32 @@ struct RoundScratch {
     uint32_t* h_result = nullptr;  // pinned, mapped
     uint32_t* d_result = nullptr;  // device alias of h_result
     int max_blocks = 0;
+    // round link (see RoundLink)
+    uint32_t* h_link = nullptr;  // mapped pinned mailbox (4 words used)
+    uint32_t* d_link = nullptr;  // device alias
+    uint32_t* d_gate = nullptr;  // 4 words of device memory
+    uint32_t link_seq = 0;
 };
 int round_scratch_get(swirl_ctx* ctx, RoundScratch** out);
+
+// ---- host side of the round link ----
+// Start of a sumcheck whose rounds leave `nv` result words at h_result + offset: marks them "not ready" for the first
+// sequence number (earlier, unlinked kernels store untagged words there).  All earlier rounds must have been consumed.
+inline void link_begin(RoundScratch* rs, size_t offset, int nv) {
+    if (rs->link_seq >= 0xfffffff0u) rs->link_seq = 0;
+    const uint32_t not_ready = link_result_tag(rs->link_seq + 1) ^ 0x80000000u;
+    volatile uint32_t* r = rs->h_result + offset;
+    for (int i = 0; i < nv; i++) r[i] = not_ready;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+inline RoundLink link_make(RoundScratch* rs, bool wait) {
+    ++rs->link_seq;
+    return RoundLink{rs->d_link, rs->d_gate, rs->link_seq, wait ? 1u : 0u};
+}
+void link_send(RoundScratch* rs, uint32_t seq, const Ext& r);  // challenge for the launch `seq`
+void link_abort(RoundScratch* rs);                             // releases every launch that still waits
+// Waits until the launch `seq` has left its `nv` result words at h_result + offset and copies them (untagged) to out.
+// Polls the stream every ~0.1 ms so that a faulted kernel surfaces as its CUDA error instead of a hang.
+int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, uint32_t* out);
 
 }  // namespace swirl

@@ -102,6 +102,7 @@ struct RoundArgs {
     uint32_t* result;  // 8 words: t(1) and the leading coefficient of t
     uint32_t* last_rows;  // non-null in the last device round of a layer: this round's whole table (rows 2y = lo, 2y+1 = hi,
                           // 4 EF each, at most 32 rows) for the host, which finishes the layer
+    RoundLink link;       // seq != 0: the previous challenge arrives through the mailbox instead of `r` (ext.cuh)
 };
 
 template <bool FROM_TREE>
@@ -142,7 +143,7 @@ __host__ __device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ex
 template <bool FROM_TREE, bool FOLD>
 __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
     const Ext lambda = Ext{{a.lambda[0], a.lambda[1], a.lambda[2], a.lambda[3]}};
-    const Ext r = Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
+    const Ext r = FOLD && a.link.seq ? link_wait(a.link) : Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
     const Ext c = Ext{{a.c[0], a.c[1], a.c[2], a.c[3]}};
     Ext s[2] = {bb::ext_zero(), bb::ext_zero()};
     const size_t a_mask = (size_t(1) << a.a_bits) - 1;
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
     for (int X = 0; X < 2; X++)
 #pragma unroll
         for (int k = 0; k < 4; k++) v[X * 4 + k] = s[X].c[k];
-    grid_sum<8>(v, a.partials, a.ticket, a.result);
+    if (a.last_rows) __threadfence_system();  // the exported table must be in host memory before the result words say "ready"
+    grid_sum<8>(v, a.partials, a.ticket, a.result, link_result_tag(a.link.seq));
 }
 
 static int round_grid(const swirl_ctx* ctx, size_t work_items) {
@@ -393,6 +395,63 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             for (int k = 0; k < 4; k++) a.r[k] = r.c[k];
             return 0;
         };
+        // ---- device rounds: launch (all up front when the round link is on), then one exchange per round ------------
+        struct Launched {
+            uint32_t seq;
+            size_t y_tail, ny;
+            bool exports;
+        };
+        std::vector<Launched> launched;
+        uint32_t res_words[8];
+        auto launch_round = [&](int sr, bool linked) -> int {
+            // tables of the remaining variables [sr+1, round)
+            if (sr + 1 < v_split) {
+                a.a_bits = v_split - 1 - sr;
+                a.A = suffix(eqA, nA, sr);
+                a.B = suffix(eqB, nB, 0);
+            } else {
+                a.a_bits = 0;
+                a.A = nullptr;
+                a.B = suffix(eqB, nB, sr + 1 - v_split);
+            }
+            size_t y_tail;
+            a.last_rows = sr == sr_host - 1 ? rs->d_result + 64 : nullptr;  // the table the host continues from
+            a.link = linked ? link_make(rs, sr > 0) : RoundLink{};
+            {
+                SwirlTimed timed(ctx, SWIRL_T_GKR);
+                if (sr == 0) {
+                    a.rows_in = rows_tree;
+                    a.ny = y_tail = (rows_tree + 1) / 2;
+                    gkr_round_kernel<true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                } else if (sr == 1) {
+                    a.rows_in = rows_tree;
+                    a.ny = y_tail = (rows_tree + 3) / 4;
+                    a.out = tab[0];
+                    a.out_stride = tab_stride[0];
+                    gkr_round_kernel<true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                    rows = 2 * a.ny;
+                    cur = 0;
+                } else {
+                    a.in = tab[cur];
+                    a.in_stride = tab_stride[cur];
+                    a.rows_in = rows;
+                    a.ny = y_tail = (rows + 3) / 4;
+                    a.out = tab[cur ^ 1];
+                    a.out_stride = tab_stride[cur ^ 1];
+                    gkr_round_kernel<false, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                    rows = 2 * a.ny;
+                    cur ^= 1;
+                }
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+            launched.push_back({a.link.seq, y_tail, a.ny, a.last_rows != nullptr});
+            return 0;
+        };
+        const bool linked = ctx->round_link;
+        if (linked) {
+            link_begin(rs, 0, 8);
+            for (int sr = 0; sr < sr_host && rc == 0; sr++) rc = launch_round(sr, true);
+        }
         for (int sr = 0; sr < round && rc == 0; sr++) {
             if (sr >= sr_host) {
                 // ---- host round: fold the small table with the previous challenge, then sweep it -------------------
@@ -424,52 +483,27 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
                 continue;
             }
             // ---- device round ---------------------------------------------------------------------------------------
-            // tables of the remaining variables [sr+1, round)
-            if (sr + 1 < v_split) {
-                a.a_bits = v_split - 1 - sr;
-                a.A = suffix(eqA, nA, sr);
-                a.B = suffix(eqB, nB, 0);
+            if (linked) {
+                if (sr > 0) link_send(rs, launched[sr].seq, rho.back());
+                rc = link_recv(ctx, rs, launched[sr].seq, 0, 8, res_words);
+                if (rc != 0) break;
             } else {
-                a.a_bits = 0;
-                a.A = nullptr;
-                a.B = suffix(eqB, nB, sr + 1 - v_split);
+                rc = launch_round(sr, false);
+                if (rc != 0) break;
+                SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+                memcpy(res_words, rs->h_result, 32);
             }
-            size_t y_tail;
-            a.last_rows = sr == sr_host - 1 ? rs->d_result + 64 : nullptr;  // the table the host continues from
-            {
-                SwirlTimed timed(ctx, SWIRL_T_GKR);
-                if (sr == 0) {
-                    a.rows_in = rows_tree;
-                    a.ny = y_tail = (rows_tree + 1) / 2;
-                    gkr_round_kernel<true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
-                } else if (sr == 1) {
-                    a.rows_in = rows_tree;
-                    a.ny = y_tail = (rows_tree + 3) / 4;
-                    a.out = tab[0];
-                    a.out_stride = tab_stride[0];
-                    gkr_round_kernel<true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
-                    rows = 2 * a.ny;
-                    cur = 0;
-                } else {
-                    a.in = tab[cur];
-                    a.in_stride = tab_stride[cur];
-                    a.rows_in = rows;
-                    a.ny = y_tail = (rows + 3) / 4;
-                    a.out = tab[cur ^ 1];
-                    a.out_stride = tab_stride[cur ^ 1];
-                    gkr_round_kernel<false, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
-                    rows = 2 * a.ny;
-                    cur ^= 1;
-                }
-                SWIRL_LAUNCH_CHECK(ctx);
-            }
-            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
-            if (a.last_rows) {  // this round's table (2 ny <= 2^(GKR_HOST_LOG+1) rows) for the host rounds that follow
-                ht.resize(2 * a.ny);
+            const Launched& L = launched[sr];
+            if (L.exports) {  // this round's table (2 ny <= 2^(GKR_HOST_LOG+1) rows) for the host rounds that follow
+                ht.resize(2 * L.ny);
                 for (size_t i = 0; i < ht.size(); i++)
                     for (int k = 0; k < 4; k++) ht[i][k] = ext_from_words(rs->h_result + 64 + i * 16 + 4 * k);
             }
-            rc = finish_round(sr, ext_from_words(rs->h_result), ext_from_words(rs->h_result + 4), y_tail);
+            rc = finish_round(sr, ext_from_words(res_words), ext_from_words(res_words + 4), L.y_tail);
+        }
+        if (rc != 0 && linked) {  // release the kernels that still wait for a challenge
+            link_abort(rs);
+            cudaStreamSynchronize(ctx->stream);
         }
         if (rc != 0) break;
         // claims: fold the final 2-row table with the last challenge

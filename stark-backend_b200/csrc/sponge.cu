@@ -95,6 +95,8 @@ extern "C" int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], in
 }
 
 // ---- host transcript entry points (transcript.hpp) --------------------------------------------
+#include <emmintrin.h>
+
 #include "ext.cuh"
 #include "transcript.hpp"
 
@@ -108,11 +110,64 @@ int round_scratch_get(swirl_ctx* ctx, RoundScratch** out) {
         SWIRL_CUDA(cudaMalloc((void**)&rs->d_ticket, 1024 * sizeof(unsigned int)));
         SWIRL_CUDA(cudaMemset(rs->d_ticket, 0, 1024 * sizeof(unsigned int)));
         SWIRL_CUDA(cudaHostAlloc((void**)&rs->h_result, 65536, cudaHostAllocMapped));
+        memset(rs->h_result, 0, 65536);
         SWIRL_CUDA(cudaHostGetDevicePointer((void**)&rs->d_result, rs->h_result, 0));
+        SWIRL_CUDA(cudaHostAlloc((void**)&rs->h_link, 4096, cudaHostAllocMapped));
+        memset(rs->h_link, 0, 4096);
+        SWIRL_CUDA(cudaHostGetDevicePointer((void**)&rs->d_link, rs->h_link, 0));
+        SWIRL_CUDA(cudaMalloc((void**)&rs->d_gate, 8 * sizeof(uint32_t)));
+        SWIRL_CUDA(cudaMemset(rs->d_gate, 0, 8 * sizeof(uint32_t)));
         ctx->round_scratch = rs;
     }
     *out = (RoundScratch*)ctx->round_scratch;
     return 0;
+}
+
+void link_send(RoundScratch* rs, uint32_t seq, const Ext& r) {
+    const uint32_t t = link_mail_tag(seq);
+    alignas(16) uint32_t w[4];
+    for (int k = 0; k < 4; k++) w[k] = r.c[k] | (((t >> k) & 1u) << 31);
+    _mm_store_si128(reinterpret_cast<__m128i*>(rs->h_link), _mm_load_si128(reinterpret_cast<const __m128i*>(w)));  // one 16-byte store
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+void link_abort(RoundScratch* rs) {
+    _mm_store_si128(reinterpret_cast<__m128i*>(rs->h_link), _mm_set1_epi32((int)0x80000000u));  // tag 15
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
+
+int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, uint32_t* out) {
+    const volatile uint32_t* res = rs->h_result + offset;
+    const uint32_t tag = link_result_tag(seq);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto next_query = t0 + std::chrono::microseconds(100);
+    ctx->link_count++;
+    auto ready = [&]() {
+        for (int i = 0; i < nv; i++)
+            if ((res[i] & 0x80000000u) != tag) return false;
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        for (int i = 0; i < nv; i++) out[i] = res[i] & 0x7fffffffu;
+        return true;
+    };
+    for (;;) {
+        for (int spin = 0; spin < 256; spin++)
+            if (ready()) return 0;
+        const auto now = std::chrono::steady_clock::now();
+        if (now < next_query) continue;
+        next_query = now + std::chrono::microseconds(100);
+        const cudaError_t e = cudaStreamQuery(ctx->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "round link: kernel failed", __FILE__, __LINE__);
+        if (e == cudaSuccess) {  // the stream drained: either the result is there by now or the kernel gave up
+            if (ready()) return 0;
+            set_error("round link: the stream finished without publishing the round (kernel time-out or abort)");
+            return SWIRL_ERR_INVALID;
+        }
+        if (now - t0 > std::chrono::seconds(20)) {
+            link_abort(rs);
+            cudaStreamSynchronize(ctx->stream);
+            set_error("round link: no answer from the device within 20 s");
+            return SWIRL_ERR_INVALID;
+        }
+    }
 }
 
 void round_scratch_free(swirl_ctx* ctx) {
@@ -121,6 +176,8 @@ void round_scratch_free(swirl_ctx* ctx) {
     cudaFree(rs->d_partials);
     cudaFree(rs->d_ticket);
     cudaFreeHost(rs->h_result);
+    cudaFreeHost(rs->h_link);
+    cudaFree(rs->d_gate);
     delete rs;
     ctx->round_scratch = nullptr;
 }

@@ -72,6 +72,8 @@ PROTOTYPES = {
     "swirl_ctx_stream": (_vp, [_vp]),
     "swirl_ctx_launch_count": (_u64, [_vp]),
     "swirl_ctx_sync_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
+    "swirl_ctx_set_round_link": (_i, [_vp, _i]),
+    "swirl_ctx_link_stats": (_i, [_vp, C.POINTER(_u64)]),
     "swirl_ctx_timing_bytes": (_i, [_vp, _i, C.POINTER(_u64)]),
     "swirl_ctx_set_ntt_plan": (_i, [_vp, _i, _sz]),
     "swirl_ctx_set_cache_rs_code_matrix": (_i, [_vp, _i]),

@@ -4,13 +4,16 @@
 //     checked against the host permutation;
 //  2. a persistent kernel that exchanges one result/challenge pair per round with the host through mapped pinned
 //     memory (no launch, no stream synchronisation), against launch + cudaStreamSynchronize per round.
-//   nvcc -O3 -std=c++17 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -I../stark-backend_b200/csrc -o latency_bench.bin latency_bench.cu
+//   nvcc -O3 -std=c++17 --expt-relaxed-constexpr -gencode arch=compute_100a,code=sm_100a -I../stark-backend_b200/csrc -o latency_bench.bin latency_bench.cu \
+//        -L../stark-backend_b200 -lswirl_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../stark-backend_b200'
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <cuda_runtime.h>
 #include "poseidon2_v2.cuh"
 #include "poseidon2_warp.cuh"
+#include "ext.cuh"
 
 __global__ void chain_thread(uint32_t* state, int n) {
     uint32_t s[16];
@@ -47,6 +50,14 @@ __global__ void handshake_kernel(volatile uint32_t* to_host, volatile uint32_t* 
 }
 __global__ void tiny_kernel(uint32_t* out, uint32_t v) {
     if (threadIdx.x < 8) out[threadIdx.x] = v + threadIdx.x;
+}
+
+// the library's round link: one pre-enqueued kernel per round, challenge in / result out through the mapped mailbox
+__global__ void linked_round_kernel(swirl::RoundLink link, uint32_t* partials, unsigned int* ticket, uint32_t* result) {
+    const swirl::Ext r = swirl::link_wait(link);
+    uint32_t v[8];
+    for (int k = 0; k < 8; k++) v[k] = bb::add(r.c[k & 3], threadIdx.x == 0 && blockIdx.x == 0 ? 1u : 0u);
+    swirl::grid_sum<8>(v, partials, ticket, result, swirl::link_result_tag(link.seq));
 }
 
 int main() {
@@ -120,6 +131,61 @@ int main() {
         }
         const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         printf("{\"bench\": \"round trip\", \"mode\": \"launch + cudaStreamSynchronize per round\", \"us_per_round_trip\": %.3f}\n", us / rounds);
+    }
+    {
+        uint32_t *h_link, *d_link, *d_gate, *h_res, *d_res, *d_part;
+        unsigned int* d_ticket;
+        cudaHostAlloc(&h_link, 4096, cudaHostAllocMapped);
+        memset(h_link, 0, 4096);
+        cudaHostGetDevicePointer(&d_link, h_link, 0);
+        cudaHostAlloc(&h_res, 4096, cudaHostAllocMapped);
+        memset(h_res, 0, 4096);
+        cudaHostGetDevicePointer(&d_res, h_res, 0);
+        cudaMalloc(&d_gate, 32);
+        cudaMemset(d_gate, 0, 32);
+        cudaMalloc(&d_part, 8192 * 64 * 4);
+        cudaMalloc(&d_ticket, 4096);
+        cudaMemset(d_ticket, 0, 4096);
+        cudaStream_t st;
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        swirl::RoundScratch rs;
+        rs.h_result = h_res;
+        rs.d_result = d_res;
+        rs.h_link = h_link;
+        rs.d_link = d_link;
+        rs.d_gate = d_gate;
+        swirl_ctx ctx;
+        ctx.stream = st;
+        for (int blocks : {1, 8, 592}) {
+            for (int batch : {1, 16}) {
+                const int rounds = 2000;
+                cudaStreamSynchronize(st);
+                auto t0 = std::chrono::steady_clock::now();
+                int bad = 0;
+                for (int k0 = 0; k0 < rounds; k0 += batch) {
+                    swirl::link_begin(&rs, 0, 8);
+                    uint32_t seqs[16];
+                    for (int b = 0; b < batch; b++) {
+                        const swirl::RoundLink l = swirl::link_make(&rs, true);
+                        seqs[b] = l.seq;
+                        linked_round_kernel<<<blocks, 256, 0, st>>>(l, d_part, d_ticket, d_res);
+                    }
+                    for (int b = 0; b < batch; b++) {
+                        swirl::Ext r{{(uint32_t)(k0 + b), 1u, 2u, 3u}};
+                        swirl::link_send(&rs, seqs[b], r);
+                        uint32_t out[8];
+                        if (swirl::link_recv(&ctx, &rs, seqs[b], 0, 8, out) != 0) bad++;
+                        // every thread adds r (blocks * 256 of them), one adds 1 more
+                        const uint64_t n = (uint64_t)blocks * 256;
+                        if (out[1] != (uint32_t)((n * 1 + 1) % bb::P) || out[0] != (uint32_t)((n * (k0 + b) + 1) % bb::P)) bad++;
+                    }
+                }
+                cudaStreamSynchronize(st);
+                const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+                printf("{\"bench\": \"round trip\", \"mode\": \"round link: %d kernels of %d blocks enqueued ahead, mailbox exchange per round\", \"us_per_round_trip\": %.3f, \"wrong_results\": %d, \"err\": \"%s\"}\n",
+                       batch, blocks, us / rounds, bad, cudaGetErrorString(cudaGetLastError()));
+            }
+        }
     }
     return 0;
 }
