@@ -566,7 +566,8 @@ struct FoldArgs {
     uint32_t first_block;
 };
 __global__ void __launch_bounds__(BC_BLOCK)
-ef_fold_multi_kernel(const FoldArgs* __restrict__ descs, const uint16_t* __restrict__ block_air, Ext r) {
+ef_fold_multi_kernel(const FoldArgs* __restrict__ descs, const uint16_t* __restrict__ block_air, Ext r, RoundLink link) {
+    if (link.seq) r = link_wait(link);  // linked: the challenge arrives through the mailbox (ext.cuh)
     const FoldArgs a = descs[block_air[blockIdx.x]];
     const size_t j = (size_t)(blockIdx.x - a.first_block) * blockDim.x + threadIdx.x;
     if (j >= a.n_out) return;
@@ -574,7 +575,7 @@ ef_fold_multi_kernel(const FoldArgs* __restrict__ descs, const uint16_t* __restr
 }
 template <int NS, int D>
 __global__ void __launch_bounds__(128, 4) batch_mle_kernel(const MleArgs* __restrict__ descs,
-                                                           const uint16_t* __restrict__ block_air) {
+                                                           const uint16_t* __restrict__ block_air, uint32_t result_tag) {
     const MleArgs a = descs[block_air[blockIdx.x]];
     const uint32_t bidx = blockIdx.x - a.first_block;
     uint32_t v[D * 12];
@@ -615,17 +616,17 @@ __global__ void __launch_bounds__(128, 4) batch_mle_kernel(const MleArgs* __rest
                 for (int c = 0; c < 4; c++) v[X * 12 + 4 * k + c] = bb::add(v[X * 12 + 4 * k + c], t.c[c]);
             }
     }
-    group_sum<D * 12>(v, a.partials, a.ticket, a.result, a.n_blocks, bidx);
+    group_sum<D * 12>(v, a.partials, a.ticket, a.result, a.n_blocks, bidx, result_tag);
 }
 
 template <int NS>
-static void launch_mle(int D, const MleArgs* descs, const uint16_t* block_air, int grid, cudaStream_t st) {
+static void launch_mle(int D, const MleArgs* descs, const uint16_t* block_air, int grid, cudaStream_t st, uint32_t tag) {
     switch (D) {
-        case 1: batch_mle_kernel<NS, 1><<<grid, 128, 0, st>>>(descs, block_air); break;
-        case 2: batch_mle_kernel<NS, 2><<<grid, 128, 0, st>>>(descs, block_air); break;
-        case 3: batch_mle_kernel<NS, 3><<<grid, 128, 0, st>>>(descs, block_air); break;
-        case 4: batch_mle_kernel<NS, 4><<<grid, 128, 0, st>>>(descs, block_air); break;
-        default: batch_mle_kernel<NS, 5><<<grid, 128, 0, st>>>(descs, block_air); break;
+        case 1: batch_mle_kernel<NS, 1><<<grid, 128, 0, st>>>(descs, block_air, tag); break;
+        case 2: batch_mle_kernel<NS, 2><<<grid, 128, 0, st>>>(descs, block_air, tag); break;
+        case 3: batch_mle_kernel<NS, 3><<<grid, 128, 0, st>>>(descs, block_air, tag); break;
+        case 4: batch_mle_kernel<NS, 4><<<grid, 128, 0, st>>>(descs, block_air, tag); break;
+        default: batch_mle_kernel<NS, 5><<<grid, 128, 0, st>>>(descs, block_air, tag); break;
     }
 }
 // NS buckets keep the per-thread slot array (local memory) as small as the program allows
@@ -1576,40 +1577,39 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     mark("fold_ple");
     // ---- MLE rounds (mod.rs:314-395, cpu.rs:463-597) --------------------------------------------------------
     const int s_deg = D + 1;
-    MleArgs* d_mle_descs = nullptr;
-    FoldArgs* d_fold_descs = nullptr;
-    uint16_t *d_mle_ba = nullptr, *d_fold_ba = nullptr;
-    size_t max_fold_blocks = 0;
-    for (size_t t = 0; t < n_airs; t++) max_fold_blocks += ((size_t)T[t].total_cols * (T[t].h / 2) + BC_BLOCK - 1) / BC_BLOCK + 1;
-    SWIRL_CUDA(dev_alloc(ctx, &d_mle_descs, 256));
-    SWIRL_CUDA(dev_alloc(ctx, &d_fold_descs, n_airs));
-    SWIRL_CUDA(dev_alloc(ctx, &d_mle_ba, (size_t)rs->max_blocks));
-    SWIRL_CUDA(dev_alloc(ctx, &d_fold_ba, max_fold_blocks));
-    to_free.push_back(d_mle_descs);
-    to_free.push_back(d_fold_descs);
-    to_free.push_back(d_mle_ba);
-    to_free.push_back(d_fold_ba);
+    // Plan of all rounds first: table sizes halve deterministically, so every round's kernel descriptors are known now.
+    // One upload for all of them (per-round copies from pageable memory were 4 blocking transfers per round), and with
+    // the round link (ext.cuh) every round's kernels are enqueued before the first result is read: the fold kernel of
+    // round k waits for the challenge in the mailbox, the evaluation kernel of round k + 1 follows it in the stream.
+    struct MleRound {
+        std::vector<int> mode;  // 0: hypercube sum, 1: single row now, 2: tail multiply, 3: nothing to evaluate
+        std::vector<size_t> desc_first, desc_count;
+        size_t desc_off = 0, n_descs = 0, ba_off = 0, n_blocks = 0;
+        size_t fold_off = 0, n_fold = 0, fba_off = 0, n_fold_blocks = 0;
+        RoundLink link{};
+    };
+    std::vector<MleRound> plan(n_max + 1);
+    std::vector<MleArgs> all_descs;
+    std::vector<FoldArgs> all_fd;
+    std::vector<uint16_t> all_ba, all_fba;
     for (int round = 1; round <= n_max; round++) {
-        const Ext r_prev = r[round - 1];
-        const Ext eq_r_acc = eq_ns.back(), eq_sharp_r_acc = eq_sharp_ns.back();
-        std::vector<int> mode(n_airs, 0);  // 0: hypercube sum, 1: single row now, 2: tail multiply, 3: nothing to evaluate
-        // eq tables of this round, one per height class still summing over a hypercube
-        for (auto& kv : eq_tab)
-            if (round <= kv.first) SWIRL_TRY(build_eq(l_skip + round, kv.first));
-        std::vector<MleArgs> descs;
-        std::vector<uint16_t> block_air;
-        std::vector<size_t> desc_first(n_airs, 0), desc_count(n_airs, 0);
+        MleRound& R = plan[round];
+        R.mode.assign(n_airs, 0);
+        R.desc_first.assign(n_airs, 0);
+        R.desc_count.assign(n_airs, 0);
+        R.desc_off = all_descs.size();
+        R.ba_off = all_ba.size();
         for (size_t t = 0; t < n_airs; t++) {
             TraceState& s = T[t];
             if (airs[t].constraint_degree == 0 && !airs[t].n_interactions && !airs[t].n_constraints) {
-                mode[t] = 3;
+                R.mode[t] = 3;
                 continue;
             }
             if (round > s.n_lift + 1) {
-                mode[t] = 2;
+                R.mode[t] = 2;
                 continue;
             }
-            desc_first[t] = descs.size();
+            R.desc_first[t] = R.n_descs;
             for (const auto& ch : s.chunks) {
                 MleArgs ma{};
                 ma.code = ch.d_code;
@@ -1618,11 +1618,11 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 ma.h = s.h;
                 ma.weights = s.d_weights;
                 ma.eq_xi = s.d_eq_xi;
-                SWIRL_REQUIRE(descs.size() < 256, "too many (AIR, program chunk) pairs for the result scratch");
-                ma.ticket = rs->d_ticket + descs.size();
-                ma.result = rs->d_result + descs.size() * 64;
+                SWIRL_REQUIRE(R.n_descs < 256, "too many (AIR, program chunk) pairs for the result scratch");
+                ma.ticket = rs->d_ticket + R.n_descs;
+                ma.result = rs->d_result + R.n_descs * 64;
                 if (round == s.n_lift + 1) {
-                    mode[t] = 1;
+                    R.mode[t] = 1;
                     ma.single = 1;
                     ma.ny = 1;
                     ma.n_blocks = 1;
@@ -1632,20 +1632,54 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                     ma.ny = size_t(1) << log_ny;
                     ma.n_blocks = (uint32_t)std::min<size_t>((ma.ny + 127) / 128, std::max<size_t>(1, (size_t)ctx->sm_count * 8 / s.chunks.size()));
                 }
-                ma.first_block = (uint32_t)block_air.size();
+                ma.first_block = (uint32_t)R.n_blocks;
                 ma.partials = rs->d_partials + (size_t)ma.first_block * 64;
-                block_air.insert(block_air.end(), ma.n_blocks, (uint16_t)descs.size());
-                descs.push_back(ma);
+                all_ba.insert(all_ba.end(), ma.n_blocks, (uint16_t)R.n_descs);
+                R.n_blocks += ma.n_blocks;
+                all_descs.push_back(ma);
+                R.n_descs++;
             }
-            desc_count[t] = descs.size() - desc_first[t];
+            R.desc_count[t] = R.n_descs - R.desc_first[t];
         }
-        if (!descs.empty()) {
-            SWIRL_REQUIRE(block_air.size() <= (size_t)rs->max_blocks, "too many blocks for the reduction scratch");
-            SWIRL_CUDA(cudaMemcpyAsync(d_mle_descs, descs.data(), descs.size() * sizeof(MleArgs), cudaMemcpyHostToDevice, ctx->stream));
-            SWIRL_CUDA(cudaMemcpyAsync(d_mle_ba, block_air.data(), block_air.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-            const int grid = (int)block_air.size();
+        SWIRL_REQUIRE(R.n_blocks <= (size_t)rs->max_blocks, "too many blocks for the reduction scratch");
+        R.fold_off = all_fd.size();
+        R.fba_off = all_fba.size();
+        for (size_t t = 0; t < n_airs; t++) {
+            TraceState& s = T[t];
+            if (s.h <= 1) continue;
+            FoldArgs f{s.ef[s.cur], s.ef[s.cur ^ 1], (size_t)s.total_cols * (s.h / 2), (uint32_t)R.n_fold_blocks};
+            const size_t nb = (f.n_out + BC_BLOCK - 1) / BC_BLOCK;
+            all_fba.insert(all_fba.end(), nb, (uint16_t)R.n_fold);
+            R.n_fold_blocks += nb;
+            all_fd.push_back(f);
+            R.n_fold++;
+            s.cur ^= 1;
+            s.h >>= 1;
+        }
+    }
+    MleArgs* d_mle_descs = nullptr;
+    FoldArgs* d_fold_descs = nullptr;
+    uint16_t *d_mle_ba = nullptr, *d_fold_ba = nullptr;
+    SWIRL_CUDA(dev_alloc(ctx, &d_mle_descs, std::max<size_t>(all_descs.size(), 1)));
+    SWIRL_CUDA(dev_alloc(ctx, &d_fold_descs, std::max<size_t>(all_fd.size(), 1)));
+    SWIRL_CUDA(dev_alloc(ctx, &d_mle_ba, std::max<size_t>(all_ba.size(), 1)));
+    SWIRL_CUDA(dev_alloc(ctx, &d_fold_ba, std::max<size_t>(all_fba.size(), 1)));
+    to_free.push_back(d_mle_descs);
+    to_free.push_back(d_fold_descs);
+    to_free.push_back(d_mle_ba);
+    to_free.push_back(d_fold_ba);
+    if (!all_descs.empty()) SWIRL_CUDA(cudaMemcpyAsync(d_mle_descs, all_descs.data(), all_descs.size() * sizeof(MleArgs), cudaMemcpyHostToDevice, ctx->stream));
+    if (!all_ba.empty()) SWIRL_CUDA(cudaMemcpyAsync(d_mle_ba, all_ba.data(), all_ba.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (!all_fd.empty()) SWIRL_CUDA(cudaMemcpyAsync(d_fold_descs, all_fd.data(), all_fd.size() * sizeof(FoldArgs), cudaMemcpyHostToDevice, ctx->stream));
+    if (!all_fba.empty()) SWIRL_CUDA(cudaMemcpyAsync(d_fold_ba, all_fba.data(), all_fba.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    auto launch_eval = [&](int round) -> int {  // eq tables + evaluation kernel of one round
+        const MleRound& R = plan[round];
+        for (auto& kv : eq_tab)
+            if (round <= kv.first) SWIRL_TRY(build_eq(l_skip + round, kv.first));
+        if (R.n_descs) {
+            const int grid = (int)R.n_blocks;
             // single-row AIRs evaluate lane 0 only; D lanes are still the kernel's width
-#define BC_MLE(NS) launch_mle<NS>(D, d_mle_descs, d_mle_ba, grid, ctx->stream)
+#define BC_MLE(NS) launch_mle<NS>(D, d_mle_descs + R.desc_off, d_mle_ba + R.ba_off, grid, ctx->stream, link_result_tag(R.link.seq))
             {
                 SwirlTimed timed(ctx, SWIRL_T_BC_MLE);
                 BC_DISPATCH_NS(max_slots, BC_MLE);
@@ -1653,14 +1687,59 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
 #undef BC_MLE
             SWIRL_LAUNCH_CHECK(ctx);
         }
-        SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+        return 0;
+    };
+    auto launch_fold = [&](int round, const Ext& r_val) -> int {
+        const MleRound& R = plan[round];
+        if (R.n_fold) {
+            ef_fold_multi_kernel<<<(unsigned)R.n_fold_blocks, BC_BLOCK, 0, ctx->stream>>>(d_fold_descs + R.fold_off, d_fold_ba + R.fba_off, r_val, R.link);
+            SWIRL_LAUNCH_CHECK(ctx);
+        }
+        return 0;
+    };
+    // linked rounds need a kernel on both ends of the exchange: one that publishes results and one that takes the challenge
+    bool linked = ctx->round_link;
+    for (int round = 1; round <= n_max; round++) linked = linked && plan[round].n_descs && plan[round].n_descs <= 64;
+    struct LinkGuard {  // an early return must release the kernels that still wait for a challenge
+        swirl_ctx* ctx;
+        RoundScratch* rs;
+        bool armed = false;
+        ~LinkGuard() {
+            if (!armed) return;
+            link_abort(rs);
+            cudaStreamSynchronize(ctx->stream);
+        }
+    } link_guard{ctx, rs};
+    if (linked) {
+        link_begin(rs, 0, 64 * 64);
+        link_guard.armed = true;
+        for (int round = 1; round <= n_max; round++) {
+            plan[round].link = link_make(rs, true);
+            SWIRL_TRY(launch_eval(round));
+            SWIRL_TRY(launch_fold(round, bb::ext_zero()));
+        }
+    }
+    std::vector<uint32_t> round_words(256 * 64);
+    for (int round = 1; round <= n_max; round++) {
+        const MleRound& R = plan[round];
+        const std::vector<int>& mode = R.mode;
+        const std::vector<size_t>&desc_first = R.desc_first, &desc_count = R.desc_count;
+        const Ext r_prev = r[round - 1];
+        const Ext eq_r_acc = eq_ns.back(), eq_sharp_r_acc = eq_sharp_ns.back();
+        if (linked) {
+            SWIRL_TRY(link_recv(ctx, rs, R.link.seq, 0, D * 12, R.n_descs, 64, round_words.data()));
+        } else {
+            SWIRL_TRY(launch_eval(round));
+            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+            for (size_t i = 0; i < R.n_descs * 64; i++) round_words[i] = rs->h_result[i];
+        }
         // sp_evals[2t] numer, [2t+1] denom, [2n+t] zerocheck: D values (head) or 1 value (tail)
         std::vector<std::vector<Ext>> sp(3 * n_airs);
         for (size_t t = 0; t < n_airs; t++) {
             TraceState& s = T[t];
             uint32_t res[64] = {0};  // sum over this AIR's program chunks
             for (size_t k = 0; k < desc_count[t]; k++)
-                for (int i = 0; i < 64; i++) res[i] = bb::add(res[i], rs->h_result[(desc_first[t] + k) * 64 + i] % bb::P);
+                for (int i = 0; i < D * 12; i++) res[i] = bb::add(res[i], round_words[(desc_first[t] + k) * 64 + i] % bb::P);
             const bool has_int = airs[t].n_interactions != 0;
             if (mode[t] == 3) {
                 sp[2 * n_airs + t].assign(D, bb::ext_zero());
@@ -1739,30 +1818,17 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         const Ext r_round = tr.sample_ext();
         r.push_back(r_round);
         prev_s_eval = hp::horner(coeffs, r_round);
-        {
-            std::vector<FoldArgs> fd;
-            std::vector<uint16_t> fba;
-            for (size_t t = 0; t < n_airs; t++) {
-                TraceState& s = T[t];
-                if (s.h <= 1) continue;
-                FoldArgs f{s.ef[s.cur], s.ef[s.cur ^ 1], (size_t)s.total_cols * (s.h / 2), (uint32_t)fba.size()};
-                fba.insert(fba.end(), (f.n_out + BC_BLOCK - 1) / BC_BLOCK, (uint16_t)fd.size());
-                fd.push_back(f);
-                s.cur ^= 1;
-                s.h >>= 1;
-            }
-            if (!fd.empty()) {
-                SWIRL_CUDA(cudaMemcpyAsync(d_fold_descs, fd.data(), fd.size() * sizeof(FoldArgs), cudaMemcpyHostToDevice, ctx->stream));
-                SWIRL_CUDA(cudaMemcpyAsync(d_fold_ba, fba.data(), fba.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-                ef_fold_multi_kernel<<<(unsigned)fba.size(), BC_BLOCK, 0, ctx->stream>>>(d_fold_descs, d_fold_ba, r_round);
-                SWIRL_LAUNCH_CHECK(ctx);
-            }
+        if (linked) {
+            if (R.n_fold) link_send(rs, R.link.seq, r_round);
+        } else {
+            SWIRL_TRY(launch_fold(round, r_round));
         }
         const Ext eq_r = hp::eq1(xi_cur, r_round);
         eq_ns.push_back(ext_mul(eq_ns[round - 1], eq_r));
         eq_sharp_ns.push_back(ext_mul(eq_sharp_ns[round - 1], eq_r));
     }
 
+    link_guard.armed = false;  // every linked launch has received its challenge
     mark("mle rounds");
     // ---- column openings (cpu.rs:644-694), observed common-main first (mod.rs:404-421) ------------------------
     std::vector<std::vector<uint32_t>> rows(n_airs);

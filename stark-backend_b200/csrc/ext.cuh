@@ -71,7 +71,10 @@ __device__ __forceinline__ bool group_sum(uint32_t (&v)[NV], uint32_t* __restric
     if (threadIdx.x < NV) partials[(size_t)bidx * NV + threadIdx.x] = tot;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) sm_last = (atomicAdd(ticket, 1u) == nblocks - 1);
+    if (threadIdx.x == 0) {
+        sm_last = (atomicAdd(ticket, 1u) == nblocks - 1);
+        if (sm_last) *ticket = 0;  // before the result is stored: a linked successor may start as soon as the host has seen it
+    }
     __syncthreads();
     if (sm_last) {
         __threadfence();
@@ -84,7 +87,6 @@ __device__ __forceinline__ bool group_sum(uint32_t (&v)[NV], uint32_t* __restric
         }
         const uint32_t t2 = block_sum<NV>(acc);
         if (threadIdx.x < NV) result[threadIdx.x] = t2 | tag;
-        if (threadIdx.x == 0) *ticket = 0;
     }
     return sm_last;
 }
@@ -101,7 +103,8 @@ __device__ __forceinline__ bool grid_sum(uint32_t (&v)[NV], uint32_t* __restrict
 // transcript stays on the host and the *launches and stream synchronisations* leave the critical path instead: the
 // kernels of all rounds of a sumcheck are enqueued up front; each one waits (block 0 polls the mapped mailbox, the
 // other blocks poll block 0's relay in device memory) for the challenge the host derives from the previous round,
-// and the host polls the round's result words in mapped memory.
+// and the host polls the round's result words in mapped memory.  (Starting the next kernel early with programmatic
+// dependent launch on top of this was measured and changes nothing: profiles/r2m_*.)
 // Every access that crosses PCIe is a full round trip (~1.5 us), so each direction is ONE transaction and carries its
 // own "ready" mark instead of a separate flag + fence: field words are < 2^31, their top bits are free.
 //  * host -> device: the challenge is one aligned 16-byte store; the top bits of its four words spell seq % 15
@@ -169,11 +172,11 @@ int round_scratch_get(swirl_ctx* ctx, RoundScratch** out);
 // ---- host side of the round link ----
 // Start of a sumcheck whose rounds leave `nv` result words at h_result + offset: marks them "not ready" for the first
 // sequence number (earlier, unlinked kernels store untagged words there).  All earlier rounds must have been consumed.
-inline void link_begin(RoundScratch* rs, size_t offset, int nv) {
+inline void link_begin(RoundScratch* rs, size_t offset, size_t nv) {
     if (rs->link_seq >= 0xfffffff0u) rs->link_seq = 0;
     const uint32_t not_ready = link_result_tag(rs->link_seq + 1) ^ 0x80000000u;
     volatile uint32_t* r = rs->h_result + offset;
-    for (int i = 0; i < nv; i++) r[i] = not_ready;
+    for (size_t i = 0; i < nv; i++) r[i] = not_ready;
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
 }
 inline RoundLink link_make(RoundScratch* rs, bool wait) {
@@ -182,8 +185,12 @@ inline RoundLink link_make(RoundScratch* rs, bool wait) {
 }
 void link_send(RoundScratch* rs, uint32_t seq, const Ext& r);  // challenge for the launch `seq`
 void link_abort(RoundScratch* rs);                             // releases every launch that still waits
-// Waits until the launch `seq` has left its `nv` result words at h_result + offset and copies them (untagged) to out.
+// Waits until the launch `seq` has left its result words in host memory: `groups` runs of `nv` words, `stride` words
+// apart, starting at h_result + offset; copies them (untagged) to out at the same spacing.
 // Polls the stream every ~0.1 ms so that a faulted kernel surfaces as its CUDA error instead of a hang.
-int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, uint32_t* out);
+int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, size_t groups, size_t stride, uint32_t* out);
+inline int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, uint32_t* out) {
+    return link_recv(ctx, rs, seq, offset, nv, 1, 0, out);
+}
 
 }  // namespace swirl

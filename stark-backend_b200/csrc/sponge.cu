@@ -135,17 +135,19 @@ void link_abort(RoundScratch* rs) {
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
 }
 
-int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, uint32_t* out) {
+int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int nv, size_t groups, size_t stride, uint32_t* out) {
     const volatile uint32_t* res = rs->h_result + offset;
     const uint32_t tag = link_result_tag(seq);
     const auto t0 = std::chrono::steady_clock::now();
     auto next_query = t0 + std::chrono::microseconds(100);
     ctx->link_count++;
     auto ready = [&]() {
-        for (int i = 0; i < nv; i++)
-            if ((res[i] & 0x80000000u) != tag) return false;
+        for (size_t g = 0; g < groups; g++)
+            for (int i = 0; i < nv; i++)
+                if ((res[g * stride + i] & 0x80000000u) != tag) return false;
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
-        for (int i = 0; i < nv; i++) out[i] = res[i] & 0x7fffffffu;
+        for (size_t g = 0; g < groups; g++)
+            for (int i = 0; i < nv; i++) out[g * stride + i] = res[g * stride + i] & 0x7fffffffu;
         return true;
     };
     for (;;) {
