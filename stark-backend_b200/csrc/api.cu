@@ -254,7 +254,7 @@ int swirl_ctx_sync_stats(swirl_ctx* ctx, uint64_t* count, double* wait_ms) {
 
 int swirl_ctx_set_round_link(swirl_ctx* ctx, int on) {
     SWIRL_REQUIRE(ctx, "null ctx");
-    ctx->round_link = on != 0;
+    ctx->round_link = on != 0 && ctx->round_link_ok;
     return 0;
 }
 

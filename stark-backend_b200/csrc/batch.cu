@@ -567,7 +567,7 @@ struct FoldArgs {
 };
 __global__ void __launch_bounds__(BC_BLOCK)
 ef_fold_multi_kernel(const FoldArgs* __restrict__ descs, const uint16_t* __restrict__ block_air, Ext r, RoundLink link) {
-    if (link.seq) r = link_wait(link);  // linked: the challenge arrives through the mailbox (ext.cuh)
+    if (!link_wait(link, r)) return;  // linked: the challenge arrives through the mailbox (ext.cuh)
     const FoldArgs a = descs[block_air[blockIdx.x]];
     const size_t j = (size_t)(blockIdx.x - a.first_block) * blockDim.x + threadIdx.x;
     if (j >= a.n_out) return;
@@ -1710,14 +1710,15 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             cudaStreamSynchronize(ctx->stream);
         }
     } link_guard{ctx, rs};
-    if (linked) {
-        link_begin(rs, 0, 64 * 64);
+    auto launch_linked = [&](int round) -> int {  // one round ahead of the exchange, see the rule in ext.cuh
+        plan[round].link = link_make(rs, true);
+        SWIRL_TRY(launch_eval(round));
+        return launch_fold(round, bb::ext_zero());
+    };
+    if (linked && n_max >= 1) {
+        link_begin(ctx, rs, 0, 64 * 64);
         link_guard.armed = true;
-        for (int round = 1; round <= n_max; round++) {
-            plan[round].link = link_make(rs, true);
-            SWIRL_TRY(launch_eval(round));
-            SWIRL_TRY(launch_fold(round, bb::ext_zero()));
-        }
+        SWIRL_TRY(launch_linked(1));
     }
     std::vector<uint32_t> round_words(256 * 64);
     for (int round = 1; round <= n_max; round++) {
@@ -1820,6 +1821,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         prev_s_eval = hp::horner(coeffs, r_round);
         if (linked) {
             if (R.n_fold) link_send(rs, R.link.seq, r_round);
+            if (round < n_max) SWIRL_TRY(launch_linked(round + 1));
         } else {
             SWIRL_TRY(launch_fold(round, r_round));
         }

@@ -40,6 +40,7 @@ struct swirl_ctx {
     // commitment for the WHIR openings (true: 2x the trace in HBM) or stream it through a column-group scratch at commit
     // time and recompute the opened rows' columns in the openings (false: the large-trace mode, BASELINE configs[3])
     bool cache_codeword = true;
+    bool round_link_ok = true;  // false once the probe found launches serialised (profiler, sanitizer): sponge.cu link_probe
     bool round_link = true;  // sumcheck rounds exchange results/challenges with the host through a mapped mailbox (ext.cuh: RoundLink)
     int jit_mode = 1;  // run-time compiled constraint kernels: 0 = never, 1 = traces of 2^17 rows and more, 2 = always (tests)
     size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)

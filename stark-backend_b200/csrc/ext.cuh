@@ -107,50 +107,71 @@ __device__ __forceinline__ bool grid_sum(uint32_t (&v)[NV], uint32_t* __restrict
 // dependent launch on top of this was measured and changes nothing: profiles/r2m_*.)
 // Every access that crosses PCIe is a full round trip (~1.5 us), so each direction is ONE transaction and carries its
 // own "ready" mark instead of a separate flag + fence: field words are < 2^31, their top bits are free.
-//  * host -> device: the challenge is one aligned 16-byte store; the top bits of its four words spell seq % 15
-//    (15 = abort), the kernel polls with one 16-byte volatile load until they spell its own sequence number;
+//  * host -> device: the challenge is one aligned 16-byte store; the top bits of its four words spell seq % 14
+//    (14 = idle, written when a sumcheck starts; 15 = abort), the kernel polls with one 16-byte volatile load until
+//    they spell its own sequence number;
 //  * device -> host: the result words carry (seq & 1) in their top bit; the host waits until all of them do.
 // Sequence numbers are consecutive inside one sumcheck, so the previous content never looks ready.
+// Failure handling: a kernel that sees the abort mark, or waits ~2 s in vain (a dead host must not hang the GPU),
+// raises a sticky flag next to the relay and returns WITHOUT publishing; every later linked kernel returns at once,
+// the stream drains, and the host's link_recv reports the missing round instead of using a made-up challenge.
+// Rule for the host: NO CUDA call while an enqueued kernel may be waiting for a mail that has not been sent.  Another
+// thread's device-synchronising call (cudaFree, a context being destroyed) holds the driver's lock until all enqueued
+// work has finished; a launch of ours queued behind that lock, with a kernel of ours waiting for us, is a deadlock
+// that only the device time-out breaks (seen with three concurrent provers).  Hence the rounds are enqueued exactly ONE
+// ahead -- kernel k + 1 is launched right after the challenge of kernel k has been sent, while k runs -- and link_recv
+// only looks at the stream after 250 ms of silence.
 struct RoundLink {
     const uint32_t* mail;  // mapped pinned, written by the host: 4 tagged challenge words (16-byte aligned)
-    uint32_t* gate;        // device: block 0's relay of the mailbox, same format
+    uint32_t* gate;        // device: [0,4) block 0's relay of the mailbox (same format), [4] sticky abort flag
     uint32_t seq;          // this launch (0 = no link: plain stream-ordered kernel)
     uint32_t wait;         // the launch needs a challenge before it starts
 };
-__host__ __device__ __forceinline__ uint32_t link_mail_tag(uint32_t seq) { return seq % 15u; }
+constexpr uint32_t LINK_TAG_IDLE = 14u, LINK_TAG_ABORT = 15u;
+__host__ __device__ __forceinline__ uint32_t link_mail_tag(uint32_t seq) { return seq % 14u; }
 __host__ __device__ __forceinline__ uint32_t link_result_tag(uint32_t seq) { return (seq & 1u) << 31; }  // 0 when seq == 0
 
-__device__ __forceinline__ uint4 link_poll(const uint32_t* p, uint32_t want) {
-    uint4 v;
+__device__ __forceinline__ bool link_poll(const uint32_t* p, uint32_t want, uint4& v) {
     const long long t0 = clock64();
     for (unsigned it = 1;; it++) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
         const uint32_t tag = (v.x >> 31) | ((v.y >> 31) << 1) | ((v.z >> 31) << 2) | ((v.w >> 31) << 3);
-        if (tag == want || tag == 15u) break;
-        if ((it & 255u) == 0 && clock64() - t0 > 4000000000ll) break;  // ~2 s: a dead host must not hang the GPU
+        if (tag == want) return true;
+        if (tag == LINK_TAG_ABORT) return false;
+        if ((it & 255u) == 0 && clock64() - t0 > 4000000000ll) return false;
     }
-    return v;
 }
-// All threads of every block call this first; returns the challenge (garbage after an abort or a time-out: the host
-// ignores the results then).
-__device__ __forceinline__ Ext link_wait(const RoundLink& l) {
+// All threads of every block call this first.  Returns false (block-uniform) when the round was aborted: the kernel
+// must return without publishing a result.
+__device__ __forceinline__ bool link_wait(const RoundLink& l, Ext& r) {
     __shared__ uint4 sm_link;
-    if (l.seq == 0 || !l.wait) return bb::ext_zero();
+    __shared__ bool sm_ok;
+    if (l.seq == 0 || !l.wait) return true;
     if (threadIdx.x == 0) {
-        const uint32_t want = link_mail_tag(l.seq);
-        uint4 v;
-        if (blockIdx.x == 0 && blockIdx.y == 0) {
-            v = link_poll(l.mail, want);
-            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(l.gate), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                         : "memory");  // one 16-byte store: the relay is consistent as well
-        } else {
-            v = link_poll(l.gate, want);
+        volatile uint32_t* g = l.gate;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        bool ok = g[4] == 0;
+        if (ok) {
+            const uint32_t want = link_mail_tag(l.seq);
+            if (blockIdx.x == 0 && blockIdx.y == 0) {
+                ok = link_poll(l.mail, want, v);
+                if (!ok) {
+                    g[4] = 1;
+                    v = make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);  // abort mark for the other blocks
+                }
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(l.gate), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                             : "memory");  // one 16-byte store: the relay is consistent as well
+            } else {
+                ok = link_poll(l.gate, want, v);
+            }
         }
         sm_link = v;
+        sm_ok = ok;
     }
     __syncthreads();
     const uint4 v = sm_link;
-    return Ext{{v.x & 0x7fffffffu, v.y & 0x7fffffffu, v.z & 0x7fffffffu, v.w & 0x7fffffffu}};
+    r = Ext{{v.x & 0x7fffffffu, v.y & 0x7fffffffu, v.z & 0x7fffffffu, v.w & 0x7fffffffu}};
+    return sm_ok;
 }
 
 // Scratch every sumcheck-type phase needs: block partials, the ticket, and a mapped pinned result
@@ -164,7 +185,7 @@ struct RoundScratch {
     // round link (see RoundLink)
     uint32_t* h_link = nullptr;  // mapped pinned mailbox (4 words used)
     uint32_t* d_link = nullptr;  // device alias
-    uint32_t* d_gate = nullptr;  // 4 words of device memory
+    uint32_t* d_gate = nullptr;  // 8 words of device memory
     uint32_t link_seq = 0;
 };
 int round_scratch_get(swirl_ctx* ctx, RoundScratch** out);
@@ -172,13 +193,8 @@ int round_scratch_get(swirl_ctx* ctx, RoundScratch** out);
 // ---- host side of the round link ----
 // Start of a sumcheck whose rounds leave `nv` result words at h_result + offset: marks them "not ready" for the first
 // sequence number (earlier, unlinked kernels store untagged words there).  All earlier rounds must have been consumed.
-inline void link_begin(RoundScratch* rs, size_t offset, size_t nv) {
-    if (rs->link_seq >= 0xfffffff0u) rs->link_seq = 0;
-    const uint32_t not_ready = link_result_tag(rs->link_seq + 1) ^ 0x80000000u;
-    volatile uint32_t* r = rs->h_result + offset;
-    for (size_t i = 0; i < nv; i++) r[i] = not_ready;
-    __atomic_thread_fence(__ATOMIC_SEQ_CST);
-}
+// Also resets the mailbox to "idle" and (stream-ordered) the relay and its abort flag.
+void link_begin(swirl_ctx* ctx, RoundScratch* rs, size_t offset, size_t nv);
 inline RoundLink link_make(RoundScratch* rs, bool wait) {
     ++rs->link_seq;
     return RoundLink{rs->d_link, rs->d_gate, rs->link_seq, wait ? 1u : 0u};

@@ -143,7 +143,8 @@ __host__ __device__ __forceinline__ void accumulate(const Ext (&lo)[4], const Ex
 template <bool FROM_TREE, bool FOLD>
 __global__ void __launch_bounds__(GKR_BLOCK) gkr_round_kernel(RoundArgs a) {
     const Ext lambda = Ext{{a.lambda[0], a.lambda[1], a.lambda[2], a.lambda[3]}};
-    const Ext r = FOLD && a.link.seq ? link_wait(a.link) : Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
+    Ext r = Ext{{a.r[0], a.r[1], a.r[2], a.r[3]}};
+    if (FOLD && !link_wait(a.link, r)) return;
     const Ext c = Ext{{a.c[0], a.c[1], a.c[2], a.c[3]}};
     Ext s[2] = {bb::ext_zero(), bb::ext_zero()};
     const size_t a_mask = (size_t(1) << a.a_bits) - 1;
@@ -447,10 +448,12 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             launched.push_back({a.link.seq, y_tail, a.ny, a.last_rows != nullptr});
             return 0;
         };
+        // Linked rounds are enqueued ONE ahead: kernel sr + 1 is launched right after kernel sr got its challenge, so
+        // no CUDA call is ever made while an enqueued kernel waits for a mail that has not been sent (ext.cuh).
         const bool linked = ctx->round_link;
-        if (linked) {
-            link_begin(rs, 0, 8);
-            for (int sr = 0; sr < sr_host && rc == 0; sr++) rc = launch_round(sr, true);
+        if (linked && sr_host > 0) {
+            link_begin(ctx, rs, 0, 8);
+            rc = launch_round(0, true);
         }
         for (int sr = 0; sr < round && rc == 0; sr++) {
             if (sr >= sr_host) {
@@ -485,7 +488,8 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             // ---- device round ---------------------------------------------------------------------------------------
             if (linked) {
                 if (sr > 0) link_send(rs, launched[sr].seq, rho.back());
-                rc = link_recv(ctx, rs, launched[sr].seq, 0, 8, res_words);
+                if (sr + 1 < sr_host) rc = launch_round(sr + 1, true);
+                if (rc == 0) rc = link_recv(ctx, rs, launched[sr].seq, 0, 8, res_words);
                 if (rc != 0) break;
             } else {
                 rc = launch_round(sr, false);

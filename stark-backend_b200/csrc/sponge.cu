@@ -102,6 +102,41 @@ extern "C" int swirl_sponge_grind(swirl_ctx* ctx, const uint32_t h_state[18], in
 
 namespace swirl {
 
+// Waits up to ~25 ms for the host's word: used once per context to find out whether launches are asynchronous at all.
+__global__ void link_probe_kernel(const uint32_t* mail, uint32_t want, uint32_t* got) {
+    const long long t0 = clock64();
+    uint4 v;
+    uint32_t tag;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mail));
+        tag = (v.x >> 31) | ((v.y >> 31) << 1) | ((v.z >> 31) << 2) | ((v.w >> 31) << 3);
+    } while (tag != want && clock64() - t0 < 50000000ll);
+    *got = tag == want ? 1u : 0u;
+}
+
+// The round link needs the host to run WHILE an enqueued kernel waits for it.  Under a profiler or a sanitizer that
+// serialises launches (ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1) the launch call itself blocks until the kernel
+// ends, and every linked round would sit out its device-side time-out.  One probe per context: a kernel that waits for
+// a word the host sends only after the launch call has returned.
+static void link_probe(swirl_ctx* ctx, RoundScratch* rs) {
+    if (!ctx->round_link) return;
+    const RoundLink l = link_make(rs, true);
+    uint32_t* d_got = rs->d_gate + 6;
+    const auto t0 = std::chrono::steady_clock::now();
+    link_probe_kernel<<<1, 1, 0, ctx->stream>>>(rs->d_link, link_mail_tag(l.seq), d_got);
+    const double launch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    link_send(rs, l.seq, bb::ext_zero());
+    uint32_t got = 0;
+    cudaError_t e = cudaMemcpyAsync(&got, d_got, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || !got || launch_ms > 10.0) {
+        ctx->round_link = false;
+        ctx->round_link_ok = false;
+        if (getenv("SWIRL_TRACE"))
+            fprintf(stderr, "[swirl] round link off: launches are serialised here (probe launch took %.1f ms, answered %u)\n", launch_ms, got);
+    }
+}
+
 int round_scratch_get(swirl_ctx* ctx, RoundScratch** out) {
     if (!ctx->round_scratch) {
         RoundScratch* rs = new RoundScratch();
@@ -118,9 +153,23 @@ int round_scratch_get(swirl_ctx* ctx, RoundScratch** out) {
         SWIRL_CUDA(cudaMalloc((void**)&rs->d_gate, 8 * sizeof(uint32_t)));
         SWIRL_CUDA(cudaMemset(rs->d_gate, 0, 8 * sizeof(uint32_t)));
         ctx->round_scratch = rs;
+        link_probe(ctx, rs);
     }
     *out = (RoundScratch*)ctx->round_scratch;
     return 0;
+}
+
+void link_begin(swirl_ctx* ctx, RoundScratch* rs, size_t offset, size_t nv) {
+    if (rs->link_seq >= 0xfffffff0u) rs->link_seq = 0;
+    const uint32_t not_ready = link_result_tag(rs->link_seq + 1) ^ 0x80000000u;
+    volatile uint32_t* r = rs->h_result + offset;
+    for (size_t i = 0; i < nv; i++) r[i] = not_ready;
+    // idle: tag 14 = bits 1, 2, 3
+    _mm_store_si128(reinterpret_cast<__m128i*>(rs->h_link), _mm_set_epi32((int)0x80000000u, (int)0x80000000u, (int)0x80000000u, 0));
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    // relay = idle as well, abort flag cleared (every earlier linked kernel has finished: its round was consumed)
+    static const uint32_t idle_gate[8] = {0, 0x80000000u, 0x80000000u, 0x80000000u, 0, 0, 0, 0};
+    cudaMemcpyAsync(rs->d_gate, idle_gate, sizeof(idle_gate), cudaMemcpyHostToDevice, ctx->stream);
 }
 
 void link_send(RoundScratch* rs, uint32_t seq, const Ext& r) {
@@ -139,7 +188,7 @@ int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int
     const volatile uint32_t* res = rs->h_result + offset;
     const uint32_t tag = link_result_tag(seq);
     const auto t0 = std::chrono::steady_clock::now();
-    auto next_query = t0 + std::chrono::microseconds(100);
+    auto next_query = t0 + std::chrono::milliseconds(250);
     ctx->link_count++;
     auto ready = [&]() {
         for (size_t g = 0; g < groups; g++)
@@ -155,7 +204,7 @@ int link_recv(swirl_ctx* ctx, RoundScratch* rs, uint32_t seq, size_t offset, int
             if (ready()) return 0;
         const auto now = std::chrono::steady_clock::now();
         if (now < next_query) continue;
-        next_query = now + std::chrono::microseconds(100);
+        next_query = now + std::chrono::milliseconds(250);
         const cudaError_t e = cudaStreamQuery(ctx->stream);
         if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "round link: kernel failed", __FILE__, __LINE__);
         if (e == cudaSuccess) {  // the stream drained: either the result is there by now or the kernel gave up

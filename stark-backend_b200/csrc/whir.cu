@@ -74,13 +74,15 @@ struct WhirRoundArgs {
     uint32_t* partials;
     unsigned int* ticket;
     uint32_t* result;  // 8 words: s(1), s(2)
+    RoundLink link;    // seq != 0: alpha arrives through the mailbox, the result words carry the ready mark (ext.cuh)
 };
 
 // MODE 0: s from the table as it is.  MODE 1: fold pairs with alpha, write, and accumulate s of
 // the folded table.  MODE 2: fold and write only.
 template <int MODE>
 __global__ void __launch_bounds__(WH_BLOCK) whir_round_kernel(WhirRoundArgs a) {
-    const Ext alpha = Ext{{a.alpha[0], a.alpha[1], a.alpha[2], a.alpha[3]}};
+    Ext alpha = Ext{{a.alpha[0], a.alpha[1], a.alpha[2], a.alpha[3]}};
+    if (MODE != 0 && !link_wait(a.link, alpha)) return;
     Ext s1 = bb::ext_zero(), s2 = bb::ext_zero();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(WH_BLOCK) whir_round_kernel(WhirRoundArgs a) {
         s2 = ext_add(s2, ext_mul(ext_sub(ext_add(f1, f1), f0), ext_sub(ext_add(w1, w1), w0)));
     }
     uint32_t v[8] = {s1.c[0], s1.c[1], s1.c[2], s1.c[3], s2.c[0], s2.c[1], s2.c[2], s2.c[3]};
-    grid_sum<8>(v, a.partials, a.ticket, a.result);
+    grid_sum<8>(v, a.partials, a.ticket, a.result, link_result_tag(a.link.seq));
 }
 
 struct PowArgs {
@@ -340,40 +342,69 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
         a.partials = rs->d_partials;
         a.ticket = rs->d_ticket;
         a.result = rs->d_result;
-        for (int round = 0; round < k; round++, sc_i++) {
+        // The k sumcheck rounds and the kernel that materialises the last fold.  With the round link they are all enqueued
+        // first and take their challenge from the mailbox; the proof-of-work search between two rounds must then stay on
+        // the host (a grind kernel would queue behind the kernels that wait for the challenge it precedes).
+        const bool linked = ctx->round_link && cfg->folding_pow_bits <= 10 && k <= 32;
+        uint32_t seqs[33] = {0};
+        auto launch_round = [&](int round) -> int {  // round == k: fold and write only
             a.f_in = f[cur];
             a.w_in = w[cur];
             a.n = n;
+            a.link = linked ? link_make(rs, round > 0) : RoundLink{};
+            seqs[round] = a.link.seq;
             if (round == 0) {
                 whir_round_kernel<0><<<wh_grid(ctx, n >> 1), WH_BLOCK, 0, ctx->stream>>>(a);
             } else {
                 a.f_out = f[cur ^ 1];
                 a.w_out = w[cur ^ 1];
-                whir_round_kernel<1><<<wh_grid(ctx, n >> 2), WH_BLOCK, 0, ctx->stream>>>(a);
+                if (round < k)
+                    whir_round_kernel<1><<<wh_grid(ctx, n >> 2), WH_BLOCK, 0, ctx->stream>>>(a);
+                else
+                    whir_round_kernel<2><<<wh_grid(ctx, n >> 1), WH_BLOCK, 0, ctx->stream>>>(a);
                 cur ^= 1;
                 n >>= 1;
             }
             SWIRL_LAUNCH_CHECK(ctx);
-            SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+            return 0;
+        };
+        if (linked) {  // one kernel ahead of the exchange, see the rule in ext.cuh
+            link_begin(ctx, rs, 0, 8);
+            SWIRL_TRY(launch_round(0));
+        }
+        for (int round = 0; round < k; round++, sc_i++) {
             uint32_t* s = sec_polys + sc_i * 8;
-            memcpy(s, rs->h_result, 32);
+            if (linked) {
+                rc = launch_round(round + 1);  // kernel `round` has its challenge already
+                if (rc == 0) rc = link_recv(ctx, rs, seqs[round], 0, 8, s);
+                if (rc != 0) {
+                    link_abort(rs);
+                    cudaStreamSynchronize(ctx->stream);
+                    break;
+                }
+            } else {
+                SWIRL_TRY(launch_round(round));
+                SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+                memcpy(s, rs->h_result, 32);
+            }
             tr.observe_ext(Ext{{s[0], s[1], s[2], s[3]}});
             tr.observe_ext(Ext{{s[4], s[5], s[6], s[7]}});
-            SWIRL_TRY(transcript_grind(ctx, ts, cfg->folding_pow_bits, &sec_fold_pow[sc_i]));
+            rc = transcript_grind(ctx, ts, cfg->folding_pow_bits, &sec_fold_pow[sc_i]);
+            if (rc != 0) {
+                if (linked) {
+                    link_abort(rs);
+                    cudaStreamSynchronize(ctx->stream);
+                }
+                break;
+            }
             const Ext alpha = tr.sample_ext();
             memcpy(a.alpha, alpha.c, 16);
+            if (linked) link_send(rs, seqs[round + 1], alpha);
         }
+        if (rc != 0) break;
         swirl::trace_mark(ctx, "whir", "sumcheck rounds", &t_prev);
         // materialise the last fold of this WHIR round
-        a.f_in = f[cur];
-        a.w_in = w[cur];
-        a.f_out = f[cur ^ 1];
-        a.w_out = w[cur ^ 1];
-        a.n = n;
-        whir_round_kernel<2><<<wh_grid(ctx, n >> 1), WH_BLOCK, 0, ctx->stream>>>(a);
-        SWIRL_LAUNCH_CHECK(ctx);
-        cur ^= 1;
-        n >>= 1;
+        if (!linked) SWIRL_TRY(launch_round(k));
         // g = MLE coefficients of f (4 coordinate columns)
         SWIRL_TRY(ext_aos_to_soa(ctx, f[cur], soa, n, n));
         SWIRL_TRY(mle_zeta(ctx, soa, n, m - k, 4, true));

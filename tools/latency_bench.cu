@@ -54,7 +54,8 @@ __global__ void tiny_kernel(uint32_t* out, uint32_t v) {
 
 // the library's round link: one pre-enqueued kernel per round, challenge in / result out through the mapped mailbox
 __global__ void linked_round_kernel(swirl::RoundLink link, uint32_t* partials, unsigned int* ticket, uint32_t* result) {
-    const swirl::Ext r = swirl::link_wait(link);
+    swirl::Ext r = bb::ext_zero();
+    if (!swirl::link_wait(link, r)) return;
     uint32_t v[8];
     for (int k = 0; k < 8; k++) v[k] = bb::add(r.c[k & 3], threadIdx.x == 0 && blockIdx.x == 0 ? 1u : 0u);
     swirl::grid_sum<8>(v, partials, ticket, result, swirl::link_result_tag(link.seq));
@@ -163,7 +164,7 @@ int main() {
                 auto t0 = std::chrono::steady_clock::now();
                 int bad = 0;
                 for (int k0 = 0; k0 < rounds; k0 += batch) {
-                    swirl::link_begin(&rs, 0, 8);
+                    swirl::link_begin(&ctx, &rs, 0, 8);
                     uint32_t seqs[16];
                     for (int b = 0; b < batch; b++) {
                         const swirl::RoundLink l = swirl::link_make(&rs, true);
