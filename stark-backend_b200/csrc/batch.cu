@@ -573,8 +573,11 @@ ef_fold_multi_kernel(const FoldArgs* __restrict__ descs, const uint16_t* __restr
     if (j >= a.n_out) return;
     st_ext(a.out + 4 * j, ext_lerp(ldg_ext(a.in + 8 * j), ldg_ext(a.in + 8 * j + 4), r));
 }
+#ifndef BC_MLE_MIN_BLOCKS
+#define BC_MLE_MIN_BLOCKS 4
+#endif
 template <int NS, int D>
-__global__ void __launch_bounds__(128, 4) batch_mle_kernel(const MleArgs* __restrict__ descs,
+__global__ void __launch_bounds__(128, BC_MLE_MIN_BLOCKS) batch_mle_kernel(const MleArgs* __restrict__ descs,
                                                            const uint16_t* __restrict__ block_air, uint32_t result_tag) {
     const MleArgs a = descs[block_air[blockIdx.x]];
     const uint32_t bidx = blockIdx.x - a.first_block;
@@ -723,7 +726,11 @@ static std::string generate_round0_source(const std::vector<Instr>& code, int n_
     s.reserve(statements * 128 + 16384);
     // the column load (4 x 16-byte loads + a 16-term dot product) is inlined while the kernel stays small
     s += loads <= 24 ? "#define SW_LOAD_ATTR __device__ __forceinline__\n" : "#define SW_LOAD_ATTR __device__ __noinline__\n";
-    s += "#define SW_MIN_BLOCKS 2\n";
+    {
+        int mb = 3;  // 85 registers: 2.98 ms against 3.57 ms at 2 (128 registers) for C2, profiles/r2s_*
+        if (const char* env = getenv("SWIRL_JIT_MIN_BLOCKS")) mb = std::max(1, std::min(4, atoi(env)));  // experiment knob
+        s += "#define SW_MIN_BLOCKS " + std::to_string(mb) + "\n";
+    }
     s += jit_prelude();
     s += "\nSW_R0_SIGNATURE(";
     s += name;

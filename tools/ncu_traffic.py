@@ -3,7 +3,7 @@ DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of its LARGEST launc
 `roofline.traffic`.   python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep [git-rev]"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FAMILIES = {"leaf": "leaf_tree_kernel", "bc_round0": "batch_round0", "ntt_pass": "ntt_strided_pass_kernel", "ntt_final": "ntt_final_pass_kernel"}
+FAMILIES = {"leaf": "leaf_tree_kernel", "bc_round0": "r0", "ntt_pass": "ntt_strided_pass_kernel", "ntt_final": "ntt_final_pass_kernel"}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 rep = sys.argv[1]
