@@ -273,6 +273,8 @@ class ShardedProver:
     def _commit(self, stacked):
         P = self.params
         H, W = stacked.height, stacked.width
+        if W < self.world:  # raised on every rank alike, before any collective
+            raise ValueError(f"sharded commitment: the stacked matrix has {W} columns, fewer than the {self.world} ranks")
         c0, c1 = column_slice(W, self.world, self.rank)
         full = _tensor_view(self.dev, stacked.stacked_ptr(), H * W)
         mine = full[c0 * H:c1 * H]
