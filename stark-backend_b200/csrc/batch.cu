@@ -1707,16 +1707,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     // linked rounds need a kernel on both ends of the exchange: one that publishes results and one that takes the challenge
     bool linked = ctx->round_link;
     for (int round = 1; round <= n_max; round++) linked = linked && plan[round].n_descs && plan[round].n_descs <= 64;
-    struct LinkGuard {  // an early return must release the kernels that still wait for a challenge
-        swirl_ctx* ctx;
-        RoundScratch* rs;
-        bool armed = false;
-        ~LinkGuard() {
-            if (!armed) return;
-            link_abort(rs);
-            cudaStreamSynchronize(ctx->stream);
-        }
-    } link_guard{ctx, rs};
+    LinkAbortGuard link_guard{ctx, rs};  // an early return must release the kernels that still wait for a challenge
     auto launch_linked = [&](int round) -> int {  // one round ahead of the exchange, see the rule in ext.cuh
         plan[round].link = link_make(rs, true);
         SWIRL_TRY(launch_eval(round));
@@ -1838,6 +1829,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     }
 
     link_guard.armed = false;  // every linked launch has received its challenge
+    if (linked) SWIRL_CUDA(link_flag_fetch(ctx, rs));
     mark("mle rounds");
     // ---- column openings (cpu.rs:644-694), observed common-main first (mod.rs:404-421) ------------------------
     std::vector<std::vector<uint32_t>> rows(n_airs);
@@ -1848,6 +1840,10 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         SWIRL_CUDA(cudaMemcpyAsync(rows[t].data(), s.ef[s.cur], rows[t].size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+    if (linked && link_aborted(rs)) {
+        set_error("round link: a fold kernel gave up waiting for its challenge");
+        return SWIRL_ERR_INVALID;
+    }
     std::vector<std::vector<std::vector<Ext>>> openings(n_airs);
     uint32_t* po = sec_open;
     for (size_t t = 0; t < n_airs; t++) {

@@ -116,16 +116,20 @@ __device__ __forceinline__ bool grid_sum(uint32_t (&v)[NV], uint32_t* __restrict
 // raises a sticky flag next to the relay and returns WITHOUT publishing; every later linked kernel returns at once,
 // the stream drains, and the host's link_recv reports the missing round instead of using a made-up challenge.
 // Rule for the host: NO CUDA call while an enqueued kernel may be waiting for a mail that has not been sent.  Another
-// thread's device-synchronising call (cudaFree, a context being destroyed) holds the driver's lock until all enqueued
-// work has finished; a launch of ours queued behind that lock, with a kernel of ours waiting for us, is a deadlock
-// that only the device time-out breaks (seen with three concurrent provers).  Hence the rounds are enqueued exactly ONE
-// ahead -- kernel k + 1 is launched right after the challenge of kernel k has been sent, while k runs -- and link_recv
-// only looks at the stream after 250 ms of silence.
+// thread's device-synchronising call (cudaFree, a context being destroyed, a module being loaded) holds the driver's lock
+// until all enqueued work has finished; a launch of ours queued behind that lock, with a kernel of ours waiting for us,
+// is a deadlock that only the device time-out breaks (seen with three concurrent provers).  Hence
+//  * the rounds are enqueued exactly ONE ahead: kernel k + 1 is launched right after the challenge of kernel k has been
+//    sent, while k runs;
+//  * at most one kernel waits per challenge and it is the LAST launch of its round (a round whose challenge has several
+//    consumers folds them into one launch: sr_fold_multi_kernel, ef_fold_multi_kernel);
+//  * link_recv only looks at the stream after 250 ms of silence.
 struct RoundLink {
     const uint32_t* mail;  // mapped pinned, written by the host: 4 tagged challenge words (16-byte aligned)
     uint32_t* gate;        // device: [0,4) block 0's relay of the mailbox (same format), [4] sticky abort flag
     uint32_t seq;          // this launch (0 = no link: plain stream-ordered kernel)
-    uint32_t wait;         // the launch needs a challenge before it starts
+    uint32_t wait;         // 1: the launch needs a challenge before it starts; 2: same, but a kernel earlier in the stream has
+                           // already relayed it (several kernels consume one challenge): every block reads the relay
 };
 constexpr uint32_t LINK_TAG_IDLE = 14u, LINK_TAG_ABORT = 15u;
 __host__ __device__ __forceinline__ uint32_t link_mail_tag(uint32_t seq) { return seq % 14u; }
@@ -153,7 +157,7 @@ __device__ __forceinline__ bool link_wait(const RoundLink& l, Ext& r) {
         bool ok = g[4] == 0;
         if (ok) {
             const uint32_t want = link_mail_tag(l.seq);
-            if (blockIdx.x == 0 && blockIdx.y == 0) {
+            if (l.wait == 1 && blockIdx.x == 0 && blockIdx.y == 0) {
                 ok = link_poll(l.mail, want, v);
                 if (!ok) {
                     g[4] = 1;
@@ -195,10 +199,34 @@ int round_scratch_get(swirl_ctx* ctx, RoundScratch** out);
 // sequence number (earlier, unlinked kernels store untagged words there).  All earlier rounds must have been consumed.
 // Also resets the mailbox to "idle" and (stream-ordered) the relay and its abort flag.
 void link_begin(swirl_ctx* ctx, RoundScratch* rs, size_t offset, size_t nv);
+// Marks `nv` result words "not ready" for the launch `seq`.  Needed between rounds only when a round may read result
+// words that the previous round did not write (their mark would be two rounds old, i.e. look ready); call it after the
+// previous round has been received and before its challenge is sent.
+inline void link_expect(RoundScratch* rs, size_t offset, size_t nv, uint32_t seq) {
+    const uint32_t not_ready = link_result_tag(seq) ^ 0x80000000u;
+    volatile uint32_t* r = rs->h_result + offset;
+    for (size_t i = 0; i < nv; i++) r[i] = not_ready;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
 inline RoundLink link_make(RoundScratch* rs, bool wait) {
     ++rs->link_seq;
     return RoundLink{rs->d_link, rs->d_gate, rs->link_seq, wait ? 1u : 0u};
 }
+// Kernels that wait for a challenge but publish nothing (folds) cannot report a time-out through a missing result: the
+// sticky flag they raise is fetched with the data the phase copies back anyway (link_flag_fetch before that copy's stream
+// synchronisation, link_aborted after it), so a kernel that gave up waiting ends the proof with an error, never with
+// tables that were silently left unfolded.
+inline cudaError_t link_flag_fetch(swirl_ctx* ctx, RoundScratch* rs) {
+    return cudaMemcpyAsync(rs->h_link + 64, rs->d_gate + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+}
+inline bool link_aborted(RoundScratch* rs) { return ((volatile uint32_t*)rs->h_link)[64] != 0; }
+// An early return between link_begin and the last link_send must release the kernels that still wait.
+struct LinkAbortGuard {
+    swirl_ctx* ctx;
+    RoundScratch* rs;
+    bool armed = false;
+    ~LinkAbortGuard();
+};
 void link_send(RoundScratch* rs, uint32_t seq, const Ext& r);  // challenge for the launch `seq`
 void link_abort(RoundScratch* rs);                             // releases every launch that still waits
 // Waits until the launch `seq` has left its result words in host memory: `groups` runs of `nv` words, `stride` words

@@ -179,6 +179,11 @@ void link_send(RoundScratch* rs, uint32_t seq, const Ext& r) {
     _mm_store_si128(reinterpret_cast<__m128i*>(rs->h_link), _mm_load_si128(reinterpret_cast<const __m128i*>(w)));  // one 16-byte store
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
 }
+LinkAbortGuard::~LinkAbortGuard() {
+    if (!armed) return;
+    link_abort(rs);
+    cudaStreamSynchronize(ctx->stream);
+}
 void link_abort(RoundScratch* rs) {
     _mm_store_si128(reinterpret_cast<__m128i*>(rs->h_link), _mm_set1_epi32((int)0x80000000u));  // tag 15
     __atomic_thread_fence(__ATOMIC_SEQ_CST);

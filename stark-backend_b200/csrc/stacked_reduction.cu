@@ -233,7 +233,8 @@ sr_tables_kernel(const uint32_t* __restrict__ eq, size_t n, TabArgs t, uint32_t*
 }
 // out[j] = in[2j] + (in[2j+1] - in[2j]) * r over a flat EF array (columns of even height stay aligned)
 __global__ void __launch_bounds__(SR_BLOCK)
-ef_fold_flat_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n_out, Ext r) {
+ef_fold_flat_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n_out, Ext r, RoundLink link) {
+    if (!link_wait(link, r)) return;  // linked rounds: the challenge arrives through the mailbox (ext.cuh)
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_out) return;
     st_ext(out + 4 * j, ext_lerp(ldg_ext(in + 8 * j), ldg_ext(in + 8 * j + 4), r));
@@ -246,6 +247,7 @@ struct MleView {
     uint32_t wA[4], wB[4];  // lambda_eq * eq_ub, lambda_rot * eq_ub (zero if none)
     uint32_t log_ny;
     uint32_t b;  // exhausted views: the bit of row_idx consumed this round
+    uint32_t vidx;  // linked rounds: index of the view (its eq_ub factor lives on the device)
 };
 struct WorkItem {
     uint32_t view, chunk;
@@ -253,7 +255,7 @@ struct WorkItem {
 
 __global__ void __launch_bounds__(SR_BLOCK)
 sr_mle_round_kernel(const MleView* __restrict__ views, const WorkItem* __restrict__ items, size_t y_per_block,
-                    uint32_t* partials, unsigned int* ticket, uint32_t* result) {
+                    uint32_t* partials, unsigned int* ticket, uint32_t* result, uint32_t tag) {
     const WorkItem it = items[blockIdx.x];
     const MleView v = views[it.view];
     const size_t ny = size_t(1) << v.log_ny;
@@ -273,18 +275,21 @@ sr_mle_round_kernel(const MleView* __restrict__ views, const WorkItem* __restric
     const Ext wA = hp::from_words(v.wA), wB = hp::from_words(v.wB);
     const Ext s1 = ext_add(ext_mul(wA, e1), ext_mul(wB, k1)), s2 = ext_add(ext_mul(wA, e2), ext_mul(wB, k2));
     uint32_t o[8] = {s1.c[0], s1.c[1], s1.c[2], s1.c[3], s2.c[0], s2.c[1], s2.c[2], s2.c[3]};
-    grid_sum<8>(o, partials, ticket, result);
+    grid_sum<8>(o, partials, ticket, result, tag);
 }
 // Views whose own variables are used up (round > n_lift): one thread per view, a 2-entry column.
+// eq_ub != null (linked rounds): wA / wB hold the lambda powers only and the view's factor prod eq1(u_j, b_j) over the
+// rounds since it was used up comes from the device array that sr_eq_ub_kernel maintains.
 __global__ void __launch_bounds__(SR_BLOCK)
 sr_mle_exhausted_kernel(const MleView* __restrict__ views, size_t n, uint32_t* partials, unsigned int* ticket,
-                        uint32_t* result) {
+                        uint32_t* result, const uint32_t* __restrict__ eq_ub, uint32_t tag) {
     Ext s1 = bb::ext_zero(), s2 = bb::ext_zero();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const MleView v = views[i];
         const Ext q0 = ldg_ext(v.q), q1 = ldg_ext(v.q + 4);
         const Ext q2 = ext_sub(ext_add(q1, q1), q0);
-        const Ext w = ext_add(ext_mul(hp::from_words(v.wA), ldg_ext(v.eq)), ext_mul(hp::from_words(v.wB), ldg_ext(v.krot)));
+        Ext w = ext_add(ext_mul(hp::from_words(v.wA), ldg_ext(v.eq)), ext_mul(hp::from_words(v.wB), ldg_ext(v.krot)));
+        if (eq_ub) w = ext_mul(w, ld_ext(eq_ub + 4 * v.vidx));
         // eq(X, b): X = 1 -> b;  X = 2 -> b ? 2 : -1
         if (v.b) {
             s1 = ext_add(s1, ext_mul(w, q1));
@@ -294,7 +299,32 @@ sr_mle_exhausted_kernel(const MleView* __restrict__ views, size_t n, uint32_t* p
         }
     }
     uint32_t o[8] = {s1.c[0], s1.c[1], s1.c[2], s1.c[3], s2.c[0], s2.c[1], s2.c[2], s2.c[3]};
-    grid_sum<8>(o, partials, ticket, result);
+    grid_sum<8>(o, partials, ticket, result, tag);
+}
+// Everything that consumes a round's challenge u, in ONE launch (linked rounds: a single kernel may wait for the mailbox
+// per challenge, and it must be the last launch of its round, see the rule in ext.cuh): the pairwise folds of the q
+// matrices and of the eq / kappa_rot tables (job.in != null: out[j] = lerp(in[2j], in[2j+1], u)), and the update
+// eq_ub[i] *= eq1(u, bit (l_skip + round - 1) of row_idx[i]) of the views used up before this round (job.in == null).
+struct SrFoldJob {
+    const uint32_t* in;
+    uint32_t* out;
+    size_t n_out;
+    uint32_t first_block;
+};
+__global__ void __launch_bounds__(SR_BLOCK)
+sr_fold_multi_kernel(const SrFoldJob* __restrict__ jobs, const uint16_t* __restrict__ block_job, uint32_t* __restrict__ eq_ub,
+                     const int* __restrict__ n_lift, const uint32_t* __restrict__ row_idx, int round, int l_skip, RoundLink link) {
+    Ext u = bb::ext_zero();
+    if (!link_wait(link, u)) return;
+    const SrFoldJob job = jobs[block_job[blockIdx.x]];
+    const size_t j = (size_t)(blockIdx.x - job.first_block) * blockDim.x + threadIdx.x;
+    if (j >= job.n_out) return;
+    if (job.in) {
+        st_ext(job.out + 4 * j, ext_lerp(ldg_ext(job.in + 8 * j), ldg_ext(job.in + 8 * j + 4), u));
+    } else if (round > n_lift[j]) {
+        const bool b = (row_idx[j] >> (l_skip + round - 1)) & 1;
+        st_ext(eq_ub + 4 * j, ext_mul(ld_ext(eq_ub + 4 * j), b ? u : ext_one_minus(u)));
+    }
 }
 
 struct HtTab {  // per distinct log_height: eq(., r) and kappa_rot(., r) tables
@@ -574,6 +604,204 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
     size_t qh = Hq;  // current height of the q_evals matrices
     std::vector<MleView> hviews, hex;
     std::vector<WorkItem> items;
+    const bool linked = ctx->round_link && views.size() < (size_t(1) << 31);
+    if (linked) {
+        // ---- linked rounds (ext.cuh): every round's descriptors are planned now (the weights that depend on earlier
+        // challenges, eq_ub, live on the device), uploaded once, and the rounds are enqueued one ahead of the exchange
+        struct SrRound {
+            size_t v_off = 0, n_views = 0, x_off = 0, n_ex = 0, i_off = 0, n_items = 0;
+            size_t j_off = 0, n_jobs = 0, b_off = 0, n_blocks = 0;  // the round's fold jobs and their block map
+        };
+        std::vector<SrRound> plan(n_stack + 1);
+        std::vector<MleView> all_views, all_ex;
+        std::vector<WorkItem> all_items;
+        std::vector<SrFoldJob> all_jobs;
+        std::vector<uint16_t> all_block_job;
+        {
+            int sim_qcur = 0;
+            size_t sim_qh = Hq;
+            std::map<int, std::pair<int, size_t>> sim;  // log_height -> (cur, len)
+            for (auto& kv : tabs) sim[kv.first] = {kv.second.cur, kv.second.len};
+            for (int round = 1; round <= n_stack; round++) {
+                SrRound& R = plan[round];
+                R.v_off = all_views.size();
+                R.x_off = all_ex.size();
+                R.i_off = all_items.size();
+                for (size_t i = 0; i < views.size(); i++) {
+                    const View& v = views[i];
+                    const HtTab& t = tabs[v.log_height];
+                    const int cur = sim[v.log_height].first;
+                    const int n_lift = t.n_lift;
+                    const int hd = std::max(n_lift - round, 0);
+                    MleView mv;
+                    const size_t row_start = round <= n_lift ? (v.row_idx >> v.log_height) << (hd + 1) : (v.row_idx >> (l_skip + round)) << 1;
+                    mv.q = qe[sim_qcur][v.com] + (v.col_idx * sim_qh + row_start) * 4;
+                    mv.eq = t.eq[cur];
+                    mv.krot = t.krot[cur];
+                    memcpy(mv.wA, lambda_pows[v.lam_eq].c, 16);
+                    if (v.lam_rot >= 0)
+                        memcpy(mv.wB, lambda_pows[v.lam_rot].c, 16);
+                    else
+                        memset(mv.wB, 0, 16);
+                    mv.log_ny = (uint32_t)hd;
+                    mv.b = 0;
+                    mv.vidx = (uint32_t)i;
+                    if (round > n_lift) {
+                        mv.b = (uint32_t)((v.row_idx >> (l_skip + round - 1)) & 1);
+                        all_ex.push_back(mv);
+                        R.n_ex++;
+                    } else {
+                        const size_t ny = size_t(1) << hd;
+                        for (size_t c = 0; c < (ny + y_per_block - 1) / y_per_block; c++) all_items.push_back(WorkItem{(uint32_t)R.n_views, (uint32_t)c});
+                        all_views.push_back(mv);
+                        R.n_views++;
+                    }
+                }
+                R.n_items = all_items.size() - R.i_off;
+                // the consumers of this round's challenge
+                R.j_off = all_jobs.size();
+                R.b_off = all_block_job.size();
+                auto add_job = [&](const uint32_t* in, uint32_t* out, size_t n_out) {
+                    const size_t nb = (n_out + SR_BLOCK - 1) / SR_BLOCK;
+                    all_jobs.push_back(SrFoldJob{in, out, n_out, (uint32_t)R.n_blocks});
+                    all_block_job.insert(all_block_job.end(), nb, (uint16_t)R.n_jobs);
+                    R.n_blocks += nb;
+                    R.n_jobs++;
+                };
+                if (sim_qh > 1) {
+                    for (size_t ci = 0; ci < n_commits; ci++) add_job(qe[sim_qcur][ci], qe[sim_qcur ^ 1][ci], pcs[ci]->layout.width * (sim_qh / 2));
+                    sim_qcur ^= 1;
+                    sim_qh >>= 1;
+                }
+                for (auto& kv : sim)
+                    if (kv.second.second > 1) {
+                        const HtTab& t = tabs[kv.first];
+                        const int cur = kv.second.first;
+                        add_job(t.eq[cur], t.eq[cur ^ 1], kv.second.second / 2);
+                        add_job(t.krot[cur], t.krot[cur ^ 1], kv.second.second / 2);
+                        kv.second.first ^= 1;
+                        kv.second.second /= 2;
+                    }
+                if (R.n_ex && round < n_stack) add_job(nullptr, nullptr, views.size());
+            }
+        }
+        MleView *d_all_views = nullptr, *d_all_ex = nullptr;
+        WorkItem* d_all_items = nullptr;
+        SrFoldJob* d_all_jobs = nullptr;
+        uint16_t* d_all_block_job = nullptr;
+        SWIRL_REQUIRE(n_commits + 2 * tabs.size() + 1 < 65536, "too many fold jobs");
+        SWIRL_CUDA(dev_alloc(ctx, &d_all_jobs, std::max<size_t>(all_jobs.size(), 1)));
+        SWIRL_CUDA(dev_alloc(ctx, &d_all_block_job, std::max<size_t>(all_block_job.size(), 1)));
+        to_free.push_back(d_all_jobs);
+        to_free.push_back(d_all_block_job);
+        uint32_t *d_eq_ub = nullptr, *d_row_idx = nullptr;
+        int* d_n_lift = nullptr;
+        SWIRL_CUDA(dev_alloc(ctx, &d_all_views, std::max<size_t>(all_views.size(), 1)));
+        SWIRL_CUDA(dev_alloc(ctx, &d_all_ex, std::max<size_t>(all_ex.size(), 1)));
+        SWIRL_CUDA(dev_alloc(ctx, &d_all_items, std::max<size_t>(all_items.size(), 1)));
+        SWIRL_CUDA(dev_alloc(ctx, &d_eq_ub, views.size() * 4));
+        SWIRL_CUDA(dev_alloc(ctx, &d_row_idx, views.size()));
+        SWIRL_CUDA(dev_alloc(ctx, &d_n_lift, views.size()));
+        to_free.push_back(d_all_views);
+        to_free.push_back(d_all_ex);
+        to_free.push_back(d_all_items);
+        to_free.push_back(d_eq_ub);
+        to_free.push_back(d_row_idx);
+        to_free.push_back(d_n_lift);
+        {
+            std::vector<uint32_t> ones(views.size() * 4, 0), rows(views.size());
+            std::vector<int> lifts(views.size());
+            for (size_t i = 0; i < views.size(); i++) {
+                ones[4 * i] = bb::R1;
+                SWIRL_REQUIRE(views[i].row_idx < (size_t(1) << 32), "row index");
+                rows[i] = (uint32_t)views[i].row_idx;
+                lifts[i] = tabs[views[i].log_height].n_lift;
+            }
+            SWIRL_CUDA(cudaMemcpyAsync(d_eq_ub, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            SWIRL_CUDA(cudaMemcpyAsync(d_row_idx, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            SWIRL_CUDA(cudaMemcpyAsync(d_n_lift, lifts.data(), lifts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            if (!all_views.empty())
+                SWIRL_CUDA(cudaMemcpyAsync(d_all_views, all_views.data(), all_views.size() * sizeof(MleView), cudaMemcpyHostToDevice, ctx->stream));
+            if (!all_ex.empty())
+                SWIRL_CUDA(cudaMemcpyAsync(d_all_ex, all_ex.data(), all_ex.size() * sizeof(MleView), cudaMemcpyHostToDevice, ctx->stream));
+            if (!all_items.empty())
+                SWIRL_CUDA(cudaMemcpyAsync(d_all_items, all_items.data(), all_items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
+            if (!all_jobs.empty()) {
+                SWIRL_CUDA(cudaMemcpyAsync(d_all_jobs, all_jobs.data(), all_jobs.size() * sizeof(SrFoldJob), cudaMemcpyHostToDevice, ctx->stream));
+                SWIRL_CUDA(cudaMemcpyAsync(d_all_block_job, all_block_job.data(), all_block_job.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                           ctx->stream));
+            }
+        }
+        std::vector<uint32_t> seqs(n_stack + 2, 0);
+        std::vector<char> waits(n_stack + 2, 0);
+        // evaluation kernels of a round, then the kernels that consume its challenge: the first of them takes it from the
+        // mailbox, the others from its relay
+        auto launch_round = [&](int round) -> int {
+            const SrRound& R = plan[round];
+            const RoundLink pub = link_make(rs, true);
+            seqs[round] = pub.seq;
+            const uint32_t tag = link_result_tag(pub.seq);
+            if (R.n_items) {
+                SWIRL_REQUIRE(R.n_items <= (size_t)rs->max_blocks, "too many work items for the reduction scratch");
+                sr_mle_round_kernel<<<(unsigned)R.n_items, SR_BLOCK, 0, ctx->stream>>>(d_all_views + R.v_off, d_all_items + R.i_off, y_per_block,
+                                                                                    rs->d_partials, rs->d_ticket, rs->d_result, tag);
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+            if (R.n_ex) {
+                const unsigned grid = (unsigned)std::min<size_t>((R.n_ex + SR_BLOCK - 1) / SR_BLOCK, 1024);
+                sr_mle_exhausted_kernel<<<grid, SR_BLOCK, 0, ctx->stream>>>(d_all_ex + R.x_off, R.n_ex, rs->d_partials, rs->d_ticket,
+                                                                         rs->d_result + 8, d_eq_ub, tag);
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+            // the one kernel that waits for this round's challenge: last launch of the round
+            if (R.n_jobs) {
+                sr_fold_multi_kernel<<<(unsigned)R.n_blocks, SR_BLOCK, 0, ctx->stream>>>(d_all_jobs + R.j_off, d_all_block_job + R.b_off, d_eq_ub,
+                                                                                      d_n_lift, d_row_idx, round, l_skip, pub);
+                SWIRL_LAUNCH_CHECK(ctx);
+                waits[round] = 1;
+            }
+            // host mirror of the state the plan simulated
+            if (qh > 1) {
+                qcur ^= 1;
+                qh >>= 1;
+            }
+            for (auto& kv : tabs) {
+                HtTab& t = kv.second;
+                if (t.len <= 1) continue;
+                t.cur ^= 1;
+                t.len /= 2;
+            }
+            return 0;
+        };
+        LinkAbortGuard guard{ctx, rs};
+        link_begin(ctx, rs, 0, 16);
+        guard.armed = true;
+        SWIRL_TRY(launch_round(1));
+        for (int round = 1; round <= n_stack; round++) {
+            const SrRound& R = plan[round];
+            uint32_t w16[16] = {0};
+            if (R.n_items && R.n_ex)
+                SWIRL_TRY(link_recv(ctx, rs, seqs[round], 0, 8, 2, 8, w16));
+            else if (R.n_items)
+                SWIRL_TRY(link_recv(ctx, rs, seqs[round], 0, 8, w16));
+            else
+                SWIRL_TRY(link_recv(ctx, rs, seqs[round], 8, 8, w16 + 8));
+            const Ext s1 = ext_add(hp::from_words(w16), hp::from_words(w16 + 8));
+            const Ext s2 = ext_add(hp::from_words(w16 + 4), hp::from_words(w16 + 12));
+            tr.observe_ext(s1);
+            tr.observe_ext(s2);
+            memcpy(p_out, s1.c, 16);
+            memcpy(p_out + 4, s2.c, 16);
+            p_out += 8;
+            const Ext u_round = tr.sample_ext();
+            u_vec.push_back(u_round);
+            // the two result groups are not written by every round (no work items late, no exhausted views early)
+            link_expect(rs, 0, 16, seqs[round] + 1);
+            if (waits[round]) link_send(rs, seqs[round], u_round);
+            if (round < n_stack) SWIRL_TRY(launch_round(round + 1));
+        }
+        guard.armed = false;
+    } else
     for (int round = 1; round <= n_stack; round++) {
         hviews.clear();
         hex.clear();
@@ -611,13 +839,14 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
             SWIRL_CUDA(cudaMemcpyAsync(d_views, hviews.data(), hviews.size() * sizeof(MleView), cudaMemcpyHostToDevice, ctx->stream));
             SWIRL_CUDA(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, ctx->stream));
             sr_mle_round_kernel<<<(unsigned)items.size(), SR_BLOCK, 0, ctx->stream>>>(d_views, d_items, y_per_block, rs->d_partials,
-                                                                                   rs->d_ticket, rs->d_result);
+                                                                                   rs->d_ticket, rs->d_result, 0u);
             SWIRL_LAUNCH_CHECK(ctx);
         }
         if (!hex.empty()) {
             SWIRL_CUDA(cudaMemcpyAsync(d_ex, hex.data(), hex.size() * sizeof(MleView), cudaMemcpyHostToDevice, ctx->stream));
             const unsigned grid = (unsigned)std::min<size_t>((hex.size() + SR_BLOCK - 1) / SR_BLOCK, 1024);
-            sr_mle_exhausted_kernel<<<grid, SR_BLOCK, 0, ctx->stream>>>(d_ex, hex.size(), rs->d_partials, rs->d_ticket, rs->d_result + 8);
+            sr_mle_exhausted_kernel<<<grid, SR_BLOCK, 0, ctx->stream>>>(d_ex, hex.size(), rs->d_partials, rs->d_ticket, rs->d_result + 8,
+                                                                         nullptr, 0u);
             SWIRL_LAUNCH_CHECK(ctx);
         }
         SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
@@ -641,7 +870,7 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
             for (size_t ci = 0; ci < n_commits; ci++) {
                 const size_t n_out = pcs[ci]->layout.width * (qh / 2);
                 ef_fold_flat_kernel<<<(unsigned)((n_out + SR_BLOCK - 1) / SR_BLOCK), SR_BLOCK, 0, ctx->stream>>>(
-                    qe[qcur][ci], qe[qcur ^ 1][ci], n_out, u_round);
+                    qe[qcur][ci], qe[qcur ^ 1][ci], n_out, u_round, RoundLink{});
                 SWIRL_LAUNCH_CHECK(ctx);
             }
             qcur ^= 1;
@@ -652,9 +881,9 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
             if (t.len <= 1) continue;
             const size_t n_out = t.len / 2;
             ef_fold_flat_kernel<<<(unsigned)((n_out + SR_BLOCK - 1) / SR_BLOCK), SR_BLOCK, 0, ctx->stream>>>(t.eq[t.cur], t.eq[t.cur ^ 1],
-                                                                                                         n_out, u_round);
+                                                                                                         n_out, u_round, RoundLink{});
             ef_fold_flat_kernel<<<(unsigned)((n_out + SR_BLOCK - 1) / SR_BLOCK), SR_BLOCK, 0, ctx->stream>>>(
-                t.krot[t.cur], t.krot[t.cur ^ 1], n_out, u_round);
+                t.krot[t.cur], t.krot[t.cur ^ 1], n_out, u_round, RoundLink{});
             ctx->launches++;
             SWIRL_LAUNCH_CHECK(ctx);
             t.cur ^= 1;
@@ -670,11 +899,17 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
     }
     swirl::trace_mark(ctx, "sr", "mle rounds", &t_prev);
     // ---- stacking openings ------------------------------------------------------------------------
+    if (linked) SWIRL_CUDA(link_flag_fetch(ctx, rs));
     for (size_t ci = 0; ci < n_commits; ci++) {
         const size_t W = pcs[ci]->layout.width;
         SWIRL_REQUIRE(qh == 1, "internal: q_evals not fully folded");
         SWIRL_CUDA(cudaMemcpyAsync(p_out, qe[qcur][ci], W * 16, cudaMemcpyDeviceToHost, ctx->stream));
         SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+        if (linked && link_aborted(rs)) {
+            set_error("round link: a fold kernel gave up waiting for its challenge");
+            cleanup();
+            return SWIRL_ERR_INVALID;
+        }
         for (size_t j = 0; j < W; j++) tr.observe_ext(hp::from_words(p_out + 4 * j));
         p_out += 4 * W;
     }

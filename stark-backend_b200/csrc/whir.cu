@@ -421,7 +421,13 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             SWIRL_TRY(merkle_commit(ctx, g_codeword, N, 4, k, g_layers));
             uint32_t* root = sec_commits + 8 * wr;
             SWIRL_CUDA(cudaMemcpyAsync(root, g_layers + (2 * S - 2) * 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+            if (linked) SWIRL_CUDA(link_flag_fetch(ctx, rs));
             SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+            if (linked && link_aborted(rs)) {
+                set_error("round link: the fold kernel gave up waiting for its challenge");
+                rc = SWIRL_ERR_INVALID;
+                break;
+            }
             tr.observe_digest(root);
             z0 = tr.sample_ext();
             Ext zp = z0;
@@ -440,7 +446,13 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
             // final polynomial: coefficients to the host (interleave the 4 coordinate columns)
             std::vector<uint32_t> cols(n * 4);
             SWIRL_CUDA(cudaMemcpyAsync(cols.data(), soa, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+            if (linked) SWIRL_CUDA(link_flag_fetch(ctx, rs));
             SWIRL_CUDA(swirl::stream_sync(ctx, __FILE__, __LINE__));
+            if (linked && link_aborted(rs)) {
+                set_error("round link: the fold kernel gave up waiting for its challenge");
+                rc = SWIRL_ERR_INVALID;
+                break;
+            }
             for (size_t i = 0; i < n; i++) {
                 for (int c = 0; c < 4; c++) sec_final[4 * i + c] = cols[c * n + i];
                 tr.observe_ext(Ext{{sec_final[4 * i], sec_final[4 * i + 1], sec_final[4 * i + 2], sec_final[4 * i + 3]}});
