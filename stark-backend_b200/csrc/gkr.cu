@@ -208,9 +208,11 @@ __global__ void __launch_bounds__(GKR_BLOCK, (FOLD || RUNS) ? 3 : 4) gkr_round_k
     grid_sum<8>(v, a.partials, a.ticket, a.result, link_result_tag(a.link.seq));
 }
 
-static int round_grid(const swirl_ctx* ctx, size_t work_items) {
+// `per_sm` = resident blocks per SM of the variant launched (its __launch_bounds__): a grid-stride sweep over more
+// blocks than fit at once runs a second, mostly empty wave
+static int round_grid(const swirl_ctx* ctx, size_t work_items, int per_sm = 4) {
     size_t blocks = (work_items + GKR_BLOCK - 1) / GKR_BLOCK;
-    const size_t cap = (size_t)ctx->sm_count * 4;
+    const size_t cap = (size_t)ctx->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     return blocks ? (int)blocks : 1;
 }
@@ -440,7 +442,7 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
             auto set_runs = [&]() {  // runs of >= 2^10 pairs, at least four per block of the grid; otherwise the plain sweep
                 a.g_bits = 0;
                 if (a.a_bits < 10) return;
-                const size_t want = (size_t)4 * round_grid(ctx, a.ny);
+                const size_t want = (size_t)4 * round_grid(ctx, a.ny, 3);
                 int gb = a.a_bits;
                 while (gb > 10 && (a.ny >> gb) < want) gb--;
                 if ((a.ny >> gb) >= want) a.g_bits = gb;
@@ -452,7 +454,7 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
                     a.ny = y_tail = (rows_tree + 1) / 2;
                     set_runs();
                     if (a.g_bits)
-                        gkr_round_kernel<true, false, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                        gkr_round_kernel<true, false, true><<<round_grid(ctx, a.ny, 3), GKR_BLOCK, 0, ctx->stream>>>(a);
                     else
                         gkr_round_kernel<true, false, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
                 } else if (sr == 1) {
@@ -462,9 +464,9 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
                     a.out = tab[0];
                     a.out_stride = tab_stride[0];
                     if (a.g_bits)
-                        gkr_round_kernel<true, true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                        gkr_round_kernel<true, true, true><<<round_grid(ctx, a.ny, 3), GKR_BLOCK, 0, ctx->stream>>>(a);
                     else
-                        gkr_round_kernel<true, true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                        gkr_round_kernel<true, true, false><<<round_grid(ctx, a.ny, 3), GKR_BLOCK, 0, ctx->stream>>>(a);
                     rows = 2 * a.ny;
                     cur = 0;
                 } else {
@@ -476,9 +478,9 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
                     a.out = tab[cur ^ 1];
                     a.out_stride = tab_stride[cur ^ 1];
                     if (a.g_bits)
-                        gkr_round_kernel<false, true, true><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                        gkr_round_kernel<false, true, true><<<round_grid(ctx, a.ny, 3), GKR_BLOCK, 0, ctx->stream>>>(a);
                     else
-                        gkr_round_kernel<false, true, false><<<round_grid(ctx, a.ny), GKR_BLOCK, 0, ctx->stream>>>(a);
+                        gkr_round_kernel<false, true, false><<<round_grid(ctx, a.ny, 3), GKR_BLOCK, 0, ctx->stream>>>(a);
                     rows = 2 * a.ny;
                     cur ^= 1;
                 }

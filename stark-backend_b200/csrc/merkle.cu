@@ -11,8 +11,8 @@
 // Layout: a CTA owns `yb` consecutive query indices y and all 2^k rows {y + t*S} of each
 // (S = query stride).  Thread (t, y) walks its row across the columns, 8 columns per sponge
 // block; neighbouring threads read neighbouring rows of one column => every load instruction is a
-// fully coalesced 128-byte line.  The next 8 columns are fetched while the current permutation
-// runs.  The 2^k digests of a query are then folded in shared memory (word-major, conflict-free)
+// fully coalesced 128-byte line.  The next 8 columns are prefetched (L1/L2, no registers) while the
+// current permutation runs.  The 2^k digests of a query are then folded in shared memory (word-major, conflict-free)
 // with the active threads packed into whole warps.  The upper tree is built 9 levels per launch.
 #include "kernels.cuh"
 #include "poseidon2.cuh"
@@ -48,19 +48,18 @@ __device__ __forceinline__ void hash_row_into(uint32_t s[16], const uint32_t* __
     const bool live = row < height;  // rows past the matrix hash as zeros
     const uint32_t* p = matrix + (live ? row : 0);
     const uint32_t nfull = width >> 3, tail = width & 7;
-    uint32_t nxt[8];
-    if (nfull) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) nxt[i] = live ? __ldg(p + (size_t)i * height) : 0u;
-    }
+    // No register double buffer: the next block's lines are requested into L1/L2 while this permutation runs and the state
+    // words are loaded right before they are used.  That keeps the kernel at 48 registers = 5 CTAs per SM, where the row
+    // sponge runs at the permutation's isolated rate (4.20 Gperm/s; 4.02 with eight prefetch registers and 4 CTAs/SM:
+    // profiles/r2x_leaf_occupancy.jsonl).
     for (uint32_t c = 0; c < nfull; c++) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = nxt[i];
+        const uint32_t* q = p + (size_t)c * 8 * height;
         if (c + 1 < nfull) {
-            const uint32_t* q = p + (size_t)(c + 1) * 8 * height;
 #pragma unroll
-            for (int i = 0; i < 8; i++) nxt[i] = live ? __ldg(q + (size_t)i * height) : 0u;
+            for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + (size_t)(8 + i) * height));
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = live ? __ldg(q + (size_t)i * height) : 0u;
         p2::permute(s);
     }
     if (tail) {
@@ -73,7 +72,7 @@ __device__ __forceinline__ void hash_row_into(uint32_t s[16], const uint32_t* __
 }
 
 // blockDim.x = yb << log_rpq (<= MK_BLOCK); grid.x = S / yb.
-__global__ void __launch_bounds__(MK_BLOCK)
+__global__ void __launch_bounds__(MK_BLOCK, 5)
 leaf_tree_kernel(const uint32_t* __restrict__ matrix, size_t height, uint32_t width, size_t S, int log_rpq,
                  int log_yb, uint32_t* __restrict__ layer0, const uint32_t* __restrict__ state_in,
                  uint32_t* __restrict__ state_out) {
