@@ -109,7 +109,15 @@ static int ctx_init(int device, cudaStream_t stream, bool owns, swirl_ctx** out)
     ctx->device = device;
     ctx->stream = stream;
     ctx->owns_stream = owns;
-    if (const char* env = getenv("SWIRL_ROUND_LINK")) ctx->round_link = atoi(env) != 0;  // A/B knob, see swirl_ctx_set_round_link
+    // The round link needs asynchronous launches (ext.cuh).  Tools that serialise them announce themselves in the
+    // environment of the process they start: Nsight Compute, Nsight Systems' CUDA injection, compute-sanitizer; a profiler
+    // that only instruments SOME kernels (ncu -k / --launch-skip) would get past the start-up probe of sponge.cu.
+    for (const char* marker : {"NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE", "NV_SANITIZER_INJECTION_TRANSPORT_TYPE",
+                               "CUDA_INJECTION64_PATH"})
+        if (getenv(marker)) ctx->round_link = ctx->round_link_ok = false;
+    if (const char* env = getenv("CUDA_LAUNCH_BLOCKING"))
+        if (atoi(env) != 0) ctx->round_link = ctx->round_link_ok = false;
+    if (const char* env = getenv("SWIRL_ROUND_LINK")) ctx->round_link = atoi(env) != 0 && ctx->round_link_ok;  // A/B knob, see swirl_ctx_set_round_link
     if (owns) {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
