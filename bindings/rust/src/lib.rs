@@ -285,6 +285,23 @@ impl B200Device {
     pub fn set_cache_rs_code_matrix(&self, on: bool) -> Result<(), B200Error> {
         check(unsafe { swirl_ctx_set_cache_rs_code_matrix(self.ctx.0, on as i32) })
     }
+    /// Run-time compiled per-AIR round-0 kernels: 0 = interpreter only, 1 = tall traces (default), 2 = always.
+    pub fn set_jit(&self, mode: i32) -> Result<(), B200Error> {
+        check(unsafe { swirl_ctx_set_jit(self.ctx.0, mode) })
+    }
+    /// Sumcheck rounds through the mapped mailbox (default) or one launch + stream synchronisation per round, the
+    /// reference's pattern (logup_zerocheck/fractional.rs:649-).  Same proof either way; the library turns it off by
+    /// itself under a profiler or sanitizer.
+    pub fn set_round_link(&self, on: bool) -> Result<(), B200Error> {
+        check(unsafe { swirl_ctx_set_round_link(self.ctx.0, on as i32) })
+    }
+    /// (stream synchronisations, rounds received through the mailbox) since the context was created.
+    pub fn sync_stats(&self) -> Result<(u64, u64), B200Error> {
+        let (mut syncs, mut ms, mut links) = (0u64, 0f64, 0u64);
+        check(unsafe { swirl_ctx_sync_stats(self.ctx.0, &mut syncs, &mut ms) })?;
+        check(unsafe { swirl_ctx_link_stats(self.ctx.0, &mut links) })?;
+        Ok((syncs, links))
+    }
     fn pcs_params(&self) -> SwirlPcsParams {
         SwirlPcsParams {
             l_skip: self.params.l_skip as i32,

@@ -176,6 +176,22 @@ inline void dev_free(swirl_ctx* ctx, T* p) {
     if (p) arena_free_block(ctx, (void*)p);
 }
 
+// Scratch blocks of one library call: handed back to the arena when the call returns, on every path.
+struct ArenaGuard {
+    swirl_ctx* ctx;
+    std::vector<void*> blocks;
+    explicit ArenaGuard(swirl_ctx* c) : ctx(c) {}
+    ArenaGuard(const ArenaGuard&) = delete;
+    ArenaGuard& operator=(const ArenaGuard&) = delete;
+    template <class T>
+    void add(T* p) {
+        if (p) blocks.push_back((void*)p);
+    }
+    ~ArenaGuard() {
+        for (void* p : blocks) arena_free_block(ctx, p);
+    }
+};
+
 inline int ilog2(size_t n) {
     int l = 0;
     while ((size_t(1) << l) < n) l++;

@@ -270,7 +270,9 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
         tree_nodes += round_up4(S[k]);  // keeps every layer segment 128-byte aligned
     }
     uint32_t* tree = nullptr;
+    ArenaGuard scratch(ctx);  // tree, eq tables, working tables: released on every return path
     SWIRL_CUDA(dev_alloc(ctx, &tree, tree_nodes * 8));
+    scratch.add(tree);
     auto layer_ptr = [&](int k) -> const uint32_t* { return k == n ? d_leaves : tree + off[k] * 8; };
     for (int k = n - 1; k >= 0; k--) {
         frac_tree_layer_kernel<<<(unsigned)((S[k] + GKR_BLOCK - 1) / GKR_BLOCK), GKR_BLOCK, 0, ctx->stream>>>(
@@ -294,7 +296,6 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
     if (assert_zero) {
         if (root_p.c[0] | root_p.c[1] | root_p.c[2] | root_p.c[3]) {
             set_error("LogupZerocheckError::NonZeroRootSum");
-            dev_free(ctx, tree);
             return SWIRL_ERR_NONZERO_ROOT_SUM;
         }
     } else {
@@ -311,12 +312,16 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
     size_t tab_stride[2] = {1, 1};
     if (n >= 2) {
         SWIRL_CUDA(dev_alloc(ctx, &eqA, (size_t(8) << 14)));  // suffix tables of <= 13 variables: < 2^14 EF
+        scratch.add(eqA);
         SWIRL_CUDA(dev_alloc(ctx, &eqB, (size_t(8) << 14)));
+        scratch.add(eqB);
         const size_t rows_max = (S[n] + 1) / 2;                // stored rows of the largest layer table
         tab_stride[0] = 2 * ((rows_max + 3) / 4);              // rows written by the first fold
         tab_stride[1] = 2 * ((tab_stride[0] + 3) / 4);
         SWIRL_CUDA(dev_alloc(ctx, &tab[0], 4 * tab_stride[0] * 4));
+        scratch.add(tab[0]);
         SWIRL_CUDA(dev_alloc(ctx, &tab[1], 4 * tab_stride[1] * 4));
+        scratch.add(tab[1]);
     }
     const Ext one = bb::ext_one();
     const uint32_t inv2 = bb::inv(bb::mont(2)), inv6 = bb::inv(bb::mont(6));
@@ -570,11 +575,6 @@ extern "C" int swirl_gkr_fractional_sumcheck_padded(swirl_ctx* ctx, swirl_transc
         poly_off += round;
     }
     for (int b = 0; b < n; b++) memcpy(h_xi + 4 * b, xi_prev[b].c, 16);
-    dev_free(ctx, tree);
-    dev_free(ctx, eqA);
-    dev_free(ctx, eqB);
-    dev_free(ctx, tab[0]);
-    dev_free(ctx, tab[1]);
     return rc;
 }
 

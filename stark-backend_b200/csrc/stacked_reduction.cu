@@ -407,10 +407,16 @@ extern "C" int swirl_stacked_reduction(swirl_ctx* ctx, swirl_transcript* ts, con
 
     // ---- eq tables per height class -----------------------------------------------------------------
     std::map<int, HtTab> tabs;
-    std::vector<void*> to_free;
-    auto cleanup = [&]() {
-        for (void* p : to_free) arena_free_block(ctx, p);
-    };
+    std::vector<void*> to_free;  // released when the call returns, on every path (declared before the link guard below, so a
+                                 // pending round is aborted and the stream drained first)
+    struct Cleanup {
+        swirl_ctx* ctx;
+        std::vector<void*>& v;
+        ~Cleanup() {
+            for (void* p : v) arena_free_block(ctx, p);
+        }
+    } cleanup_guard{ctx, to_free};
+    auto cleanup = []() {};
     for (const View& v : views) {
         if (tabs.count(v.log_height)) continue;
         HtTab t;
