@@ -288,16 +288,21 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
         const size_t wds = (size_t)cfg->num_queries[r] * ((size_t(4) << k) + (size_t)(m + log_blowup - r - k) * 8);
         open_words = wds > open_words ? wds : open_words;
     }
-    SWIRL_CUDA(dev_alloc(ctx, &d_mu, total_w * 4));
-    SWIRL_CUDA(dev_alloc(ctx, &soa, H * 4));
-    SWIRL_CUDA(dev_alloc(ctx, &f[0], H * 4));
-    SWIRL_CUDA(dev_alloc(ctx, &f[1], H * 2));
-    SWIRL_CUDA(dev_alloc(ctx, &w[0], H * 4));
-    SWIRL_CUDA(dev_alloc(ctx, &w[1], H * 2));
-    SWIRL_CUDA(dev_alloc(ctx, &d_idx, (size_t)max_q + 1));
-    SWIRL_CUDA(dev_alloc(ctx, &d_zs, (size_t)max_q + 1));
-    SWIRL_CUDA(dev_alloc(ctx, &d_gam, ((size_t)max_q + 1) * 4));
-    SWIRL_CUDA(dev_alloc(ctx, &d_open, open_words + 4));
+    ArenaGuard scratch(ctx);  // the tables that live for the whole call: released on every return path
+#define WH_ALLOC(ptr, count)                          \
+    SWIRL_CUDA(dev_alloc(ctx, &(ptr), (count)));      \
+    scratch.add(ptr)
+    WH_ALLOC(d_mu, total_w * 4);
+    WH_ALLOC(soa, H * 4);
+    WH_ALLOC(f[0], H * 4);
+    WH_ALLOC(f[1], H * 2);
+    WH_ALLOC(w[0], H * 4);
+    WH_ALLOC(w[1], H * 2);
+    WH_ALLOC(d_idx, (size_t)max_q + 1);
+    WH_ALLOC(d_zs, (size_t)max_q + 1);
+    WH_ALLOC(d_gam, ((size_t)max_q + 1) * 4);
+    WH_ALLOC(d_open, open_words + 4);
+#undef WH_ALLOC
     SWIRL_CUDA(cudaMemcpyAsync(d_mu, mu_pows.data(), total_w * 16, cudaMemcpyHostToDevice, ctx->stream));
     {
         size_t off = 0;
@@ -538,17 +543,7 @@ extern "C" int swirl_whir_open(swirl_ctx* ctx, swirl_transcript* ts, const swirl
         m -= k;
         log_rs -= 1;
     }
-    dev_free(ctx, rs_codeword);
+    dev_free(ctx, rs_codeword);  // the per-round codeword / digest layers rotate and are released as they are replaced
     dev_free(ctx, rs_layers);
-    dev_free(ctx, d_mu);
-    dev_free(ctx, soa);
-    dev_free(ctx, f[0]);
-    dev_free(ctx, f[1]);
-    dev_free(ctx, w[0]);
-    dev_free(ctx, w[1]);
-    dev_free(ctx, d_idx);
-    dev_free(ctx, d_zs);
-    dev_free(ctx, d_gam);
-    dev_free(ctx, d_open);
     return rc;
 }
