@@ -101,9 +101,9 @@ __device__ __forceinline__ bool grid_sum(uint32_t (&v)[NV], uint32_t* __restrict
 // launch + cudaStreamSynchronize per round that exchange costs ~10 us (tools/latency_bench.cu); a device-resident
 // sponge is no way out, because a lone Poseidon2 permutation takes 4.2 us on the GPU (0.86 us on the host).  So the
 // transcript stays on the host and the *launches and stream synchronisations* leave the critical path instead: the
-// kernels of all rounds of a sumcheck are enqueued up front; each one waits (block 0 polls the mapped mailbox, the
-// other blocks poll block 0's relay in device memory) for the challenge the host derives from the previous round,
-// and the host polls the round's result words in mapped memory.  (Starting the next kernel early with programmatic
+// kernels of a round are enqueued while the previous round still runs; the kernel that needs the previous round's
+// challenge waits for it on the device (block 0 polls the mapped mailbox, the other blocks poll block 0's relay in
+// device memory), and the host polls the round's result words in mapped memory.  (Starting the next kernel early with programmatic
 // dependent launch on top of this was measured and changes nothing: profiles/r2m_*.)
 // Every access that crosses PCIe is a full round trip (~1.5 us), so each direction is ONE transaction and carries its
 // own "ready" mark instead of a separate flag + fence: field words are < 2^31, their top bits are free.
@@ -113,8 +113,9 @@ __device__ __forceinline__ bool grid_sum(uint32_t (&v)[NV], uint32_t* __restrict
 //  * device -> host: the result words carry (seq & 1) in their top bit; the host waits until all of them do.
 // Sequence numbers are consecutive inside one sumcheck, so the previous content never looks ready.
 // Failure handling: a kernel that sees the abort mark, or waits ~2 s in vain (a dead host must not hang the GPU),
-// raises a sticky flag next to the relay and returns WITHOUT publishing; every later linked kernel returns at once,
-// the stream drains, and the host's link_recv reports the missing round instead of using a made-up challenge.
+// raises a sticky flag next to the relay and returns WITHOUT publishing or folding; every later waiting kernel returns
+// at once, the stream drains, and the host reports the missing round (link_recv) or the raised flag (link_aborted)
+// instead of using a made-up challenge.
 // Rule for the host: NO CUDA call while an enqueued kernel may be waiting for a mail that has not been sent.  Another
 // thread's device-synchronising call (cudaFree, a context being destroyed, a module being loaded) holds the driver's lock
 // until all enqueued work has finished; a launch of ours queued behind that lock, with a kernel of ours waiting for us,
