@@ -98,6 +98,8 @@ extern "C" {
     pub fn swirl_stacked_reduction(ctx: *mut SwirlCtx, ts: *mut SwirlTranscript, pcs: *const *const SwirlPcs, n_commits: usize, need_rot: *const *const u8, h_r: *const u32, r_len: usize, h_proof: *mut u32, proof_words: usize, h_u: *mut u32) -> c_int;
     pub fn swirl_ctx_set_jit(ctx: *mut SwirlCtx, mode: c_int) -> c_int;
     pub fn swirl_jit_round0_source(air: *const SwirlAirCtx, which: c_int, out: *mut std::ffi::c_char, cap: usize) -> usize;
+    pub fn swirl_ctx_jit_stats(ctx: *mut SwirlCtx, out: *mut u64) -> c_int;
+    pub fn swirl_jit_mle_source(air: *const SwirlAirCtx, max_constraint_degree: c_int, n_airs: usize, out: *mut std::ffi::c_char, cap: usize) -> usize;
     pub fn swirl_batch_constraints_proof_words(l_skip: c_int, max_constraint_degree: c_int, airs: *const SwirlAirCtx, n_airs: usize) -> usize;
     pub fn swirl_prove_batch_constraints(ctx: *mut SwirlCtx, ts: *mut SwirlTranscript, l_skip: c_int, max_constraint_degree: c_int, logup_pow_bits: c_int, airs: *const SwirlAirCtx, n_airs: usize, h_proof: *mut u32, proof_words: usize, h_r: *mut u32) -> c_int;
     pub fn swirl_prove_openings(ctx: *mut SwirlCtx, ts: *mut SwirlTranscript, cfg: *const SwirlWhirConfig, pcs: *const *const SwirlPcs, n_commits: usize, need_rot: *const *const u8, h_r: *const u32, r_len: usize, h_stacking_proof: *mut u32, stacking_words: usize, h_whir_proof: *mut u32, whir_words: usize) -> c_int;

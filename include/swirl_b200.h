@@ -362,9 +362,18 @@ int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* ts, int l_sk
  * words).  This returns that source for inspection (which = 0: constraint roots, 1: interaction roots); host only, the
  * matrices of `air` need only their shapes.  Returns the source length; copies at most cap - 1 characters into out.
  * Reference counterpart: the rule compiler + interpreter, cuda-backend/src/logup_zerocheck/rules/mod.rs:27-130. */
-/* 0 = interpreter only, 1 = compile the programs of tall traces (default), 2 = compile every program (tests). */
+/* mode & 3: 0 = interpreter only, 1 = compile the programs of tall traces (default), 2 = compile every program (tests).
+ * mode & 4: the MLE rounds run compiled kernels as well (one kernel per AIR: a switch over its sub-programs, value slots
+ * as D extension-field lanes in registers); also selected by SWIRL_JIT_MLE=1 in the environment. */
 int swirl_ctx_set_jit(swirl_ctx* ctx, int mode);
 size_t swirl_jit_round0_source(const swirl_air_ctx* air, int which, char* out, size_t cap);
+/* The MLE-round kernel of one AIR for max_constraint_degree D, as it would be compiled when `n_airs` AIRs share the proof
+ * (the number of sub-programs per AIR depends on it).  The sub-programs' instructions and their (case, column shift,
+ * weight shift) follow the kernel as comment lines.  Host only; returns 0 when the interpreter would be used. */
+size_t swirl_jit_mle_source(const swirl_air_ctx* air, int max_constraint_degree, size_t n_airs, char* out, size_t cap);
+/* out = {round-0 kernels compiled, round-0 launches of compiled kernels, MLE-round kernels compiled, MLE-round launches of
+ * compiled kernels} since the context was created: tells a caller (and the tests) which path really ran. */
+int swirl_ctx_jit_stats(swirl_ctx* ctx, uint64_t out[4]);
 
 /* ---- phase level: OpeningProver::prove_openings (hal.rs:118-138; cpu_backend.rs:139-220) =
  *      swirl_stacked_reduction, u_cube = (u_0^(2^i))_{i<l_skip} ++ u[1..], swirl_whir_open.

@@ -48,6 +48,17 @@ void orc_ef_mul(uint32_t out[4], const uint32_t a[4], const uint32_t b[4]) {
     EF z = x * y;
     memcpy(out, &z, 16);
 }
+// verifier/whir.rs:352-389 on n = 2^k values; pinned by the reference's fold_single / fold_double identities
+// (crates/backend-tests/src/lib.rs:1191-1227) in tests/test_whir.py
+void orc_binary_k_fold(uint32_t out[4], const uint32_t* values, int k, const uint32_t* alphas, uint32_t x) {
+    std::vector<EF> v(size_t(1) << k), al(k);
+    memcpy(v.data(), values, v.size() * 16);
+    memcpy(al.data(), alphas, al.size() * 16);
+    F fx;
+    memcpy(&fx, &x, 4);
+    const EF z = binary_k_fold(v, al, fx);
+    memcpy(out, &z, 16);
+}
 void orc_ef_inv(uint32_t out[4], const uint32_t a[4]) {
     EF x;
     memcpy(&x, a, 16);

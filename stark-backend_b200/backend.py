@@ -475,8 +475,15 @@ class B200Device:
         check(self.lib.swirl_ctx_set_cache_rs_code_matrix(self.ctx, 1 if on else 0))
 
     def set_jit(self, mode):
-        """Run-time compiled per-AIR constraint kernels: 0 = interpreter only, 1 = tall traces (default), 2 = always."""
+        """Run-time compiled per-AIR constraint kernels: 0 = interpreter only, 1 = tall traces (default), 2 = always;
+        + 4 = the MLE rounds run compiled kernels as well."""
         check(self.lib.swirl_ctx_set_jit(self.ctx, int(mode)))
+
+    def jit_stats(self):
+        """{r0_compiled, r0_launches, mle_compiled, mle_launches} of this context (swirl_ctx_jit_stats)."""
+        out = (C.c_uint64 * 4)()
+        check(self.lib.swirl_ctx_jit_stats(self.ctx, out))
+        return dict(zip(("r0_compiled", "r0_launches", "mle_compiled", "mle_launches"), (int(x) for x in out)))
 
     def mem_stats(self, reset_peak=False):
         """{live, peak, held, device_free} bytes of the context's scratch arena (traces handed in by the caller not counted)."""

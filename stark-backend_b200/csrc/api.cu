@@ -117,6 +117,7 @@ static int ctx_init(int device, cudaStream_t stream, bool owns, swirl_ctx** out)
         if (getenv(marker)) ctx->round_link = ctx->round_link_ok = false;
     if (const char* env = getenv("CUDA_LAUNCH_BLOCKING"))
         if (atoi(env) != 0) ctx->round_link = ctx->round_link_ok = false;
+    if (const char* env = getenv("SWIRL_JIT_MLE")) ctx->jit_mle = atoi(env) != 0;
     if (const char* env = getenv("SWIRL_ROUND_LINK")) ctx->round_link = atoi(env) != 0 && ctx->round_link_ok;  // A/B knob, see swirl_ctx_set_round_link
     if (owns) {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -199,8 +200,17 @@ int swirl_ctx_set_cache_rs_code_matrix(swirl_ctx* ctx, int on) {
 }
 
 int swirl_ctx_set_jit(swirl_ctx* ctx, int mode) {
-    SWIRL_REQUIRE(ctx && mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
-    ctx->jit_mode = mode;
+    SWIRL_REQUIRE(ctx && mode >= 0 && (mode & 3) <= 2 && mode < 8, "mode must be 0, 1 or 2, plus 4 for compiled MLE rounds");
+    ctx->jit_mode = mode & 3;
+    // SWIRL_JIT_MLE in the environment outranks the mode bit (A/B runs of unmodified callers); mode 0 is always the interpreter
+    if (const char* env = getenv("SWIRL_JIT_MLE")) ctx->jit_mle = atoi(env) != 0;
+    else ctx->jit_mle = (mode & 4) != 0;
+    return 0;
+}
+
+int swirl_ctx_jit_stats(swirl_ctx* ctx, uint64_t out[4]) {
+    SWIRL_REQUIRE(ctx && out, "null argument");
+    for (int i = 0; i < 4; i++) out[i] = ctx->jit_stats[i];
     return 0;
 }
 

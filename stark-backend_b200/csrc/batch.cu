@@ -557,6 +557,7 @@ struct MleArgs {
     uint32_t* partials;
     unsigned int* ticket;
     uint32_t* result;
+    uint32_t sub, col_shift, w_shift;  // run-time compiled kernels only: case of the generated switch, operand shifts
 };
 // every AIR with live tables folds in one launch: out[j] = lerp(in[2j], in[2j+1], r)
 struct FoldArgs {
@@ -785,6 +786,171 @@ static std::string generate_round0_source(const std::vector<Instr>& code, int n_
     return s;
 }
 
+// ---- host: an AIR's sub-programs -> ONE CUDA C++ kernel for the MLE rounds ------------------------------------------
+// The MLE rounds launch a descriptor per (AIR, sub-program).  The generated kernel is a switch over the sub-programs'
+// code ("cases"); sub-programs that are equal up to one constant shift of their global columns and one of their weight
+// indices -- the same 16 constraints on the next 16 columns -- share a case and carry the shifts in their descriptor.
+// Value slots are arrays of D extension-field lanes (csrc/jit_prelude.cuh, SW_D section).
+struct MleCaseRef {
+    int case_id = -1;
+    uint32_t col_shift = 0, w_shift = 0;
+};
+constexpr size_t JIT_MLE_MAX_STATEMENTS = 256;  // all cases together, after loop detection
+constexpr int JIT_MLE_MAX_LANE_SLOTS = 40;      // slots x D of one case: 4 registers each
+
+// y == ref with every global column (I_VAR / I_PREF: c) shifted by *dc and every weight index (I_ACC: b, I_MULACC: c) by *dw
+static bool mle_equal_up_to_shift(const std::vector<Instr>& ref, const std::vector<Instr>& y, uint32_t* dc, uint32_t* dw) {
+    if (ref.size() != y.size()) return false;
+    bool have_c = false, have_w = false;
+    *dc = *dw = 0;
+    auto shift = [](bool& have, uint32_t* d, uint32_t from, uint32_t to) {
+        const uint32_t delta = to - from;  // modulo 2^32, like the device's addition
+        if (!have) {
+            have = true;
+            *d = delta;
+        }
+        return *d == delta;
+    };
+    for (size_t i = 0; i < ref.size(); i++) {
+        const Instr &r = ref[i], &x = y[i];
+        if (r.op_dst != x.op_dst) return false;
+        switch (r.op_dst & 0xff) {
+            case I_VAR:
+            case I_PREF:  // part and column-in-part (a, b) are not read by the MLE rounds
+                if (!shift(have_c, dc, r.c, x.c)) return false;
+                break;
+            case I_ACC:
+                if (r.a != x.a || r.c != x.c || !shift(have_w, dw, r.b, x.b)) return false;
+                break;
+            case I_MULACC:
+                if (r.a != x.a || r.b != x.b || !shift(have_w, dw, r.c, x.c)) return false;
+                break;
+            case I_CONST:
+                if (r.a != x.a) return false;
+                break;
+            case I_NEG:
+                if (r.a != x.a) return false;
+                break;
+            default:
+                if (r.a != x.a || r.b != x.b) return false;
+        }
+    }
+    return true;
+}
+
+// `codes[i]` / `n_slots[i]`: sub-program i.  refs[i] = its case and shifts.  Returns "" when the kernel would be too
+// large to compile in seconds or a case needs more registers than a thread has (the interpreter runs instead).
+// With `listing`, every sub-program's instructions are appended as comment lines (tests replay them on the host).
+static std::string generate_mle_source(const std::vector<const std::vector<Instr>*>& codes, const std::vector<int>& n_slots, int D,
+                                       const char* name, std::vector<MleCaseRef>* refs, bool listing = false) {
+    refs->assign(codes.size(), MleCaseRef{});
+    std::vector<size_t> case_of;  // case -> representative sub-program
+    for (size_t i = 0; i < codes.size(); i++) {
+        for (size_t k = 0; k < case_of.size() && (*refs)[i].case_id < 0; k++) {
+            uint32_t dc, dw;
+            if (mle_equal_up_to_shift(*codes[case_of[k]], *codes[i], &dc, &dw)) (*refs)[i] = MleCaseRef{(int)k, dc, dw};
+        }
+        if ((*refs)[i].case_id < 0) {
+            (*refs)[i] = MleCaseRef{(int)case_of.size(), 0, 0};
+            case_of.push_back(i);
+        }
+    }
+    size_t statements = 0;
+    std::vector<std::vector<JitRun>> runs(case_of.size());
+    for (size_t k = 0; k < case_of.size(); k++) {
+        const std::vector<Instr>& code = *codes[case_of[k]];
+        if (n_slots[case_of[k]] * D > JIT_MLE_MAX_LANE_SLOTS) return std::string();
+        runs[k] = jit_find_runs(code);
+        size_t n = code.size();
+        for (const JitRun& r : runs[k]) n -= r.period * (r.reps - 1);
+        statements += n;
+    }
+    if (statements > JIT_MLE_MAX_STATEMENTS) return std::string();
+    std::string s;
+    s.reserve(statements * 96 + 32768);
+    s += "#define SW_LOAD_ATTR __device__ __noinline__\n#define SW_MIN_BLOCKS 1\n";  // the round-0 part of the prelude is not used
+    s += "#define SW_D " + std::to_string(D) + "\n#define SW_MLE_MIN_BLOCKS 4\n";
+    s += jit_prelude();
+    s += "\nSW_MLE_SIGNATURE(";
+    s += name;
+    s += ") {\nSW_MLE_PROLOGUE\n";
+    auto v = [](uint32_t slot) { return "s" + std::to_string(slot); };
+    auto opnd = [](uint32_t val, int64_t step) {
+        if (step == 0) return std::to_string(val) + "u";
+        return "(" + std::to_string(val) + "u + (uint32_t)(it * (" + std::to_string(step) + ")))";
+    };
+    auto emit = [&](const Instr& in, const std::array<int64_t, 3>& d) {
+        const uint32_t op = in.op_dst & 0xff, dst = in.op_dst >> 8;
+        switch (op) {
+            case I_VAR: s += "LDV(" + v(dst) + ", " + opnd(in.c, d[2]) + ")\n"; break;
+            case I_PREF: s += "PFV(" + opnd(in.c, d[2]) + ")\n"; break;
+            case I_CONST: s += "CST(" + v(dst) + ", " + std::to_string(in.a) + "u)\n"; break;
+            case I_ADD: s += "ADD(" + v(dst) + ", " + v(in.a) + ", " + v(in.b) + ")\n"; break;
+            case I_SUB: s += "SUB(" + v(dst) + ", " + v(in.a) + ", " + v(in.b) + ")\n"; break;
+            case I_MUL: s += "MUL(" + v(dst) + ", " + v(in.a) + ", " + v(in.b) + ")\n"; break;
+            case I_NEG: s += "NEG(" + v(dst) + ", " + v(in.a) + ")\n"; break;
+            case I_MULACC: s += "MACV(" + std::to_string(dst) + ", " + opnd(in.c, d[2]) + ", " + v(in.a) + ", " + v(in.b) + ")\n"; break;
+            default: s += "ACCV(" + std::to_string(in.a) + ", " + opnd(in.b, d[1]) + ", " + v(in.c) + ")\n";  // I_ACC
+        }
+    };
+    const std::array<int64_t, 3> zero{0, 0, 0};
+    for (size_t k = 0; k < case_of.size(); k++) {
+        const std::vector<Instr>& code = *codes[case_of[k]];
+        s += "case " + std::to_string(k) + ": {\n";
+        for (int i = 0; i < n_slots[case_of[k]]; i++) s += "SLOT(" + v((uint32_t)i) + ")\n";
+        size_t ri = 0;
+        for (size_t i = 0; i < code.size();) {
+            if (ri < runs[k].size() && runs[k][ri].start == i) {
+                const JitRun& r = runs[k][ri++];
+                s += "#pragma unroll 1\nfor (int it = 0; it < " + std::to_string(r.reps) + "; it++) {\n";
+                for (size_t j = 0; j < r.period; j++) emit(code[i + j], r.delta[j]);
+                s += "}\n";
+                i += r.period * r.reps;
+            } else {
+                emit(code[i], zero);
+                i++;
+            }
+        }
+        s += "} break;\n";
+    }
+    s += "SW_MLE_EPILOGUE\n}\n";
+    if (listing) {
+        for (size_t i = 0; i < codes.size(); i++) {
+            s += "// SUB " + std::to_string(i) + " case " + std::to_string((*refs)[i].case_id) + " col_shift " + std::to_string((*refs)[i].col_shift) +
+                 " w_shift " + std::to_string((*refs)[i].w_shift) + " n_slots " + std::to_string(n_slots[i]) + "\n";
+            for (const Instr& in : *codes[i])
+                s += "// I " + std::to_string(i) + " " + std::to_string(in.op_dst & 0xff) + " " + std::to_string(in.op_dst >> 8) + " " +
+                     std::to_string(in.a) + " " + std::to_string(in.b) + " " + std::to_string(in.c) + "\n";
+        }
+    }
+    return s;
+}
+
+// the sub-programs of an AIR: K chunks shared between constraint roots and interaction roots in proportion to their
+// counts, at least one per non-empty class (never mixed: the zerocheck part of round 0 is needed on one coset fewer than
+// the LogUp part, cpu.rs:338-361 vs :405-409)
+struct ChunkRange {
+    size_t r0, r1;
+    bool zerocheck;
+};
+static std::vector<ChunkRange> chunk_ranges(size_t nc, size_t n_roots, size_t n_airs) {
+    std::vector<ChunkRange> out;
+    const size_t k_max = std::max<size_t>(2, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
+    const size_t K = std::max<size_t>(1, std::min(k_max, (n_roots + BC_CHUNK_ROOTS - 1) / BC_CHUNK_ROOTS));
+    size_t k_zc = nc ? std::max<size_t>(1, K * nc / std::max<size_t>(n_roots, 1)) : 0;
+    size_t k_lg = n_roots > nc ? std::max<size_t>(1, K - std::min(K, k_zc)) : 0;
+    if (k_zc + k_lg > k_max && k_zc > 1) k_zc = k_max - k_lg;
+    for (int cls = 0; cls < 2; cls++) {
+        const size_t base = cls == 0 ? 0 : nc, cnt = cls == 0 ? nc : n_roots - nc, kk = cls == 0 ? k_zc : k_lg;
+        for (size_t k = 0; k < kk; k++) {
+            const size_t r0 = base + cnt * k / kk, r1 = base + cnt * (k + 1) / kk;
+            if (r0 != r1) out.push_back(ChunkRange{r0, r1, cls == 0});
+        }
+    }
+    if (out.empty()) out.push_back(ChunkRange{0, 0, false});  // no roots at all: one empty program keeps the descriptor logic uniform
+    return out;
+}
+
 }  // namespace swirl
 
 using namespace swirl;
@@ -812,7 +978,16 @@ struct TraceState {
         int n_slots = 0;
         bool zerocheck_only = false;  // only constraint roots: round 0 needs it on d - 1 cosets, not d
         std::shared_ptr<Jit> jit;     // whole programs only
+        std::shared_ptr<std::vector<Instr>> h_code;  // sub-programs only: host copy for the MLE-round generator
     };
+    struct MleJit {  // all sub-programs of the AIR as one run-time compiled kernel for the MLE rounds
+        int state = 0;  // 0 = not tried, 1 = ready, -1 = unavailable
+        int D = 0;
+        JitKernel kernel;
+        std::vector<MleCaseRef> refs;  // per sub-program: case and operand shifts
+        ~MleJit() { jit_release(&kernel); }
+    };
+    std::shared_ptr<MleJit> mle_jit;
     std::vector<Chunk> chunks;
     Chunk whole[2];  // the constraint roots / the interaction roots as one program each (round 0 of tall traces)
     BasePart* d_parts = nullptr;
@@ -833,6 +1008,7 @@ struct ProgramCache {
     struct Entry {
         TraceState::Chunk whole[2];
         std::vector<TraceState::Chunk> chunks;
+        std::shared_ptr<TraceState::MleJit> mle_jit;
     };
     std::map<std::string, Entry> entries;
     std::vector<void*> buffers;  // device code of all entries
@@ -1052,11 +1228,12 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             s.whole[0] = hit->second.whole[0];
             s.whole[1] = hit->second.whole[1];
             s.chunks = hit->second.chunks;
+            s.mle_jit = hit->second.mle_jit;
         } else {
             // sub-programs never mix constraint and interaction roots: the zerocheck part of round 0 is needed on one
             // coset fewer than the LogUp part (cpu.rs:338-361 vs :405-409)
             const size_t nc = a.n_constraints;
-            auto compile_range = [&](size_t r0, size_t r1, bool zc, TraceState::Chunk* c, bool keep_host = false) -> int {
+            auto compile_range = [&](size_t r0, size_t r1, bool zc, TraceState::Chunk* c, bool keep_host = false, bool keep_mle = false) -> int {
                 Program pr;
                 SWIRL_TRY(compile_program(a, s.L, std::vector<Root>(roots.begin() + r0, roots.begin() + r1), &pr, BC_PREFETCH_VARS));
                 c->n_instr = (uint32_t)pr.code.size();
@@ -1067,6 +1244,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                     c->jit->h_code = pr.code;
                     c->jit->n_slots = pr.n_slots;
                 }
+                if (keep_mle) c->h_code = std::make_shared<std::vector<Instr>>(pr.code);
                 c->d_code = nullptr;  // an empty program is never dereferenced
                 if (!pr.code.empty()) {  // owned by the cache, released with the context
                     SWIRL_CUDA(cudaMalloc((void**)&c->d_code, pr.code.size() * sizeof(Instr)));
@@ -1078,31 +1256,17 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
             };
             SWIRL_TRY(compile_range(0, nc, true, &s.whole[0], true));
             SWIRL_TRY(compile_range(nc, roots.size(), false, &s.whole[1], true));
-            const size_t k_max = std::max<size_t>(2, std::min<size_t>(BC_MAX_CHUNKS, 240 / n_airs));
-            const size_t K = std::max<size_t>(1, std::min(k_max, (roots.size() + BC_CHUNK_ROOTS - 1) / BC_CHUNK_ROOTS));
-            // K chunks shared between the two classes in proportion to their roots, at least one per non-empty class
-            size_t k_zc = nc ? std::max<size_t>(1, K * nc / std::max<size_t>(roots.size(), 1)) : 0;
-            size_t k_lg = roots.size() > nc ? std::max<size_t>(1, K - std::min(K, k_zc)) : 0;
-            if (k_zc + k_lg > k_max && k_zc > 1) k_zc = k_max - k_lg;
-            for (int cls = 0; cls < 2; cls++) {
-                const size_t base = cls == 0 ? 0 : nc, cnt = cls == 0 ? nc : roots.size() - nc, kk = cls == 0 ? k_zc : k_lg;
-                for (size_t k = 0; k < kk; k++) {
-                    const size_t r0 = base + cnt * k / kk, r1 = base + cnt * (k + 1) / kk;
-                    if (r0 == r1) continue;
-                    TraceState::Chunk c;
-                    SWIRL_TRY(compile_range(r0, r1, cls == 0, &c));
-                    s.chunks.push_back(c);
-                }
-            }
-            if (s.chunks.empty()) {  // no roots at all: one empty program keeps the descriptor logic uniform
+            for (const ChunkRange& cr : chunk_ranges(nc, roots.size(), n_airs)) {
                 TraceState::Chunk c;
-                SWIRL_TRY(compile_range(0, 0, false, &c));
+                SWIRL_TRY(compile_range(cr.r0, cr.r1, cr.zerocheck, &c, false, true));
                 s.chunks.push_back(c);
             }
+            s.mle_jit = std::make_shared<TraceState::MleJit>();
             ProgramCache::Entry e;
             e.whole[0] = s.whole[0];
             e.whole[1] = s.whole[1];
             e.chunks = s.chunks;
+            e.mle_jit = s.mle_jit;
             cache->entries.emplace(std::move(key), std::move(e));
         }
     }
@@ -1313,6 +1477,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                         const std::string src = generate_round0_source(j.h_code, j.n_slots, "swirl_r0_jit");
                         const int jrc = src.empty() ? -1 : jit_compile(ctx, src, "swirl_r0_jit", &j.kernel);
                         j.state = jrc == 0 ? 1 : -1;
+                        ctx->jit_stats[0] += jrc == 0;
                         if (src.empty()) {
                             if (trace_on) fprintf(stderr, "[swirl jit] program of %zu instructions is too irregular to compile quickly: interpreter\n", j.h_code.size());
                         } else if (trace_on || jrc != 0)
@@ -1399,6 +1564,7 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                     if (grp.first) {
                         void* kargs[2] = {(void*)&d_descs, (void*)&d_ba};
                         SWIRL_CUDA(cudaLaunchKernel((const void*)grp.first, dim3(blocks), dim3(BC_BLOCK), kargs, 0, ctx->stream));
+                        ctx->jit_stats[1]++;
                     } else {
                         BC_DISPATCH_NS(max_slots_r0, BC_R0);
                     }
@@ -1588,13 +1754,64 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
     // One upload for all of them (per-round copies from pageable memory were 4 blocking transfers per round), and with
     // the round link (ext.cuh) every round's kernels are enqueued before the first result is read: the fold kernel of
     // round k waits for the challenge in the mailbox, the evaluation kernel of round k + 1 follows it in the stream.
+    struct MleJitGroup {  // consecutive AIRs that share a run-time compiled kernel: one launch
+        void* kernel;
+        uint32_t first_block, n_blocks;
+    };
     struct MleRound {
         std::vector<int> mode;  // 0: hypercube sum, 1: single row now, 2: tail multiply, 3: nothing to evaluate
         std::vector<size_t> desc_first, desc_count;
         size_t desc_off = 0, n_descs = 0, ba_off = 0, n_blocks = 0;
         size_t fold_off = 0, n_fold = 0, fba_off = 0, n_fold_blocks = 0;
+        std::vector<MleJitGroup> jit_groups;
         RoundLink link{};
     };
+    // Run-time compiled evaluation kernels (jit.hpp): one kernel per distinct AIR, a switch over its
+    // sub-programs with the value slots as D extension-field lanes in registers.  All or nothing per proof: if one AIR's
+    // kernel cannot be built (too irregular, too many live values), every AIR takes the interpreter launch.
+    bool mle_jit = ctx->jit_mle && ctx->jit_mode != 0 && jit_available() && n_max >= 1;
+    if (mle_jit && ctx->jit_mode != 2) {
+        bool tall = false;
+        for (size_t t = 0; t < n_airs; t++) tall = tall || T[t].log_height >= 17;
+        mle_jit = tall;
+    }
+    for (size_t t = 0; t < n_airs && mle_jit; t++) {
+        TraceState& s = T[t];
+        if (airs[t].constraint_degree == 0 && !airs[t].n_interactions && !airs[t].n_constraints) continue;  // never evaluated
+        if (!s.mle_jit) {
+            mle_jit = false;
+            break;
+        }
+        TraceState::MleJit& j = *s.mle_jit;
+        if (j.state == 1 && j.D != D) {  // the same AIR under another max_constraint_degree: rebuild
+            jit_release(&j.kernel);
+            j.state = 0;
+        }
+        if (j.state == 0) {
+            const auto tj = std::chrono::steady_clock::now();
+            std::vector<const std::vector<Instr>*> codes;
+            std::vector<int> ns;
+            bool have = true;
+            for (const auto& ch : s.chunks) {
+                have = have && ch.h_code;
+                codes.push_back(ch.h_code.get());
+                ns.push_back(ch.n_slots);
+            }
+            const std::string src = have ? generate_mle_source(codes, ns, D, "swirl_mle_jit", &j.refs) : std::string();
+            const int jrc = src.empty() ? -1 : jit_compile(ctx, src, "swirl_mle_jit", &j.kernel);
+            j.state = jrc == 0 ? 1 : -1;
+            j.D = D;
+            ctx->jit_stats[2] += jrc == 0;
+            if (src.empty()) {
+                if (trace_on) fprintf(stderr, "[swirl jit] MLE rounds: %zu sub-programs are too irregular or too wide to compile: interpreter\n", s.chunks.size());
+            } else if (trace_on || jrc != 0)
+                fprintf(stderr, "[swirl jit] MLE-round kernel for %zu sub-programs: %s (%.0f ms)%s%s\n", s.chunks.size(),
+                        jrc == 0 ? "compiled" : "FAILED, using the interpreter",
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tj).count(), jrc == 0 ? "" : ": ",
+                        jrc == 0 ? "" : swirl_last_error());
+        }
+        if (j.state != 1 || j.refs.size() != s.chunks.size()) mle_jit = false;
+    }
     std::vector<MleRound> plan(n_max + 1);
     std::vector<MleArgs> all_descs;
     std::vector<FoldArgs> all_fd;
@@ -1617,8 +1834,15 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 continue;
             }
             R.desc_first[t] = R.n_descs;
-            for (const auto& ch : s.chunks) {
+            for (size_t ci = 0; ci < s.chunks.size(); ci++) {
+                const auto& ch = s.chunks[ci];
                 MleArgs ma{};
+                if (mle_jit) {
+                    const MleCaseRef& cr = s.mle_jit->refs[ci];
+                    ma.sub = (uint32_t)cr.case_id;
+                    ma.col_shift = cr.col_shift;
+                    ma.w_shift = cr.w_shift;
+                }
                 ma.code = ch.d_code;
                 ma.n_instr = ch.n_instr;
                 ma.base = s.ef[s.cur];
@@ -1647,6 +1871,14 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
                 R.n_descs++;
             }
             R.desc_count[t] = R.n_descs - R.desc_first[t];
+            if (mle_jit && R.desc_count[t]) {
+                const uint32_t fb = all_descs[R.desc_off + R.desc_first[t]].first_block, nb = (uint32_t)R.n_blocks - fb;
+                void* k = s.mle_jit->kernel.kernel;
+                if (!R.jit_groups.empty() && R.jit_groups.back().kernel == k)
+                    R.jit_groups.back().n_blocks += nb;
+                else
+                    R.jit_groups.push_back(MleJitGroup{k, fb, nb});
+            }
         }
         SWIRL_REQUIRE(R.n_blocks <= (size_t)rs->max_blocks, "too many blocks for the reduction scratch");
         R.fold_off = all_fd.size();
@@ -1683,7 +1915,18 @@ extern "C" int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* t
         const MleRound& R = plan[round];
         for (auto& kv : eq_tab)
             if (round <= kv.first) SWIRL_TRY(build_eq(l_skip + round, kv.first));
-        if (R.n_descs) {
+        if (R.n_descs && mle_jit) {
+            SwirlTimed timed(ctx, SWIRL_T_BC_MLE);
+            for (const MleJitGroup& g : R.jit_groups) {
+                const MleArgs* dd = d_mle_descs + R.desc_off;
+                const uint16_t* ba = d_mle_ba + R.ba_off + g.first_block;
+                uint32_t block_base = g.first_block, tag = link_result_tag(R.link.seq);
+                void* kargs[4] = {(void*)&dd, (void*)&ba, (void*)&block_base, (void*)&tag};
+                SWIRL_CUDA(cudaLaunchKernel((const void*)g.kernel, dim3(g.n_blocks), dim3(128), kargs, 0, ctx->stream));
+                ctx->jit_stats[3]++;
+                SWIRL_LAUNCH_CHECK(ctx);
+            }
+        } else if (R.n_descs) {
             const int grid = (int)R.n_blocks;
             // single-row AIRs evaluate lane 0 only; D lanes are still the kernel's width
 #define BC_MLE(NS) launch_mle<NS>(D, d_mle_descs + R.desc_off, d_mle_ba + R.ba_off, grid, ctx->stream, link_result_tag(R.link.seq))
@@ -1900,6 +2143,41 @@ extern "C" size_t swirl_jit_round0_source(const swirl_air_ctx* air, int which, c
     Program pr;
     if (compile_program(*air, L, roots, &pr, BC_PREFETCH_VARS) != 0) return 0;
     const std::string src = generate_round0_source(pr.code, pr.n_slots, "swirl_r0_jit");
+    if (out && cap) {
+        const size_t n = std::min(src.size(), cap - 1);
+        memcpy(out, src.data(), n);
+        out[n] = 0;
+    }
+    return src.size();
+}
+
+// The MLE-round kernel of one AIR (see swirl_b200.h).  Host only.
+extern "C" size_t swirl_jit_mle_source(const swirl_air_ctx* air, int max_constraint_degree, size_t n_airs, char* out, size_t cap) {
+    if (!air || max_constraint_degree < 1 || max_constraint_degree > 5 || n_airs == 0) return 0;
+    AirLayout L;
+    if (air_layout(*air, &L) != 0) return 0;
+    std::vector<Root> roots;
+    for (uint64_t k = 0; k < air->n_constraints; k++) roots.push_back(Root{air->constraint_idx[k], 0, (uint32_t)k});
+    uint32_t w = (uint32_t)air->n_constraints;
+    for (uint64_t i = 0; i < air->n_interactions; i++) {
+        const swirl_interaction& it = air->interactions[i];
+        roots.push_back(Root{it.count_node, 1, w++});
+        for (uint32_t j = 0; j < it.msg_len; j++) roots.push_back(Root{air->msg_nodes[it.msg_offset + j], 2, w++});
+    }
+    std::vector<Program> progs;
+    for (const ChunkRange& cr : chunk_ranges(air->n_constraints, roots.size(), n_airs)) {
+        Program pr;
+        if (compile_program(*air, L, std::vector<Root>(roots.begin() + cr.r0, roots.begin() + cr.r1), &pr, BC_PREFETCH_VARS) != 0) return 0;
+        progs.push_back(std::move(pr));
+    }
+    std::vector<const std::vector<Instr>*> codes;
+    std::vector<int> ns;
+    for (const Program& pr : progs) {
+        codes.push_back(&pr.code);
+        ns.push_back(pr.n_slots);
+    }
+    std::vector<MleCaseRef> refs;
+    const std::string src = generate_mle_source(codes, ns, max_constraint_degree, "swirl_mle_jit", &refs, true);
     if (out && cap) {
         const size_t n = std::min(src.size(), cap - 1);
         memcpy(out, src.data(), n);

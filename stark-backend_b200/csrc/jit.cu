@@ -4,7 +4,10 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <map>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <vector>
 
 namespace swirl {
@@ -61,12 +64,38 @@ const char* jit_prelude() {
     return src;
 }
 
+static int jit_load(swirl_ctx* ctx, const std::vector<char>& cubin, const char* name, JitKernel* out) {
+    SWIRL_CUDA(cudaSetDevice(ctx->device));
+    cudaLibrary_t lib = nullptr;
+    SWIRL_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaKernel_t k = nullptr;
+    cudaError_t e = cudaLibraryGetKernel(&k, lib, name);
+    if (e != cudaSuccess) {
+        cudaLibraryUnload(lib);
+        return cuda_fail(e, "cudaLibraryGetKernel", __FILE__, __LINE__);
+    }
+    out->kernel = (void*)k;
+    out->library = (void*)lib;
+    return 0;
+}
+
 int jit_compile(swirl_ctx* ctx, const std::string& source, const char* name, JitKernel* out) {
     Nvrtc& n = nvrtc();
     if (!n.ok) {
         set_error("NVRTC is not available");
         return SWIRL_ERR_INVALID;
     }
+    // cubins are shared by all contexts of the process (a prover per thread compiles each program once, not once per
+    // context); loading a cubin into a context is cheap
+    static std::mutex cache_mutex;
+    static std::map<std::string, std::shared_ptr<const std::vector<char>>> cubin_cache;
+    std::shared_ptr<const std::vector<char>> cached;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        auto it = cubin_cache.find(source);
+        if (it != cubin_cache.end()) cached = it->second;
+    }
+    if (cached) return jit_load(ctx, *cached, name, out);
     nvrtcProgram prog = nullptr;
     nvrtcResult r = n.create(&prog, source.c_str(), "swirl_jit.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) {
@@ -86,21 +115,15 @@ int jit_compile(swirl_ctx* ctx, const std::string& source, const char* name, Jit
     }
     size_t cs = 0;
     n.cubin_size(prog, &cs);
-    std::vector<char> cubin(cs);
-    n.cubin(prog, cubin.data());
+    auto cubin = std::make_shared<std::vector<char>>(cs);
+    n.cubin(prog, cubin->data());
     n.destroy(&prog);
-    SWIRL_CUDA(cudaSetDevice(ctx->device));
-    cudaLibrary_t lib = nullptr;
-    SWIRL_CUDA(cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    cudaKernel_t k = nullptr;
-    cudaError_t e = cudaLibraryGetKernel(&k, lib, name);
-    if (e != cudaSuccess) {
-        cudaLibraryUnload(lib);
-        return cuda_fail(e, "cudaLibraryGetKernel", __FILE__, __LINE__);
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        if (cubin_cache.size() >= 256) cubin_cache.clear();  // bound the cache; entries in use are kept alive by their users
+        cubin_cache.emplace(source, cubin);
     }
-    out->kernel = (void*)k;
-    out->library = (void*)lib;
-    return 0;
+    return jit_load(ctx, *cubin, name, out);
 }
 
 void jit_release(JitKernel* k) {

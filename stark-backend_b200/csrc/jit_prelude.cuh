@@ -178,3 +178,170 @@ SW_LOAD_ATTR uint32_t load_point(const BasePart bp, uint32_t col, size_t x, cons
         for (int gg = 0; gg < G; gg++) s = f_add(s, sm[(gg * P + pi) * 13 + k]);                                      \
         a.partials[(size_t)bidx * (P * 12) + o] = s;                                                                  \
     }
+
+// ---- MLE rounds: what `batch_mle_kernel<NS, D>` of batch.cu does around `run_program`, for generated programs ----------
+// One launch serves a run of AIRs that share the kernel; a descriptor is one (AIR, sub-program) pair and names its
+// `case` of the generated switch.  Sub-programs that differ only by a constant shift of their columns and weights (the
+// same constraint applied to the next 16 columns) share a case: the shifts travel in the descriptor.  Value slots are
+// arrays of SW_D extension-field lanes (X = 1..D in lockstep), all indices static after unrolling.
+#ifdef SW_D
+__device__ __forceinline__ Ext ext_one() { return Ext{{SW_R1, 0u, 0u, 0u}}; }
+__device__ __forceinline__ Ext ext_from(uint32_t a) { return Ext{{a, 0u, 0u, 0u}}; }
+__device__ __forceinline__ Ext ext_sub(const Ext& a, const Ext& b) {
+    return Ext{{f_sub(a.c[0], b.c[0]), f_sub(a.c[1], b.c[1]), f_sub(a.c[2], b.c[2]), f_sub(a.c[3], b.c[3])}};
+}
+__device__ __forceinline__ Ext ext_neg(const Ext& a) { return Ext{{f_neg(a.c[0]), f_neg(a.c[1]), f_neg(a.c[2]), f_neg(a.c[3])}}; }
+
+struct MleArgs {  // batch.cu, member for member
+    const void* code;
+    uint32_t n_instr;
+    const uint32_t* base;
+    size_t h;
+    const uint32_t* weights;
+    const uint32_t* eq_xi;
+    size_t ny;
+    int single;
+    uint32_t first_block, n_blocks;
+    uint32_t* partials;
+    unsigned int* ticket;
+    uint32_t* result;
+    uint32_t sub, col_shift, w_shift;
+};
+
+#ifndef SW_HOST_EMU
+__device__ __forceinline__ uint32_t warp_sum_f(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = f_add(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int NV>
+__device__ __forceinline__ uint32_t block_sum_f(uint32_t (&v)[NV]) {
+    __shared__ uint32_t sm_part[32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const uint32_t s = warp_sum_f(v[i]);
+        if (lane == 0) sm_part[warp][i] = s;
+    }
+    __syncthreads();
+    uint32_t s = 0;
+    if (threadIdx.x < NV)
+        for (int w = 0; w < nwarps; w++) s = f_add(s, sm_part[w][threadIdx.x]);
+    return s;
+}
+// ext.cuh: group_sum -- the last block of the group to finish adds the partials and publishes the tagged totals
+template <int NV>
+__device__ __forceinline__ void group_sum_f(uint32_t (&v)[NV], uint32_t* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                            uint32_t* __restrict__ result, unsigned nblocks, unsigned bidx, uint32_t tag) {
+    __shared__ bool sm_last;
+    const uint32_t tot = block_sum_f<NV>(v);
+    if (nblocks == 1) {
+        if (threadIdx.x < NV) result[threadIdx.x] = tot | tag;
+        return;
+    }
+    if (threadIdx.x < NV) partials[(size_t)bidx * NV + threadIdx.x] = tot;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sm_last = (atomicAdd(ticket, 1u) == nblocks - 1);
+        if (sm_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (sm_last) {
+        __threadfence();
+        uint32_t acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] = 0;
+        for (unsigned b = threadIdx.x; b < nblocks; b += blockDim.x) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) acc[i] = f_add(acc[i], __ldcg(partials + (size_t)b * NV + i));
+        }
+        const uint32_t t2 = block_sum_f<NV>(acc);
+        if (threadIdx.x < NV) result[threadIdx.x] = t2 | tag;
+    }
+}
+#else
+// host emulation (tests): the harness runs the threads one after the other; totals are accumulated in place
+template <int NV>
+void group_sum_f(uint32_t (&v)[NV], uint32_t*, unsigned int*, uint32_t* result, unsigned, unsigned, uint32_t tag) {
+    for (int i = 0; i < NV; i++) result[i] = f_add(result[i] & 0x7fffffffu, v[i]) | tag;
+}
+#endif
+
+// rows 2y, 2y+1 of column `gcol` -> its values at X = 1..D: t1, t1 + d, t1 + 2d, ...; a single-row table gives lane 0
+__device__ __forceinline__ void mle_load(const MleArgs& a, size_t y, uint32_t gcol, Ext (&out)[SW_D]) {
+    const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
+    if (a.single) {
+        const Ext t = ldg_ext(c);
+#pragma unroll
+        for (int l = 0; l < SW_D; l++) out[l] = t;
+        return;
+    }
+    const Ext t0 = ldg_ext(c + 8 * y), t1 = ldg_ext(c + 8 * y + 4);
+    const Ext d = ext_sub(t1, t0);
+    out[0] = t1;
+#pragma unroll
+    for (int l = 1; l < SW_D; l++) out[l] = ext_add(out[l - 1], d);
+}
+#ifndef SW_HOST_EMU
+__device__ __forceinline__ void mle_prefetch(const MleArgs& a, size_t y, uint32_t gcol) {
+    const uint32_t* c = a.base + ((size_t)gcol * a.h) * 4;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c + (a.single ? 0 : 8 * y)));
+}
+#else
+inline void mle_prefetch(const MleArgs&, size_t, uint32_t) {}
+#endif
+
+// statements the generator emits; cs / ws are the descriptor's column / weight shifts
+#define SW_LANES _Pragma("unroll") for (int l_ = 0; l_ < SW_D; l_++)
+#define LDV(dst, gcol) mle_load(a, y, (uint32_t)(gcol) + cs, dst);
+#define PFV(gcol) mle_prefetch(a, y, (uint32_t)(gcol) + cs);
+#define CST(dst, val) { SW_LANES dst[l_] = ext_from(val); }
+#define ADD(dst, p, q) { SW_LANES dst[l_] = ext_add(p[l_], q[l_]); }
+#define SUB(dst, p, q) { SW_LANES dst[l_] = ext_sub(p[l_], q[l_]); }
+#define MUL(dst, p, q) { SW_LANES dst[l_] = ext_mul(p[l_], q[l_]); }
+#define NEG(dst, p) { SW_LANES dst[l_] = ext_neg(p[l_]); }
+// acc[lane][k] += weights[w] * s   /   += weights[w] * (p * q)
+#define ACCV(k, w, s)                                                      \
+    {                                                                      \
+        const Ext w_ = ldg_ext(a.weights + 4 * ((uint32_t)(w) + ws));      \
+        SW_LANES acc[l_][k] = ext_add(acc[l_][k], ext_mul(w_, s[l_]));     \
+    }
+#define MACV(k, w, p, q)                                                               \
+    {                                                                                  \
+        const Ext w_ = ldg_ext(a.weights + 4 * ((uint32_t)(w) + ws));                  \
+        SW_LANES acc[l_][k] = ext_add(acc[l_][k], ext_mul(w_, ext_mul(p[l_], q[l_]))); \
+    }
+#define SLOT(name) Ext name[SW_D];
+
+// A generated kernel is:  SW_MLE_SIGNATURE(name) { SW_MLE_PROLOGUE  case 0: { ... } break; ...  SW_MLE_EPILOGUE }
+// `block_air` points at the launch's first block; block_base is that block's index in the round's numbering (the
+// descriptors' first_block counts in it).
+#define SW_MLE_SIGNATURE(NAME)                                                                                          \
+    extern "C" __global__ void __launch_bounds__(128, SW_MLE_MIN_BLOCKS) NAME(const MleArgs* __restrict__ descs,        \
+                                                                              const uint16_t* __restrict__ block_air,   \
+                                                                              uint32_t block_base, uint32_t result_tag)
+#define SW_MLE_PROLOGUE                                                                                                 \
+    const MleArgs a = descs[block_air[blockIdx.x]];                                                                     \
+    const uint32_t bidx = blockIdx.x + block_base - a.first_block;                                                      \
+    const uint32_t cs = a.col_shift, ws = a.w_shift;                                                                    \
+    uint32_t v[SW_D * 12];                                                                                              \
+    _Pragma("unroll") for (int i = 0; i < SW_D * 12; i++) v[i] = 0;                                                     \
+    for (size_t y = (size_t)bidx * blockDim.x + threadIdx.x; y < a.ny; y += (size_t)a.n_blocks * blockDim.x) {          \
+        const Ext e = a.single ? ext_one() : ldg_ext(a.eq_xi + 4 * y);                                                  \
+        Ext acc[SW_D][3];                                                                                               \
+        _Pragma("unroll") for (int X = 0; X < SW_D; X++)                                                                \
+            _Pragma("unroll") for (int k = 0; k < 3; k++) acc[X][k] = ext_zero();                                       \
+        switch (a.sub) {
+#define SW_MLE_EPILOGUE                                                                                                 \
+            default: break;                                                                                             \
+        }                                                                                                               \
+        _Pragma("unroll") for (int X = 0; X < SW_D; X++)                                                                \
+            _Pragma("unroll") for (int k = 0; k < 3; k++) {                                                             \
+                const Ext t = ext_mul(e, acc[X][k]);                                                                    \
+                _Pragma("unroll") for (int c = 0; c < 4; c++) v[X * 12 + 4 * k + c] = f_add(v[X * 12 + 4 * k + c], t.c[c]); \
+            }                                                                                                           \
+    }                                                                                                                   \
+    group_sum_f<SW_D * 12>(v, a.partials, a.ticket, a.result, a.n_blocks, bidx, result_tag);
+#endif  // SW_D

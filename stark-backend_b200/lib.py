@@ -126,6 +126,8 @@ PROTOTYPES = {
     "swirl_prove_openings": (_i, [_vp, C.POINTER(TranscriptC), C.POINTER(WhirConfigC), _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _sz]),
     "swirl_ctx_set_jit": (_i, [_vp, _i]),
     "swirl_jit_round0_source": (_sz, [_vp, _i, C.c_char_p, _sz]),
+    "swirl_jit_mle_source": (_sz, [_vp, _i, _sz, C.c_char_p, _sz]),
+    "swirl_ctx_jit_stats": (_i, [_vp, _vp]),
     "swirl_stacked_layout": (_i, [_i, _i, _sz, _vp, _vp, C.POINTER(_u64), C.POINTER(_u64), _vp]),
 }
 

@@ -79,6 +79,13 @@ class Oracle:
         self.L.orc_ef_mul(_p(out), _p(a), _p(b))
         return out
 
+    def binary_k_fold(self, values, alphas, x):
+        """verifier/whir.rs:352-389: values (2^k, 4), alphas (k, 4), x a base-field Montgomery word."""
+        values, alphas = np.ascontiguousarray(values, np.uint32), np.ascontiguousarray(alphas, np.uint32)
+        out = np.zeros(4, np.uint32)
+        self.L.orc_binary_k_fold(_p(out), _p(values), C.c_int(len(alphas)), _p(alphas), C.c_uint32(int(x)))
+        return out
+
     def ef_inv(self, a):
         a = np.ascontiguousarray(a, np.uint32)
         out = np.zeros(4, np.uint32)

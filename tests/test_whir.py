@@ -13,6 +13,20 @@ CASES = [
     (4, 8, 1, dict(k=4, num_queries=[9, 6], mu_pow_bits=4, query_phase_pow_bits=5, folding_pow_bits=3), [4, 1, 3]),
     (0, 5, 1, dict(k=1, num_queries=[4, 4, 3], mu_pow_bits=1, query_phase_pow_bits=1, folding_pow_bits=1), [2]),
 ]
+# the shape grid of the reference's whir_single_fib_{n_stack}_{log_blowup}_{k}_{log_final_poly_len} tests (backend-tests/src/lib.rs:
+# 1229-1251, 1673-1700: l_skip = 2, one 2-column commitment, PoW bits 1 / 2 / 3 as test_whir_config_small sets them); rounds =
+# ceil((l_skip + n_stack - log_final_poly_len) / k)
+_SMALL = dict(mu_pow_bits=3, query_phase_pow_bits=1, folding_pow_bits=2)
+CASES += [
+    (2, 0, 1, dict(k=1, num_queries=[3, 2], **_SMALL), [2]),
+    (2, 2, 1, dict(k=1, num_queries=[4, 3], **_SMALL), [2]),
+    (2, 2, 1, dict(k=2, num_queries=[4, 3], **_SMALL), [2]),
+    (2, 2, 1, dict(k=3, num_queries=[4], **_SMALL), [2]),
+    (2, 2, 1, dict(k=4, num_queries=[4], **_SMALL), [2]),
+    (2, 2, 2, dict(k=4, num_queries=[3], **_SMALL), [2]),
+    # whir_multiple_commitments (lib.rs:1269-1348): five commitments of 3..12 columns, l_skip = n_stack = 3, two rounds of 6 / 5 queries
+    (3, 3, 1, dict(k=2, num_queries=[6, 5], mu_pow_bits=1, query_phase_pow_bits=1, folding_pow_bits=1), [5, 12, 3, 8, 10]),
+]
 
 
 def make_case(oracle, case, seed):
@@ -78,3 +92,61 @@ def test_gpu_whir_large_accepted_by_oracle_verifier(dev, oracle):
     openings = oracle.whir_stacking_openings(l_skip, mats[0][0], H, widths[0], u)
     assert oracle.whir_verify(st, l_skip, n_stack, log_blowup, cfg, proof, widths, openings, root.reshape(1, 8), u)
     assert np.array_equal(st, ts.words())
+
+
+# ---- the reference's binary_k_fold identities (backend-tests/src/lib.rs:1191-1227: fold_single, fold_double) -----------
+# The expected values are formed here in Python integers (F_p[x] / (x^4 - 11), canonical representatives), independent of
+# the oracle's field code; the oracle's verifier-side fold must reproduce them.
+_P = 0x78000001
+
+
+def _ef(*c):
+    return tuple(int(x) % _P for x in c)
+
+
+def _add(a, b):
+    return tuple((x + y) % _P for x, y in zip(a, b))
+
+
+def _sub(a, b):
+    return tuple((x - y) % _P for x, y in zip(a, b))
+
+
+def _mul(a, b):
+    r = [0] * 7
+    for i in range(4):
+        for j in range(4):
+            r[i + j] += a[i] * b[j]
+    return tuple((r[i] + 11 * (r[i + 4] if i < 3 else 0)) % _P for i in range(4))
+
+
+def _scale(a, s):
+    return tuple(x * s % _P for x in a)
+
+
+def _fold_step(lo, hi, alpha, x):  # lo + (alpha - x) (lo - hi) / (2 x)
+    return _add(lo, _scale(_mul(_sub(alpha, _ef(x, 0, 0, 0)), _sub(lo, hi)), pow(2 * x, -1, _P)))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_binary_k_fold_satisfies_the_reference_identities(oracle, seed):
+    rng = np.random.default_rng(seed)
+    ef = lambda: _ef(*rng.integers(0, _P, size=4))
+    mont = lambda e: oracle.to_mont(np.array(e, dtype=np.uint64))
+    canon = lambda w: tuple(int(v) for v in oracle.from_mont(w))
+    x = int(rng.integers(1, _P))
+    xm = int(oracle.to_mont(np.array([x], dtype=np.uint64))[0])
+    # k = 1
+    a0, a1, alpha = ef(), ef(), ef()
+    got = oracle.binary_k_fold(np.stack([mont(a0), mont(a1)]), np.stack([mont(alpha)]), xm)
+    assert canon(got) == _fold_step(a0, a1, alpha, x)
+    # k = 2: pairs (a0, a2) at x and (a1, a3) at tw * x, then the two results at x^2
+    a = [ef() for _ in range(4)]
+    al = [ef(), ef()]
+    tw = pow(0x1A427A41, 1 << 25, _P)  # two_adic_generator(2): the 2^27-th root of unity of BabyBear, raised to 2^25
+    assert pow(tw, 4, _P) == 1 and pow(tw, 2, _P) != 1
+    b0 = _fold_step(a[0], a[2], al[0], x)
+    b1 = _fold_step(a[1], a[3], al[0], tw * x % _P)
+    want = _fold_step(b0, b1, al[1], x * x % _P)
+    got = oracle.binary_k_fold(np.stack([mont(v) for v in a]), np.stack([mont(v) for v in al]), xm)
+    assert canon(got) == want
