@@ -118,6 +118,7 @@ static int ctx_init(int device, cudaStream_t stream, bool owns, swirl_ctx** out)
     if (const char* env = getenv("CUDA_LAUNCH_BLOCKING"))
         if (atoi(env) != 0) ctx->round_link = ctx->round_link_ok = false;
     if (const char* env = getenv("SWIRL_JIT_MLE")) ctx->jit_mle = atoi(env) != 0;
+    if (const char* env = getenv("SWIRL_JIT_MODE")) ctx->jit_mode = std::max(0, std::min(2, atoi(env)));  // initial swirl_ctx_set_jit mode (A/B runs)
     if (const char* env = getenv("SWIRL_ROUND_LINK")) ctx->round_link = atoi(env) != 0 && ctx->round_link_ok;  // A/B knob, see swirl_ctx_set_round_link
     if (owns) {
         e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -201,10 +202,8 @@ int swirl_ctx_set_cache_rs_code_matrix(swirl_ctx* ctx, int on) {
 
 int swirl_ctx_set_jit(swirl_ctx* ctx, int mode) {
     SWIRL_REQUIRE(ctx && mode >= 0 && (mode & 3) <= 2 && mode < 8, "mode must be 0, 1 or 2, plus 4 for compiled MLE rounds");
-    ctx->jit_mode = mode & 3;
-    // SWIRL_JIT_MLE in the environment outranks the mode bit (A/B runs of unmodified callers); mode 0 is always the interpreter
-    if (const char* env = getenv("SWIRL_JIT_MLE")) ctx->jit_mle = atoi(env) != 0;
-    else ctx->jit_mle = (mode & 4) != 0;
+    ctx->jit_mode = mode & 3;  // 0 switches every compiled kernel off, the MLE rounds' included
+    if (mode & 4) ctx->jit_mle = true;  // otherwise the context keeps its setting (default, or SWIRL_JIT_MLE in the environment)
     return 0;
 }
 
