@@ -364,8 +364,9 @@ int swirl_prove_batch_constraints(swirl_ctx* ctx, swirl_transcript* ts, int l_sk
  * Reference counterpart: the rule compiler + interpreter, cuda-backend/src/logup_zerocheck/rules/mod.rs:27-130. */
 /* mode & 3: 0 = interpreter only, 1 = compile the programs of tall traces (default), 2 = compile every program (tests).
  * mode & 4: the MLE rounds run compiled kernels as well (one kernel per AIR: a switch over its sub-programs, value slots
- * as D extension-field lanes in registers), under the same tall-trace rule; SWIRL_JIT_MLE=0/1 in the environment sets
- * the context's initial choice, mode 0 switches every compiled kernel off. */
+ * as D extension-field lanes in registers), under the same tall-trace rule.  On by default since it was measured
+ * (profiles/r3a_*); SWIRL_JIT_MLE=0/1 in the environment sets the context's initial choice, mode 0 switches every
+ * compiled kernel off. */
 int swirl_ctx_set_jit(swirl_ctx* ctx, int mode);
 size_t swirl_jit_round0_source(const swirl_air_ctx* air, int which, char* out, size_t cap);
 /* The MLE-round kernel of one AIR for max_constraint_degree D, as it would be compiled when `n_airs` AIRs share the proof

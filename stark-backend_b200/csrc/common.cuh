@@ -43,7 +43,7 @@ struct swirl_ctx {
     bool round_link_ok = true;  // false once the probe found launches serialised (profiler, sanitizer): sponge.cu link_probe
     bool round_link = true;  // sumcheck rounds exchange results/challenges with the host through a mapped mailbox (ext.cuh: RoundLink)
     int jit_mode = 1;  // run-time compiled constraint kernels: 0 = never, 1 = traces of 2^17 rows and more, 2 = always (tests)
-    bool jit_mle = false;  // the MLE rounds run compiled kernels too (batch.cu: generate_mle_source)
+    bool jit_mle = true;  // the MLE rounds run compiled kernels too (batch.cu: generate_mle_source); SWIRL_JIT_MLE=0: interpreter
     uint64_t jit_stats[4] = {0, 0, 0, 0};  // round-0 kernels built / launched, MLE-round kernels built / launched (swirl_ctx_jit_stats)
     size_t ntt_scratch_bytes = size_t(4) << 30;  // inter-pass scratch per column group (measured: one big launch beats L2-sized groups)
     // optional per-kernel-family CUDA-event timing (bench.py's roofline numbers)
