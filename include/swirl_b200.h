@@ -53,7 +53,8 @@ int swirl_ctx_synchronize(swirl_ctx* ctx);
 void* swirl_ctx_stream(swirl_ctx* ctx);            /* the cudaStream_t */
 uint64_t swirl_ctx_launch_count(swirl_ctx* ctx);   /* kernels launched through this ctx so far */
 /* Tuning / test knobs: largest single-pass NTT radix (log2, default 11, range 1..13) and the
- * bytes of inter-pass scratch kept per column group (default 48 MiB, meant to stay L2 resident). */
+ * bytes of inter-pass scratch per column group (default 4 GiB = one launch over all columns of C2: L2-sized groups
+ * were measured slower because the passes are multiplier-bound; 0 keeps the current value). */
 int swirl_ctx_set_ntt_plan(swirl_ctx* ctx, int max_log_radix, size_t scratch_bytes);
 /* GpuProverConfig::cache_rs_code_matrix (reference cuda-backend/src/device.rs:102-121).  on (default here): commitments keep
  * their RS codeword for the WHIR openings.  off (the reference's default): the codeword is streamed through a 32-column
