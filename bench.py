@@ -195,7 +195,7 @@ def cpu_prove_sample(oracle, log_rows):
                                f"workload; n_stack {n_stack}, WHIR queries {cfg['num_queries']}, same PoW bits)")
 
 
-def reference_sample_log_rows(t14_seconds, steps, budget_s=240.0):
+def reference_sample_log_rows(t14_seconds, steps, budget_s=150.0):
     """Largest sample (rows = 2^k, 14 <= k <= LOG_ROWS) whose `steps` proofs fit the budget; a proof's cost is linear in
     the rows within ~15 % (profiles/r2_cpu_full_proof_*.jsonl: 2^16 -> 2^20 is 14.2x the time for 16x the rows)."""
     k = 14
