@@ -141,3 +141,56 @@ def test_gpu_gkr_large_accepted_by_oracle_verifier(dev, oracle):
     assert ok and np.array_equal(stv, ts.words())
     assert np.array_equal(numer, oracle.eval_mle_evals_at_point(leaves[:, :4], log_n, xi))
     assert np.array_equal(denom, oracle.eval_mle_evals_at_point(leaves[:, 4:], log_n, xi))
+
+
+# ---- the reference's own GKR unit tests (crates/stark-backend/tests/fractional_sumcheck_gkr.rs) on the oracle ------------
+def _ef(oracle, x):
+    return np.array([oracle.to_mont(np.array([x % P], dtype=np.uint64))[0], 0, 0, 0], dtype=np.uint32)
+
+
+def test_oracle_verifier_rejects_nonzero_base_layer_numerator(oracle):
+    """test_gkr_base_layer_numerator_zero (:62-87): claims p = (1, 2), q = (3, 4), q0 = 12: p0 = 1*4 + 2*3 = 10 != 0."""
+    claims = np.concatenate([_ef(oracle, 1), _ef(oracle, 3), _ef(oracle, 2), _ef(oracle, 4)]).reshape(1, 16)  # p_xi_0, q_xi_0, p_xi_1, q_xi_1
+    proof = dict(frac_sum=np.concatenate([_ef(oracle, 0), _ef(oracle, 12)]), claims=claims, polys=np.zeros((0, 12), np.uint32))
+    assert not oracle.gkr_verify(np.zeros(18, np.uint32), 1, proof)[0]
+    # the same shape with a vanishing numerator (p = (3, -4): 3*4 - 4*3 = 0) and q0 = 12 passes the base-layer check
+    good = np.concatenate([_ef(oracle, 3), _ef(oracle, 3), _ef(oracle, P - 4), _ef(oracle, 4)]).reshape(1, 16)
+    proof = dict(frac_sum=np.concatenate([_ef(oracle, 0), _ef(oracle, 12)]), claims=good, polys=np.zeros((0, 12), np.uint32))
+    assert oracle.gkr_verify(np.zeros(18, np.uint32), 1, proof)[0]
+    # and a wrong q0 does not
+    proof["frac_sum"] = np.concatenate([_ef(oracle, 0), _ef(oracle, 13)])
+    assert not oracle.gkr_verify(np.zeros(18, np.uint32), 1, proof)[0]
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3])
+def test_oracle_gkr_trivial_fractions_integration(oracle, log_n):
+    """test_gkr_{1,2,3}_round_integration (:89-214): 2^n fractions 0/1 from a fresh transcript; the verifier returns a zero
+    numerator claim and a non-zero denominator claim."""
+    leaves = np.zeros((1 << log_n, 8), np.uint32)
+    leaves[:, 4] = _ef(oracle, 1)[0]
+    st, stv = np.zeros(18, np.uint32), np.zeros(18, np.uint32)
+    proof = oracle.gkr_prove(st, leaves, log_n, True)
+    ok, numer, denom, _ = oracle.gkr_verify(stv, log_n, proof)
+    assert ok and not numer.any() and denom.any()
+    assert np.array_equal(st, stv)
+
+
+def test_oracle_gkr_mixed_fractions(oracle):
+    """test_gkr_mixed_fractions (:220-251): 5/1 + (-5)/1."""
+    leaves = np.zeros((2, 8), np.uint32)
+    leaves[0, :4], leaves[1, :4] = _ef(oracle, 5), _ef(oracle, P - 5)
+    leaves[:, 4] = _ef(oracle, 1)[0]
+    st, stv = np.zeros(18, np.uint32), np.zeros(18, np.uint32)
+    proof = oracle.gkr_prove(st, leaves, 1, True)
+    ok, _, denom, _ = oracle.gkr_verify(stv, 1, proof)
+    assert ok and denom.any()
+
+
+def test_oracle_verifier_rejects_wrong_shapes(oracle):
+    """test_multiple_rounds_shape (:20-60): a proof for one round offered as a two-round proof is rejected (layer count /
+    sumcheck polynomial count)."""
+    leaves = np.zeros((2, 8), np.uint32)
+    leaves[:, 4] = _ef(oracle, 1)[0]
+    proof = oracle.gkr_prove(np.zeros(18, np.uint32), leaves, 1, True)
+    two = dict(frac_sum=proof["frac_sum"], claims=np.concatenate([proof["claims"], proof["claims"]]), polys=np.zeros((1, 12), np.uint32))
+    assert not oracle.gkr_verify(np.zeros(18, np.uint32), 2, two)[0]
