@@ -59,9 +59,13 @@ def test_oracle_stacked_reduction_accepted_by_oracle_verifier(oracle, case):
     bad = claims.copy()
     bad[0, 0] ^= 1
     assert not oracle.stacked_reduction_verify(make_case(oracle, case, 31)[2], l_skip, n_stack, data, bad, r, proof)[0]
-    badp = proof.copy()
-    badp[-1] ^= 1
-    assert not oracle.stacked_reduction_verify(make_case(oracle, case, 31)[2], l_skip, n_stack, data, claims, r, badp)[0]
+    # one negative case per proof section, as the reference has them (tests/stacked_reduction.rs:192-245): univariate round
+    # coefficients, sumcheck round polynomials, stacking openings
+    n0 = (2 * ((1 << l_skip) - 1) + 1) * 4
+    for idx in [0, n0 - 1] + ([n0, n0 + n_stack * 8 - 1] if n_stack else []) + [n0 + n_stack * 8, len(proof) - 1]:
+        badp = proof.copy()
+        badp[idx] ^= 1
+        assert not oracle.stacked_reduction_verify(make_case(oracle, case, 31)[2], l_skip, n_stack, data, claims, r, badp)[0], idx
 
 
 def gpu_commits(dev, l_skip, n_stack, data):
