@@ -128,6 +128,16 @@ def sender_receiver(log_send, log_recv, rng, bus=3, balanced=True):
     return s_air, r_air
 
 
+def dummy_interaction(row_major, is_send, bus=0):
+    """DummyInteractionAir::new(1, is_send, bus) (test_utils/dummy_airs/interaction/dummy_interaction_air.rs:94-122) on a
+    literal row-major [count, field] table as the reference's interaction tests write them (backend-tests/src/lib.rs:844-1018):
+    a send pushes (bus, [field], count), a receive pushes (bus, [field], -count); no constraints."""
+    rows = [row_major[i:i + 2] for i in range(0, len(row_major), 2)]
+    d = Dag()
+    count = d.main(0) if is_send else d.neg(d.main(0))
+    return Air(d, [], [(count, bus, [d.main(1)])], 1, False, mont_matrix([[r[0] for r in rows], [r[1] for r in rows]]))
+
+
 def with_parts(log_n, rng):
     """An AIR with a preprocessed trace and one cached main next to the common main, rotations used:
     prep col p, cached col c, common cols (x, y):  y' = y + p * c  on transitions;  x * (x - 1) = 0;

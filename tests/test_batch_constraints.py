@@ -84,6 +84,41 @@ def test_oracle_unbalanced_logup_is_an_error(oracle):
         oracle.bc_prove(st, 2, 2, 0, A.flatten([s, r]), 2, 2)
 
 
+# ---- the reference's literal interaction tables (backend-tests/src/lib.rs:844-1018): row-major [count, field] ------------
+_RECV = [1, 5, 3, 4, 4, 4, 2, 5, 0, 123, 545, 889, 1, 889, 0, 456]
+REFERENCE_INTERACTION_TABLES = {
+    # name: ([(table, is_send), ...], balanced)
+    "interaction_multi_rows_neg": ([([0, 1, 3, 5, 7, 4, 546, 0], True),
+                                    ([1, 5, 3, 4, 4, 4, 2, 5, 0, 123, 545, 0, 0, 0, 0, 456], False)], False),
+    "interaction_all_zero_sender": ([([0, 1, 0, 5, 0, 4, 0, 889], True)], True),
+    "interaction_multi_senders": ([([0, 1, 3, 5, 6, 4, 333, 889], True), ([1, 4, 213, 889], True), (_RECV, False)], True),
+    "interaction_multi_senders_neg": ([([0, 1, 3, 5, 5, 4, 333, 889], True), ([1, 4, 213, 889], True), (_RECV, False)], False),
+    "interaction_multi_sender_receiver": ([([0, 1, 3, 5, 6, 4, 333, 889], True), ([1, 4, 213, 889], True),
+                                           ([1, 5, 3, 4, 4, 4, 2, 5, 0, 123, 545, 889, 0, 289, 0, 456], False), ([1, 889], False)], True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_INTERACTION_TABLES))
+def test_oracle_on_the_reference_interaction_tables(oracle, name):
+    """The oracle must agree with the outcome the reference's test asserts: balanced tables prove and verify (l_skip = 2 as
+    default_test_params_small; traces of 8, 4, 2 and 1 rows, i.e. lifted ones included), unbalanced ones are a prover error."""
+    tables, balanced = REFERENCE_INTERACTION_TABLES[name]
+    airs = sorted([A.dummy_interaction(t, send) for t, send in tables], key=lambda a: -a.height)  # ProvingContext::into_sorted
+    l_skip, D, pow_bits = 2, 3, 1
+    n_max = max(max(a.height.bit_length() - 1 - l_skip for a in airs), 0)
+    st = np.zeros(18, np.uint32)
+    oracle.sponge_observe(st, oracle.to_mont(np.arange(3)))
+    stv = st.copy()
+    flat = A.flatten(airs)
+    if not balanced:
+        with pytest.raises(ValueError):
+            oracle.bc_prove(st, l_skip, D, pow_bits, flat, len(airs), n_max)
+        return
+    proof, r = oracle.bc_prove(st, l_skip, D, pow_bits, flat, len(airs), n_max)
+    ok, rv = oracle.bc_verify(stv, l_skip, D, pow_bits, flat, len(airs), n_max, proof)
+    assert ok and np.array_equal(r, rv) and np.array_equal(st, stv)
+
+
 def to_device_airs(dev, airs):
     out = []
     for a in airs:
