@@ -177,3 +177,25 @@ def test_gpu_violated_constraint_proof_equals_oracle_and_is_rejected(dev, oracle
     got, rg = dev.prove_batch_constraints(ts, l_skip, D, pow_bits, to_device_airs(dev, airs))
     assert np.array_equal(got, want) and np.array_equal(rg, r)
     assert not oracle.bc_verify(stv, l_skip, D, pow_bits, A.flatten(airs), 1, n_max, got)[0]
+
+
+# ---- zero interactions (backend-tests/src/lib.rs:378-480) -----------------------------------------------------------------
+@pytest.mark.parametrize("log_trace_degree", [0, 1, 2, 3, 4, 6])
+def test_oracle_zero_interactions_q0_is_one_and_not_malleable(oracle, log_trace_degree):
+    """batch_sumcheck_zero_interactions / ..._malleable_q0: Fibonacci alone at l_skip = 2 (default_test_params_small); the
+    sampled r has max(log_height - l_skip, 0) + 1 entries; the honest q0_claim is ONE and any other value is rejected."""
+    l_skip, D, pow_bits = 2, 3, 1
+    air = A.fibonacci(log_trace_degree)
+    n_max = max(log_trace_degree - l_skip, 0)
+    flat = A.flatten([air])
+    st = np.zeros(18, np.uint32)
+    stv = st.copy()
+    proof, r = oracle.bc_prove(st, l_skip, D, pow_bits, flat, 1, n_max)
+    assert r.shape[0] == n_max + 1
+    one = oracle.to_mont(np.array([1], dtype=np.uint64))[0]
+    assert list(proof[1:5]) == [one, 0, 0, 0]  # [0] = logup_pow_witness, [1:5] = q0_claim
+    ok, rv = oracle.bc_verify(stv, l_skip, D, pow_bits, flat, 1, n_max, proof)
+    assert ok and np.array_equal(r, rv)
+    bad = proof.copy()
+    bad[1] = oracle.to_mont(np.array([2], dtype=np.uint64))[0]
+    assert not oracle.bc_verify(np.zeros(18, np.uint32), l_skip, D, pow_bits, flat, 1, n_max, bad)[0]
