@@ -138,6 +138,30 @@ def dummy_interaction(row_major, is_send, bus=0):
     return Air(d, [], [(count, bus, [d.main(1)])], 1, False, mont_matrix([[r[0] for r in rows], [r[1] for r in rows]]))
 
 
+def self_interaction(width, log_height, bus):
+    """SelfInteractionAir + SelfInteractionChip (test_utils/dummy_airs/interaction/self_interaction_air.rs:26-86): eight
+    interactions on one bus whose messages are the whole local / next row (forward and reversed) with constant, row-sum and
+    first-column multiplicities; trace[row][i] = (row + i) mod width, so every pair cancels over the cyclic trace.  As in
+    the reference, `next_sum` is (deliberately or not) the sum of the LOCAL row."""
+    n = 1 << log_height
+    cols = [[(r + i) % width for r in range(n)] for i in range(width)]
+    d = Dag()
+    local = [d.main(i, 0) for i in range(width)]
+    nxt = [d.main(i, 1) for i in range(width)]
+    zero, one = d.const(0), d.const(1)
+    local_sum = zero
+    for v in local:
+        local_sum = d.add(local_sum, v)
+    next_sum = local_sum
+    inter = [
+        (one, bus, list(local)), (d.neg(one), bus, list(nxt)),
+        (local_sum, bus, list(local)), (d.neg(next_sum), bus, list(nxt)),
+        (local[0], bus, list(local)), (d.neg(nxt[0]), bus, list(nxt)),
+        (local_sum, bus, list(reversed(local))), (d.neg(next_sum), bus, list(reversed(nxt))),
+    ]
+    return Air(d, [], inter, 1, True, mont_matrix(cols))
+
+
 def with_parts(log_n, rng):
     """An AIR with a preprocessed trace and one cached main next to the common main, rotations used:
     prep col p, cached col c, common cols (x, y):  y' = y + p * c  on transitions;  x * (x - 1) = 0;

@@ -1,0 +1,39 @@
+"""GPU comparisons that were written AFTER this round's GPU time was spent and have therefore never run on a device.
+They run in a process of their own (tests/unverified_gpu_runner.py: a fault there cannot take the session down), are marked
+`xfail(strict=False)` -- a pass shows up as XPASS, a mismatch as xfail, neither turns the suite red -- and the file sorts last.
+Their CPU halves (the oracle against its own verifier chain, on the same inputs) are ordinary tests in test_prove_matrix.py
+and test_batch_constraints.py.  When one of these has passed on a B200, move it into the file it belongs to and drop the mark."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import test_batch_constraints as tbc
+import test_prove_matrix as tpm
+
+unverified = pytest.mark.xfail(strict=False, reason="never run on a GPU (added after the round's GPU budget was spent)")
+NAMES = ["prove:" + c[0] for c in tpm.CPU_ONLY_CASES] + ["tables:" + n for n in sorted(tbc.REFERENCE_INTERACTION_TABLES)]
+
+
+@pytest.fixture(scope="module")
+def runner_results():
+    here = os.path.dirname(os.path.abspath(__file__))
+    try:
+        out = subprocess.run([sys.executable, os.path.join(here, "unverified_gpu_runner.py")], capture_output=True, text=True, timeout=180).stdout
+    except subprocess.TimeoutExpired as e:
+        out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+    for line in reversed(out.strip().split("\n")):
+        try:
+            return json.loads(line)
+        except ValueError:
+            continue
+    return {}
+
+
+@pytest.mark.gpu
+@unverified
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_equals_oracle_on_reference_fixtures_added_without_gpu(runner_results, name):
+    assert runner_results.get(name, "not run (the runner stopped before it)") == "pass"
