@@ -21,7 +21,7 @@ NAMES = ["prove:" + c[0] for c in tpm.CPU_ONLY_CASES] + ["tables:" + n for n in 
 def runner_results():
     here = os.path.dirname(os.path.abspath(__file__))
     try:
-        out = subprocess.run([sys.executable, os.path.join(here, "unverified_gpu_runner.py")], capture_output=True, text=True, timeout=180).stdout
+        out = subprocess.run([sys.executable, os.path.join(here, "unverified_gpu_runner.py")], capture_output=True, text=True, timeout=90).stdout
     except subprocess.TimeoutExpired as e:
         out = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
     for line in reversed(out.strip().split("\n")):
