@@ -138,6 +138,25 @@ def dummy_interaction(row_major, is_send, bus=0):
     return Air(d, [], [(count, bus, [d.main(1)])], 1, False, mont_matrix([[r[0] for r in rows], [r[1] for r in rows]]))
 
 
+def dummy_interaction_chip(counts, fields, is_send, bus=0, partition=False):
+    """DummyInteractionChip (dummy_interaction_air.rs:126-260): rows (count, fields...) padded with zero rows to a power of
+    two; with `partition` the count column is the common main and the fields are one cached main (new_with_partition)."""
+    n = 1
+    while n < len(counts):
+        n *= 2
+    w = len(fields[0])
+    counts = list(counts) + [0] * (n - len(counts))
+    fields = [list(f) for f in fields] + [[0] * w] * (n - len(fields))
+    d = Dag()
+    if partition:
+        cnt, msg = d.main(0, 0, 1), [d.main(i, 0, 0) for i in range(w)]  # part 0 = the cached main, last part = common main
+        mats = dict(common_main=mont_matrix([counts]), cached=[mont_matrix([[f[i] for f in fields] for i in range(w)])])
+    else:
+        cnt, msg = d.main(0), [d.main(1 + i) for i in range(w)]
+        mats = dict(common_main=mont_matrix([counts] + [[f[i] for f in fields] for i in range(w)]), cached=[])
+    return Air(d, [], [(cnt if is_send else d.neg(cnt), bus, msg)], 1, False, mats["common_main"], cached=mats["cached"])
+
+
 def self_interaction(width, log_height, bus):
     """SelfInteractionAir + SelfInteractionChip (test_utils/dummy_airs/interaction/self_interaction_air.rs:26-86): eight
     interactions on one bus whose messages are the whole local / next row (forward and reversed) with constant, row-sum and

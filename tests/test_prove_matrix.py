@@ -73,6 +73,27 @@ CPU_ONLY_CASES = [
 ]
 
 
+def cached_interaction(last_field):
+    """interaction_cached_trace_neg (backend-tests/src/lib.rs:1020-1071): a sender without partition and a receiver whose
+    message fields live in a cached main; with [889, 10] in the receiver's seventh row (the reference's data) the tables do not
+    balance, with [889, 4] they do."""
+    def make(rng):
+        recv = A.dummy_interaction_chip([1, 3, 4, 2, 0, 545, 1, 0],
+                                        [[5, 1], [4, 2], [4, 2], [5, 1], [123, 3], [889, 4], last_field, [456, 5]], False, 0, partition=True)
+        send = A.dummy_interaction_chip([0, 7, 3, 546], [[1, 1], [4, 2], [5, 1], [889, 4]], True, 0)
+        return [recv, send]
+    return make
+
+
+CPU_ONLY_CASES.append(("interaction_cached_trace_balanced", 2, 3, cached_interaction([889, 4]), ()))
+
+
+def test_oracle_rejects_the_reference_unbalanced_cached_interaction(oracle):
+    P, airs, is_required = make_case(("interaction_cached_trace_neg", 2, 3, cached_interaction([889, 10]), ()))
+    with pytest.raises(ValueError):
+        oracle_prove(oracle, P, airs, is_required, oracle.to_mont(np.arange(40, 48)))
+
+
 def params_for(l_skip, n_stack):
     m = l_skip + n_stack
     k = 2 if m >= 4 else 1
